@@ -1,0 +1,174 @@
+"""Pin the CPU oracle (oracle/np_oracle.py) against fixtures produced by the unmodified reference.
+
+The reference has no tests of its own, so `tests/golden/*.npz` -- outputs of the reference's functions on
+seeded inputs (tests/golden/make_golden.py) -- are the golden vectors.  Bit-exact for index / layout /
+elementwise work; 1e-6 relative for reductions (the reference reduces in fp32, the oracle in fp64).
+"""
+import numpy as np
+import pytest
+
+from oracle import np_oracle as O
+
+REL = 1e-6
+
+UPSAMPLE_CASES = ['tiny_f32', 'odd_f32', 'lab600_f32', 'wide609_f32', 'd1_f32', 'f64', 'i64', 'f16', 'u8',
+                  'emptyrow', 'allzero', 'int32dur']
+
+
+@pytest.mark.parametrize('case', UPSAMPLE_CASES)
+def test_upsample_bit_exact(golden, case):
+    g = golden('upsample')
+    x, dur, want = g['ups_%s_x' % case], g['ups_%s_dur' % case], g['ups_%s_out' % case]
+    got = O.upsample_to_repetitions(x, dur[:, :, None])
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert np.array_equal(got, want)
+    # The same layout through the explicit index map (-1 -> zero row).
+    index_map = O.upsample_index_map(dur)
+    padded = np.concatenate([x, np.zeros_like(x[:, :1])], axis=1)
+    via_map = padded[np.arange(x.shape[0])[:, None], index_map]
+    assert np.array_equal(via_map, want)
+
+
+def test_upsample_scan_outputs(golden):
+    g = golden('upsample')
+    dur = g['ups_odd_f32_dur']
+    ends, n_frames, max_frames = O.dur_scan(dur)
+    assert np.array_equal(n_frames, dur.sum(axis=1))
+    assert max_frames == g['ups_odd_f32_out'].shape[1]
+    assert np.array_equal(ends, np.cumsum(dur, axis=1))
+
+
+def test_upsample_errors():
+    x = np.zeros((2, 3, 4), np.float32)
+    with pytest.raises(TypeError):
+        O.upsample_to_repetitions(x, np.ones((2, 3, 1), np.float32))
+    with pytest.raises(ValueError):
+        O.upsample_to_repetitions(x, np.array([[1, -1, 2], [0, 0, 0]]))
+    with pytest.raises(IndexError):
+        O.upsample_to_repetitions(np.zeros((2, 3), np.float32), np.ones((2, 3), np.int64))
+
+
+def test_upsample_backward(golden):
+    g = golden('upsample')
+    got = O.upsample_backward(g['upsbwd_grad_out'], g['upsbwd_dur'])
+    np.testing.assert_allclose(got, g['upsbwd_grad_x'], rtol=REL, atol=1e-6)
+
+
+def test_sequence_mask(golden):
+    g = golden('sequence_mask')
+    seq_len = g['mask_seq_len']
+    assert np.array_equal(O.sequence_mask(seq_len), g['mask_default'])
+    assert O.sequence_mask(seq_len).dtype == np.uint8
+    assert np.array_equal(O.sequence_mask(seq_len, 7, np.float32), g['mask_len7_f32'])
+    assert np.array_equal(O.sequence_mask(seq_len, 4), g['mask_len4_u8'])
+
+
+@pytest.mark.parametrize('case', ['btd', 'td', 'btd187', 'sd'])
+def test_normalisers_bit_exact(golden, case):
+    g = golden('normalise')
+    x = g['norm_%s_x' % case]
+    mean, std = g['norm_%s_mean' % case], g['norm_%s_std' % case]
+    mmin, mmax = g['norm_%s_mmin' % case], g['norm_%s_mmax' % case]
+    for fn, args, key in [(O.normalise_mvn, (mean, std), 'mvn'), (O.denormalise_mvn, (mean, std), 'demvn'),
+                          (O.normalise_minmax, (mmin, mmax), 'minmax'),
+                          (O.denormalise_minmax, (mmin, mmax), 'deminmax')]:
+        got = fn(x, *args)
+        want = g['norm_%s_%s' % (case, key)]
+        assert got.dtype == np.float32
+        assert np.array_equal(got, want), key
+
+
+def test_fused_normalise_upsample_bit_exact(golden):
+    g = golden('normalise')
+    got = O.normalise_upsample(g['fused_x'], g['fused_dur'], 'minmax', g['fused_mmin'], g['fused_mmax'])
+    assert np.array_equal(got, g['fused_minmax_out'])
+    got = O.normalise_upsample(g['fused_x'], g['fused_dur'], 'mvn', g['fused_mean'], g['fused_std'])
+    assert np.array_equal(got, g['fused_mvn_out'])
+
+
+@pytest.mark.parametrize('case', ['small', 'wide', 'd1'])
+@pytest.mark.parametrize('masked', [True, False])
+def test_losses(golden, case, masked):
+    g = golden('losses')
+    seq_len = g['loss_%s_seq_len' % case] if masked else None
+    tag = 'masked' if masked else 'full'
+    pred, tgt = g['loss_%s_pred' % case], g['loss_%s_tgt' % case]
+    want = g['loss_%s_mse_%s' % (case, tag)]
+    assert O.masked_loss(pred, tgt, seq_len, 'mse') == pytest.approx(float(want), rel=REL)
+    np.testing.assert_allclose(O.masked_loss_grad(pred, tgt, seq_len, 'mse'),
+                               g['loss_%s_mse_%s_grad' % (case, tag)], rtol=2e-6, atol=1e-9)
+    prob, label = g['loss_%s_prob' % case], g['loss_%s_label' % case]
+    want = g['loss_%s_bce_%s' % (case, tag)]
+    assert O.masked_loss(prob, label, seq_len, 'bce') == pytest.approx(float(want), rel=REL)
+    np.testing.assert_allclose(O.masked_loss_grad(prob, label, seq_len, 'bce'),
+                               g['loss_%s_bce_%s_grad' % (case, tag)], rtol=2e-6, atol=1e-9)
+
+
+def test_loss_zero_length_is_nan(golden):
+    assert np.isnan(golden('losses')['loss_zero_len'])
+    pred = np.ones((2, 4, 3), np.float32)
+    assert np.isnan(O.masked_loss(pred, pred, np.array([0, 3]), 'mse'))
+    with pytest.raises(RuntimeError):
+        O.masked_loss(pred, pred, np.array([[1], [3]]), 'mse')
+
+
+def _metric_inputs(g, i):
+    keys = ['seq_len', 'tgt', 'pred', 'lf0_t', 'lf0_p', 'voiced', 'bits_t', 'bits_p']
+    return {k: g['met_b%d_%s' % (i, k)] for k in keys}
+
+
+METRICS = {
+    'mean': lambda b, s: O.mean_acc(b['tgt'], s),
+    'rmse': lambda b, s: O.rmse_acc(b['tgt'], b['pred'], s),
+    'mae': lambda b, s: O.mae_acc(b['tgt'], b['pred'], s),
+    'melcep': lambda b, s: O.melcep_acc(b['tgt'], b['pred'], s),
+    'distortion': lambda b, s: O.distortion_acc(b['tgt'], b['pred'], s),
+    'f0': lambda b, s: O.f0_acc(np.exp(b['lf0_t']), np.exp(b['lf0_p']), b['voiced'], s),
+    'lf0': lambda b, s: O.lf0_acc(b['lf0_t'], b['lf0_p'], b['voiced'], s),
+    'lf0_floatmask': lambda b, s: O.lf0_acc(b['lf0_t'], b['lf0_p'], b['voiced'].astype(np.float32), s),
+    'error': lambda b, s: O.error_acc(b['bits_t'], b['bits_p'], s),
+    'accuracy': lambda b, s: O.accuracy_acc(b['bits_t'], b['bits_p'], s),
+    'error_u8': lambda b, s: O.error_acc(b['bits_t'].astype(np.uint8), b['bits_p'].astype(np.uint8), s),
+    'vuvacc': lambda b, s: O.mean_acc((b['bits_t'] == b['bits_p']).astype(np.float32), s),
+}
+
+
+@pytest.mark.parametrize('name', sorted(METRICS))
+@pytest.mark.parametrize('masked', [True, False])
+def test_metric_accumulators(golden, name, masked):
+    g = golden('metrics')
+    total, count = 0., 0.
+    for i in range(2):
+        b = _metric_inputs(g, i)
+        s, c = METRICS[name](b, b['seq_len'] if masked else None)
+        total, count = total + s, count + c
+    key = 'met_%s_%s' % (name, 'masked' if masked else 'full')
+    assert count == float(g[key + '_count'])
+    assert total == pytest.approx(float(g[key + '_sum']), rel=REL)
+    if name in ('rmse', 'melcep', 'f0', 'lf0', 'lf0_floatmask'):
+        result = O.rmse_result(total, count)
+    elif name == 'distortion':
+        result = O.mean_result(total, count) * O.DISTORTION_DB_CONST
+    elif name in ('error', 'accuracy', 'error_u8'):
+        result = O.mean_result(total, count) * 100.
+    else:
+        result = O.mean_result(total, count)
+    assert result == pytest.approx(float(g[key + '_result']), rel=REL)
+
+
+def test_ema_bit_exact(golden):
+    g = golden('ema')
+    decay = float(g['ema_decay'])
+    for i in range(int(g['ema_n'])):
+        shadow = g['ema_shadow0_%d' % i].copy()
+        for step in range(3):
+            O.ema_update(shadow, g['ema_param%d_%d' % (step, i)], decay)
+            assert np.array_equal(shadow, g['ema_shadow%d_%d' % (step + 1, i)])
+
+
+@pytest.mark.parametrize('case', ['readme_l1', 'rnn_in', 'out187', 'out1'])
+def test_linear(golden, case):
+    g = golden('linear')
+    x, w, b = g['lin_%s_x' % case], g['lin_%s_w' % case], g['lin_%s_b' % case]
+    np.testing.assert_allclose(O.linear(x, w, b), g['lin_%s_y' % case], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(O.linear(x, w, b, 'sigmoid'), g['lin_%s_sig' % case], rtol=1e-5, atol=1e-6)
