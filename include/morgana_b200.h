@@ -1,0 +1,212 @@
+/* morgana_b200 -- C ABI of the B200-native (sm_100a) kernels for morgana's per-batch frame-rate feature path.
+ *
+ * The reference (ZackHodari/morgana) is pure Python/PyTorch and has no FFI: the "interface" each entry point
+ * replaces is a Python callable, cited as <file>:<lines> relative to the reference root.  INTEGRATION.md shows the
+ * ctypes binding and the monkey-patch a maintainer of the reference would add.
+ *
+ * Conventions (every entry point):
+ *   - plain C types only: raw DEVICE pointers, sizes, strides (in ELEMENTS unless a name ends in _bytes) and a
+ *     CUDA stream handle; no torch types.
+ *   - returns MG_OK (0) or a negative MG_ERR_* code; never throws; mg_last_error() gives a thread-local message.
+ *   - never allocates, never synchronises the stream, never touches host memory of the caller: all buffers,
+ *     including workspaces, are owned by the caller.  Launches go on the stream that is passed in.
+ *   - inputs are read-only; only the documented outputs are written (mg_ema_update_f32 updates `shadow` in place,
+ *     as the reference does: utils.py:436-448).
+ */
+#ifndef MORGANA_B200_H_
+#define MORGANA_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MG_ABI_VERSION 1
+
+#define MG_OK 0
+#define MG_ERR_INVALID_ARG (-1)
+#define MG_ERR_CUDA (-2)
+#define MG_ERR_UNSUPPORTED (-3)
+
+typedef void* mg_stream_t; /* cudaStream_t */
+
+int mg_abi_version(void);
+const char* mg_last_error(void);
+/* Number of SMs of the current device (grid sizing), or a negative error code. */
+int mg_sm_count(void);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K1  duration scan -- replaces `repeated_lens = sum(repeats, 1); max(repeated_lens).item()` and the per-utterance
+ *     np.repeat index construction of utils.upsample_to_repetitions (morgana/utils.py:198-199, 214-220).
+ *
+ * dur        (B, P) durations, int64 (dur_is_i32 = 0) or int32 (= 1); row stride dur_stride_b, item stride 1.
+ * ends       (B, P) int32 out: inclusive running sum per utterance; item p covers frames [ends[p-1], ends[p]).
+ * n_frames   (B,)   int64 out: sum_p dur[b, p] (what the reference calls repeated_lens).
+ * summary    int64[4] out: [0] max_b n_frames (the T of the output), [1] number of negative durations (the reference
+ *            raises ValueError for any, utils.py:220), [2] sum_b n_frames, [3] number of utterances whose total
+ *            exceeds INT32_MAX (unsupported).  The caller reads it back (32 bytes) to size the output.
+ */
+int mg_dur_scan(const void* dur, int dur_is_i32, int64_t dur_stride_b, int B, int P,
+                int32_t* ends, int64_t* n_frames, int64_t* summary, mg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K2  fused normalise + duration-driven expansion -- replaces utils.upsample_to_repetitions (utils.py:175-228) and,
+ *     with norm_mode != 0, its composition with data.normalise_mvn / normalise_minmax (data.py:533-534, 579-583).
+ *
+ *     out[b, t, :] = norm(x[b, p(b,t), :])  for t <  n_frames[b]   (p(b,t): the item whose interval holds t)
+ *     out[b, t, :] = 0                      for t >= n_frames[b]   (never norm(0): utils.py:206-207, 214)
+ *
+ * x          (B, P, D) fp32; strides x_stride_b / x_stride_p in elements, innermost contiguous.
+ * ends       (B, P) int32 from mg_dur_scan.
+ * norm_mode  MG_NORM_NONE | MG_NORM_MVN (p0 = mean, p1 = std_dev: (x - p0) / (p1 + 1e-8))
+ *                         | MG_NORM_MINMAX (p0 = mmin, p1 = mmax: (x - p0) / scale, scale = p1 - p0, 1 where |scale| <= 1e-8)
+ * p0, p1     (D,) fp32 when param_stride_b = 0, else (B, D) with that row stride (speaker-dependent, data.py:460-501).
+ * out        (B, T, D) fp32, contiguous.  T may exceed max n_frames (extra rows are zero) but not be smaller.
+ * path       MG_PATH_AUTO, or force MG_PATH_BULK (smem-staged rows + cp.async.bulk stores; needs D % 4 == 0 and
+ *            16-byte aligned `out`) / MG_PATH_DIRECT (register-staged vector stores; any D).
+ */
+#define MG_NORM_NONE 0
+#define MG_NORM_MVN 1
+#define MG_NORM_MINMAX 2
+#define MG_PATH_AUTO 0
+#define MG_PATH_BULK 1
+#define MG_PATH_DIRECT 2
+int mg_upsample_norm_f32(const float* x, int64_t x_stride_b, int64_t x_stride_p, const int32_t* ends,
+                         const float* p0, const float* p1, int64_t param_stride_b, int norm_mode,
+                         float* out, int B, int P, int D, int64_t T, int path, mg_stream_t stream);
+
+/* Dtype-agnostic expansion (the reference preserves any dtype): rows of row_bytes bytes are copied.
+ * Strides in BYTES.  out is (B, T, row_bytes) contiguous. */
+int mg_upsample_bytes(const void* x, int64_t x_stride_b_bytes, int64_t x_stride_p_bytes, const int32_t* ends,
+                      void* out, int B, int P, int64_t row_bytes, int64_t T, int path, mg_stream_t stream);
+
+/* Backward of K2 w.r.t. x -- replaces autograd's IndexBackward0 of utils.py:226 (an atomic index_put_) with a
+ * deterministic per-item segment sum:  grad_x[b, p, :] = (sum_{t in item p} grad_out[b, t, :]) / denom(norm).
+ * grad_out (B, T, D) contiguous; grad_x (B, P, D) contiguous; p0/p1/param_stride_b/norm_mode as in K2. */
+int mg_upsample_norm_bwd_f32(const float* grad_out, const int32_t* ends, const float* p0, const float* p1,
+                             int64_t param_stride_b, int norm_mode, float* grad_x,
+                             int B, int P, int D, int64_t T, mg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K3  standalone normalise / denormalise -- replaces data.normalise_mvn, denormalise_mvn, normalise_minmax,
+ *     denormalise_minmax on torch tensors (morgana/data.py:533-538, 579-590).
+ *
+ * x, out     (rows, D) fp32 contiguous (out may alias x).
+ * rows_per_param  0: p0/p1 are (D,) shared by all rows; > 0: row r uses parameter row r / rows_per_param of a
+ *            contiguous (n, D) table (speaker-dependent: rows_per_param = T).
+ * inverse    0: normalise; 1: denormalise (x * s + p0 as a multiply then an add, data.py:537-538, 586-590).
+ */
+int mg_normalise_f32(const float* x, const float* p0, const float* p1, int norm_mode, int inverse, float* out,
+                     int64_t rows, int D, int64_t rows_per_param, mg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K4 / K5  seq_len-masked one-pass reductions -- replace losses.sequence_loss -> mse / bce (morgana/losses.py:9-56)
+ *     and the accumulate() arithmetic of metrics.Mean / RMSE / MAE / Error / Accuracy / F0Distortion / LF0Distortion /
+ *     Distortion / MelCepDistortion (morgana/metrics.py:383-394, 492-495, 520-522, 547-549, 574-576, 597-609, 630-634,
+ *     657-665, 690-694), without materialising utils.sequence_mask (utils.py:115-144).
+ *
+ * Up to MG_MAX_TERMS terms are reduced in ONE launch; term i sees rows t < n_b = clamp(seq_len[b], 0, T) of utterance b
+ * (seq_len == NULL: every row).  For each term the kernel produces
+ *     sum   = sum_b S_b,  S_b = sum_{t < n_b} rowfn(a[b,t,:], b[b,t,:]) * m[b,t]
+ *     count = sum_b (sum_{t < n_b} m[b,t])           (frames, not frames x D: SURVEY.md Q2; m == NULL -> 1)
+ *             -- or T*B*D when seq_len == NULL and the kind is not mask-carrying, as Mean.accumulate does (numel)
+ *     loss  = (1 / (B * D)) * sum_b S_b / n_b        (losses.py:37-42; 0/0 -> nan as in the reference)
+ * and, when `grad` is non-NULL (loss kinds only), d loss / d a scaled by grad_scale * (*grad_scale_dev, if non-NULL),
+ * written over all T rows (zero in the padding).
+ *
+ * Reduction order is fixed by the launch geometry (per-thread -> warp shuffle -> CTA -> per-CTA slot -> last CTA sums
+ * the slots in index order), so results are bit-reproducible run to run; no floating-point atomics.
+ */
+#define MG_MAX_TERMS 12
+
+#define MG_RED_SQDIFF 0      /* (a - b)^2             mse loss; RMSE / MelCepDistortion (caller offsets the pointers) */
+#define MG_RED_ABSDIFF 1     /* |a - b|               L1 loss; MAE */
+#define MG_RED_BCE 2         /* -(b log a + (1-b) log(1-a)), logs clamped at -100 (ATen); a = probability, b = label */
+#define MG_RED_SUM 3         /* a                     Mean */
+#define MG_RED_ROOT_SQDIFF 4 /* sqrt(sum_d (a-b)^2)   Distortion: one value per frame */
+#define MG_RED_SQDIFF_EXP 5  /* (exp a - exp b)^2     LF0Distortion (with m = voiced) */
+#define MG_RED_XOR 6         /* a ^ b on uint8/bool   Error (exact integer sum) */
+#define MG_RED_AND 7         /* a & b on uint8/bool   Accuracy */
+#define MG_RED_EQ 8          /* (a == b) ? 1 : 0      V/UV accuracy as models/RNN_SPSS.py:127 builds it, fused */
+
+/* Fuse the `output_features['vuv'] > 0.5` of models/RNN_SPSS.py:122 into the reduction instead of a separate pass: */
+#define MG_FLAG_M_GT_HALF 1 /* the per-frame weight is (m > 0.5) ? 1 : 0 */
+#define MG_FLAG_A_GT_HALF 2 /* MG_RED_EQ compares (a > 0.5) with (b != 0) */
+#define MG_FLAG_IN_TOTAL 4  /* add grad_scale * loss of this term into the first record's weighted_loss_f32 */
+
+#define MG_DT_F32 0
+#define MG_DT_U8 1 /* uint8 or bool */
+
+struct mg_term_result;
+
+typedef struct mg_term {
+  const void* a; /* (B, T, D) view: element (b, t, d) at a + b*a_sb + t*a_st + d */
+  const void* b; /* second operand or NULL (MG_RED_SUM) */
+  const void* m; /* optional per-frame weight (B, T) -- F0Distortion's is_voiced; NULL = 1 */
+  float* grad;   /* optional (B, T, D) gradient w.r.t. a (loss kinds), strides g_sb / g_st */
+  const float* grad_scale_dev; /* optional device scalar multiplied into the gradient (upstream grad_output) */
+  struct mg_term_result* result; /* device record this term writes (or adds to, see `accumulate`) */
+  int64_t a_sb, a_st, b_sb, b_st, m_sb, m_st, g_sb, g_st;
+  int32_t D;
+  int32_t kind;    /* MG_RED_* */
+  int32_t ab_dtype; /* MG_DT_F32 (all float kinds) or MG_DT_U8 (XOR / AND / EQ / SUM) */
+  int32_t m_dtype;  /* MG_DT_F32 or MG_DT_U8 */
+  int32_t b_is_u8;  /* MG_RED_EQ only: b is uint8/bool while a is f32 (probability > 0.5 is NOT applied here) */
+  int32_t accumulate; /* 0: result = this batch; 1: result.sum / count / isum += this batch (streaming-metric state:
+                         `self.sum += ...; self.count += ...` of metrics.py:389-394 without leaving the device) */
+  float grad_scale; /* host-side factor of the gradient (e.g. 0.25 for loss / 4) */
+  int32_t flags;    /* MG_FLAG_* */
+} mg_term;
+
+/* Result record per term (device memory, 48 bytes, 16-byte aligned, written by the last CTA). */
+typedef struct mg_term_result {
+  double sum;
+  double count;
+  double loss;
+  int64_t isum;  /* exact integer sum for MG_DT_U8 operands */
+  float sum_f32; /* the same three values rounded once to fp32, for zero-copy views from the host framework */
+  float count_f32;
+  float loss_f32;
+  float weighted_loss_f32; /* record of term 0 only: sum of grad_scale * loss over the MG_FLAG_IN_TOTAL terms, i.e. the
+                              model's total loss `(mse + mse + mse + bce) / 4` (models/RNN_SPSS.py:131-139) in one launch */
+} mg_term_result;
+
+/* Bytes of workspace mg_masked_reduce needs for this geometry.  The workspace must be zero-filled ONCE when it is
+ * allocated; the kernel leaves it clean for the next launch.  One workspace per concurrently-used stream. */
+int64_t mg_masked_reduce_workspace_bytes(int n_terms, int B, int64_t T);
+
+int mg_masked_reduce(const mg_term* terms /* host array */, int n_terms, const int64_t* seq_len /* (B,) or NULL */,
+                     int B, int64_t T, void* workspace, int64_t workspace_bytes, mg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K6  multi-tensor EMA -- replaces utils.ExponentialMovingAverage._update_param / update_params (utils.py:443-456):
+ *     shadow[i] = shadow[i] - one_minus_decay * (shadow[i] - param[i]), two roundings then the subtract (bit-exact
+ *     with the reference's two ATen kernels; not the FMA / decay*s + (1-decay)*x form).
+ * shadow, param   HOST arrays of n_tensors DEVICE pointers; numel the element counts.  One launch per 64 tensors.
+ */
+int mg_ema_update_f32(float* const* shadow, const float* const* param, const int64_t* numel, int n_tensors,
+                      float one_minus_decay, mg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * K7  dense layer on the tcgen05 tensor cores -- replaces nn.Linear (+ nn.Sigmoid) of the example models
+ *     (README.rst:65-73; models/RNN_SPSS.py:33,38,41; models/f0_test_model.py:29,41,44):
+ *     y[M, N] = act(x[M, K] @ w[N, K]^T + bias[N]),  bf16 operands, fp32 accumulation in TMEM.
+ *
+ * x          (M, K) bf16, row stride ldx (elements, multiple of 8); K multiple of 8.
+ * w          (N, K) bf16, row stride ldw (multiple of 8).
+ * y          (M, N) fp32 (y_is_bf16 = 0) or bf16 (= 1), row stride ldy.
+ * act        MG_ACT_NONE | MG_ACT_SIGMOID.
+ */
+#define MG_ACT_NONE 0
+#define MG_ACT_SIGMOID 1
+int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* y, int64_t ldy,
+                   int y_is_bf16, int M, int N, int K, int act, mg_stream_t stream);
+
+/* fp32 -> bf16 row conversion with K padding (feeds K7 from the fp32 frame-rate features; pads K to ld_out with 0). */
+int mg_cast_pad_bf16(const float* x, int64_t ldx, void* out, int64_t ld_out, int64_t rows, int K, mg_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MORGANA_B200_H_ */

@@ -1,0 +1,475 @@
+// K4 / K5 -- seq_len-masked losses (forward + optional backward) and streaming-metric accumulators in one pass.
+//
+// Replaces losses.sequence_loss -> mse / bce (reference morgana/losses.py:9-56: pointwise loss temp, sequence_mask
+// temp, masked-product temp, sum over time, divide, mean = 4 full passes forward and ~3 backward) and the accumulate()
+// arithmetic of metrics.Mean/RMSE/MAE/Error/Accuracy/F0Distortion/LF0Distortion/Distortion/MelCepDistortion
+// (morgana/metrics.py:383-394, 492-495, 520-522, 547-549, 574-576, 597-609, 630-634, 657-665, 690-694), each of which
+// builds a (B, T, 1) mask, a masked temp, two reductions and an .item() sync.
+//
+// The mask is never materialised: CTA (chunk, b, term) touches only rows t < n_b of utterance b, so padded input is
+// not read at all.  Algorithmic HBM bytes: 8*D*sum_b n_b per two-operand term (+ 4*D*B*T when a gradient is written).
+//
+// Determinism: thread partials (fp64) -> fixed shuffle tree -> fixed order over warps -> one slot per CTA -> the last
+// CTA to finish (integer ticket) combines slots in index order.  No floating-point atomics anywhere.
+#include <string.h>
+
+#include "mg_common.cuh"
+
+namespace {
+
+constexpr int kRedThreads = 256;
+constexpr int kRedWarps = kRedThreads / 32;
+constexpr int kMaxChunks = 64;          // chunks (CTAs) per utterance per term: bounds the workspace
+constexpr int64_t kTargetElems = 32768; // elements of one operand per CTA
+
+struct ReduceParams {
+  mg_term terms[MG_MAX_TERMS];
+  int rows_per_cta[MG_MAX_TERMS];
+  int n_chunks[MG_MAX_TERMS];
+  const int64_t* seq_len;
+  double2* partials;       // [term][b][kMaxChunks] (sum, count)
+  unsigned int* ticket;
+  int64_t T;
+  int n_terms;
+  int B;
+};
+
+// ---- pointwise functions ------------------------------------------------------------------------------------------
+template <int KIND>
+__device__ __forceinline__ float elem_fwd(float a, float b) {
+  if constexpr (KIND == MG_RED_SQDIFF) {
+    const float d = __fsub_rn(a, b);
+    return __fmul_rn(d, d);
+  } else if constexpr (KIND == MG_RED_ABSDIFF) {
+    return fabsf(__fsub_rn(a, b));
+  } else if constexpr (KIND == MG_RED_BCE) {
+    // ATen binary_cross_entropy: (y - 1) * max(log1p(-p), -100) - y * max(log(p), -100)
+    const float log_p = fmaxf(logf(a), -100.f);
+    const float log_1mp = fmaxf(log1pf(-a), -100.f);
+    return __fsub_rn(__fmul_rn(__fsub_rn(b, 1.f), log_1mp), __fmul_rn(b, log_p));
+  } else if constexpr (KIND == MG_RED_SUM) {
+    return a;
+  } else if constexpr (KIND == MG_RED_SQDIFF_EXP) {
+    const float d = __fsub_rn(expf(a), expf(b));   // full-precision expf, as torch.exp (metrics.py:631-632)
+    return __fmul_rn(d, d);
+  } else {  // MG_RED_ROOT_SQDIFF accumulates squared differences per frame; the root is taken by the caller
+    const float d = __fsub_rn(a, b);
+    return __fmul_rn(d, d);
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ float elem_bwd(float a, float b) {
+  if constexpr (KIND == MG_RED_SQDIFF) {
+    return __fmul_rn(2.f, __fsub_rn(a, b));
+  } else if constexpr (KIND == MG_RED_ABSDIFF) {
+    const float d = __fsub_rn(a, b);
+    return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+  } else {  // MG_RED_BCE: ATen binary_cross_entropy_backward, (p - y) / max((1 - p) * p, 1e-12)
+    return __fdiv_rn(__fsub_rn(a, b), fmaxf(__fmul_rn(__fsub_rn(1.f, a), a), 1e-12f));
+  }
+}
+
+__host__ __device__ constexpr bool kind_has_b(int kind) { return kind != MG_RED_SUM; }
+
+// ---- contiguous rows: flat 16-byte stream with an alignment peel -----------------------------------------------------
+template <int KIND, bool GRAD>
+__device__ __forceinline__ void run_flat(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ g,
+                                         int64_t n, float w, double& sum) {
+  constexpr bool HAS_B = kind_has_b(KIND);
+  const int tid = threadIdx.x;
+  const uintptr_t mis = reinterpret_cast<uintptr_t>(a) & 15;
+  const bool vec_ok = (!HAS_B || (reinterpret_cast<uintptr_t>(b) & 15) == mis) &&
+                      (!GRAD || (reinterpret_cast<uintptr_t>(g) & 15) == mis);
+  const int64_t head = vec_ok ? min(n, static_cast<int64_t>(((16 - mis) & 15) >> 2)) : n;
+
+  // scalar head (everything when the operands disagree on alignment)
+  {
+    int64_t i = tid;
+    for (; i + 3 * kRedThreads < head; i += 4 * kRedThreads) {
+      float av[4], bv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        av[j] = __ldcs(a + i + j * kRedThreads);
+        bv[j] = HAS_B ? __ldcs(b + i + j * kRedThreads) : 0.f;
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        sum += static_cast<double>(elem_fwd<KIND>(av[j], bv[j]));
+        if constexpr (GRAD) g[i + j * kRedThreads] = __fmul_rn(elem_bwd<KIND>(av[j], bv[j]), w);
+      }
+    }
+    for (; i < head; i += kRedThreads) {
+      const float av = __ldcs(a + i), bv = HAS_B ? __ldcs(b + i) : 0.f;
+      sum += static_cast<double>(elem_fwd<KIND>(av, bv));
+      if constexpr (GRAD) g[i] = __fmul_rn(elem_bwd<KIND>(av, bv), w);
+    }
+  }
+  if (!vec_ok) return;
+
+  const int64_t nvec = (n - head) >> 2;
+  const float4* a4 = reinterpret_cast<const float4*>(a + head);
+  const float4* b4 = reinterpret_cast<const float4*>(b + head);
+  float4* g4 = reinterpret_cast<float4*>(g + head);
+  auto one = [&](float4 av, float4 bv, int64_t i) {
+    // Per-vector partial in fp32 order x,y,z,w, folded into the fp64 thread accumulator.
+    const float f0 = elem_fwd<KIND>(av.x, bv.x), f1 = elem_fwd<KIND>(av.y, bv.y);
+    const float f2 = elem_fwd<KIND>(av.z, bv.z), f3 = elem_fwd<KIND>(av.w, bv.w);
+    sum += (static_cast<double>(f0) + static_cast<double>(f1)) + (static_cast<double>(f2) + static_cast<double>(f3));
+    if constexpr (GRAD) {
+      float4 gv;
+      gv.x = __fmul_rn(elem_bwd<KIND>(av.x, bv.x), w);
+      gv.y = __fmul_rn(elem_bwd<KIND>(av.y, bv.y), w);
+      gv.z = __fmul_rn(elem_bwd<KIND>(av.z, bv.z), w);
+      gv.w = __fmul_rn(elem_bwd<KIND>(av.w, bv.w), w);
+      g4[i] = gv;
+    }
+  };
+  int64_t i = tid;
+  for (; i + 3 * kRedThreads < nvec; i += 4 * kRedThreads) {
+    float4 av[4], bv[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      av[j] = __ldcs(a4 + i + j * kRedThreads);
+      bv[j] = HAS_B ? __ldcs(b4 + i + j * kRedThreads) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) one(av[j], bv[j], i + j * kRedThreads);
+  }
+  for (; i < nvec; i += kRedThreads) one(__ldcs(a4 + i), HAS_B ? __ldcs(b4 + i) : make_float4(0.f, 0.f, 0.f, 0.f), i);
+
+  for (int64_t k = head + (nvec << 2) + tid; k < n; k += kRedThreads) {
+    const float av = __ldcs(a + k), bv = HAS_B ? __ldcs(b + k) : 0.f;
+    sum += static_cast<double>(elem_fwd<KIND>(av, bv));
+    if constexpr (GRAD) g[k] = __fmul_rn(elem_bwd<KIND>(av, bv), w);
+  }
+}
+
+// ---- strided rows (column slices of a wider tensor): scalar, (row, col) advanced without division ---------------------
+template <int KIND, bool GRAD>
+__device__ __forceinline__ void run_strided(const float* __restrict__ a, int64_t a_st, const float* __restrict__ b,
+                                            int64_t b_st, float* __restrict__ g, int64_t g_st, int64_t n_rows, int D,
+                                            float w, double& sum) {
+  constexpr bool HAS_B = kind_has_b(KIND);
+  int64_t r = threadIdx.x / D;
+  int d = threadIdx.x % D;
+  const int64_t step_r = kRedThreads / D;
+  const int step_d = kRedThreads % D;
+  while (r < n_rows) {
+    const float av = __ldcs(a + r * a_st + d);
+    const float bv = HAS_B ? __ldcs(b + r * b_st + d) : 0.f;
+    sum += static_cast<double>(elem_fwd<KIND>(av, bv));
+    if constexpr (GRAD) g[r * g_st + d] = __fmul_rn(elem_bwd<KIND>(av, bv), w);
+    r += step_r;
+    d += step_d;
+    if (d >= D) { d -= D; ++r; }
+  }
+}
+
+// ---- one value per frame: Distortion's root, and every kind that carries a per-frame weight m ------------------------
+__device__ __forceinline__ float load_weight(const void* m, int m_dtype, int flags, int64_t idx) {
+  if (m_dtype == MG_DT_U8) return static_cast<float>(__ldg(static_cast<const unsigned char*>(m) + idx));
+  const float w = __ldg(static_cast<const float*>(m) + idx);
+  if (flags & MG_FLAG_M_GT_HALF) return w > 0.5f ? 1.f : 0.f;   // `vuv = output_features['vuv'] > 0.5`, RNN_SPSS.py:122
+  return w;
+}
+
+template <int KIND>
+__device__ __forceinline__ void run_per_frame(const float* __restrict__ a, int64_t a_st, const float* __restrict__ b,
+                                              int64_t b_st, const void* m, int64_t m_st, int m_dtype, int flags,
+                                              int64_t m_off, int64_t n_rows, int D, double& sum, double& cnt) {
+  constexpr bool HAS_B = kind_has_b(KIND);
+  for (int64_t r = threadIdx.x; r < n_rows; r += kRedThreads) {
+    const float weight = m ? load_weight(m, m_dtype, flags, m_off + r * m_st) : 1.f;
+    float acc = 0.f;   // the reference sums the feature axis in fp32 (metrics.py:661)
+    for (int d = 0; d < D; ++d) {
+      const float av = __ldg(a + r * a_st + d);
+      const float bv = HAS_B ? __ldg(b + r * b_st + d) : 0.f;
+      acc = __fadd_rn(acc, elem_fwd<KIND>(av, bv));
+    }
+    if constexpr (KIND == MG_RED_ROOT_SQDIFF) acc = sqrtf(acc);   // metrics.py:662
+    sum += static_cast<double>(__fmul_rn(acc, weight));
+    cnt += static_cast<double>(weight);
+  }
+}
+
+// ---- integer / comparison kinds on uint8 (bool) or float operands -----------------------------------------------------
+__device__ __forceinline__ float load_as_float(const void* p, bool is_u8, int64_t idx) {
+  if (is_u8) return static_cast<float>(__ldg(static_cast<const unsigned char*>(p) + idx));
+  return __ldg(static_cast<const float*>(p) + idx);
+}
+
+__device__ __forceinline__ void run_discrete(const mg_term& tm, int64_t a_off, int64_t b_off, int64_t n_rows,
+                                             double& sum) {
+  const int D = tm.D;
+  const bool a_u8 = tm.ab_dtype == MG_DT_U8;
+  const bool b_u8 = a_u8 || tm.b_is_u8;
+  int64_t r = threadIdx.x / D;
+  int d = threadIdx.x % D;
+  const int64_t step_r = kRedThreads / D;
+  const int step_d = kRedThreads % D;
+  long long acc = 0;
+  while (r < n_rows) {
+    const int64_t ia = a_off + r * tm.a_st + d, ib = b_off + r * tm.b_st + d;
+    if (tm.kind == MG_RED_EQ) {
+      float av = load_as_float(tm.a, a_u8, ia), bv = load_as_float(tm.b, b_u8, ib);
+      if (tm.flags & MG_FLAG_A_GT_HALF) { av = av > 0.5f ? 1.f : 0.f; bv = bv != 0.f ? 1.f : 0.f; }
+      acc += av == bv ? 1 : 0;
+    } else {
+      const unsigned av = __ldg(static_cast<const unsigned char*>(tm.a) + ia);
+      if (tm.kind == MG_RED_SUM) acc += av;
+      else {
+        const unsigned bv = __ldg(static_cast<const unsigned char*>(tm.b) + ib);
+        acc += (tm.kind == MG_RED_XOR) ? (av ^ bv) : (av & bv);
+      }
+    }
+    r += step_r;
+    d += step_d;
+    if (d >= D) { d -= D; ++r; }
+  }
+  sum += static_cast<double>(acc);   // exact: |acc| < 2^53
+}
+
+// Zero rows [row_begin, row_end) of the gradient (the padding of this chunk).
+__device__ __forceinline__ void zero_grad_rows(float* g, int64_t g_st, int D, int64_t row_begin, int64_t row_end) {
+  if (row_end <= row_begin) return;
+  if (g_st == D) {
+    float* z = g + row_begin * g_st;
+    const int64_t n = (row_end - row_begin) * D;
+    const int64_t head = min(n, static_cast<int64_t>(((16 - (reinterpret_cast<uintptr_t>(z) & 15)) & 15) >> 2));
+    for (int64_t i = threadIdx.x; i < head; i += kRedThreads) z[i] = 0.f;
+    const int64_t nvec = (n - head) >> 2;
+    float4* z4 = reinterpret_cast<float4*>(z + head);
+    for (int64_t i = threadIdx.x; i < nvec; i += kRedThreads) z4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int64_t i = head + (nvec << 2) + threadIdx.x; i < n; i += kRedThreads) z[i] = 0.f;
+  } else {
+    const int64_t n = (row_end - row_begin) * D;
+    for (int64_t i = threadIdx.x; i < n; i += kRedThreads) g[(row_begin + i / D) * g_st + (i % D)] = 0.f;
+  }
+}
+
+template <int KIND>
+__device__ __forceinline__ void run_float_term(const mg_term& tm, int b, int64_t r0, int64_t n_valid, int64_t r1,
+                                               float w, double& sum, double& cnt) {
+  const float* a = static_cast<const float*>(tm.a) + b * tm.a_sb + r0 * tm.a_st;
+  const float* bb = kind_has_b(KIND) ? static_cast<const float*>(tm.b) + b * tm.b_sb + r0 * tm.b_st : nullptr;
+  const int D = tm.D;
+  if (tm.m != nullptr || KIND == MG_RED_ROOT_SQDIFF) {
+    run_per_frame<KIND>(a, tm.a_st, bb, tm.b_st, tm.m, tm.m_st, tm.m_dtype, tm.flags, b * tm.m_sb + r0 * tm.m_st, n_valid, D, sum, cnt);
+    return;
+  }
+  constexpr bool CAN_GRAD = KIND == MG_RED_SQDIFF || KIND == MG_RED_ABSDIFF || KIND == MG_RED_BCE;
+  const bool contiguous = tm.a_st == D && (!kind_has_b(KIND) || tm.b_st == D);
+  if constexpr (CAN_GRAD) {
+    if (tm.grad != nullptr) {
+      float* g = tm.grad + b * tm.g_sb + r0 * tm.g_st;
+      if (contiguous && tm.g_st == D) run_flat<KIND, true>(a, bb, g, n_valid * D, w, sum);
+      else run_strided<KIND, true>(a, tm.a_st, bb, tm.b_st, g, tm.g_st, n_valid, D, w, sum);
+      zero_grad_rows(g, tm.g_st, D, n_valid, r1 - r0);
+      return;
+    }
+  }
+  if (contiguous) run_flat<KIND, false>(a, bb, nullptr, n_valid * D, 0.f, sum);
+  else run_strided<KIND, false>(a, tm.a_st, bb, tm.b_st, nullptr, 0, n_valid, D, 0.f, sum);
+}
+
+__device__ __forceinline__ int64_t valid_frames(const int64_t* seq_len, int b, int64_t T) {
+  if (seq_len == nullptr) return T;
+  const int64_t n = __ldg(seq_len + b);
+  return n < 0 ? 0 : (n > T ? T : n);   // mask = arange(T) < seq_len  (utils.py:140-142)
+}
+
+__global__ void __launch_bounds__(kRedThreads)
+masked_reduce_kernel(const __grid_constant__ ReduceParams prm) {
+  __shared__ double s_a[kRedWarps], s_b[kRedWarps], s_c[kRedWarps];
+  __shared__ bool s_is_last;
+
+  const int term_idx = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
+  const mg_term& tm = prm.terms[term_idx];
+  const int64_t T = prm.T;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (chunk < prm.n_chunks[term_idx]) {
+    const int64_t n_b = valid_frames(prm.seq_len, b, T);
+    const int64_t R = prm.rows_per_cta[term_idx];
+    const int64_t r0 = chunk * R;
+    const int64_t r1 = min(r0 + R, T);
+    const int64_t n_valid = max(static_cast<int64_t>(0), min(r1, n_b) - r0);   // valid rows of this chunk
+    double sum = 0., cnt = 0.;
+
+    float w = 0.f;
+    if (tm.grad != nullptr) {
+      double scale = static_cast<double>(tm.grad_scale);
+      if (tm.grad_scale_dev != nullptr) scale *= static_cast<double>(__ldg(tm.grad_scale_dev));
+      w = static_cast<float>(scale / (static_cast<double>(n_b) * prm.B * tm.D));
+    }
+
+    if (n_valid > 0 || tm.grad != nullptr) {
+      if (tm.ab_dtype == MG_DT_U8 || tm.kind == MG_RED_EQ) {
+        run_discrete(tm, b * tm.a_sb + r0 * tm.a_st, b * tm.b_sb + r0 * tm.b_st, n_valid, sum);
+      } else {
+        switch (tm.kind) {
+          case MG_RED_SQDIFF: run_float_term<MG_RED_SQDIFF>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
+          case MG_RED_ABSDIFF: run_float_term<MG_RED_ABSDIFF>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
+          case MG_RED_BCE: run_float_term<MG_RED_BCE>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
+          case MG_RED_SUM: run_float_term<MG_RED_SUM>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
+          case MG_RED_ROOT_SQDIFF: run_float_term<MG_RED_ROOT_SQDIFF>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
+          default: run_float_term<MG_RED_SQDIFF_EXP>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
+        }
+      }
+    }
+
+    if (n_valid > 0) {
+      sum = mg_warp_sum(sum);
+      cnt = mg_warp_sum(cnt);
+      if (lane == 0) { s_a[warp] = sum; s_b[warp] = cnt; }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double s = 0., c = 0.;
+#pragma unroll
+        for (int i = 0; i < kRedWarps; ++i) { s += s_a[i]; c += s_b[i]; }
+        prm.partials[(static_cast<int64_t>(term_idx) * prm.B + b) * kMaxChunks + chunk] = make_double2(s, c);
+      }
+    }
+  }
+
+  // ---- ticket: the last CTA of the grid combines all slots in index order --------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+    s_is_last = atomicAdd(prm.ticket, 1u) == total - 1;
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  __threadfence();
+
+  double weighted_total = 0.;   // meaningful in thread 0 only
+  for (int t = 0; t < prm.n_terms; ++t) {
+    const mg_term& tt = prm.terms[t];
+    const int64_t R = prm.rows_per_cta[t];
+    const bool discrete = tt.ab_dtype == MG_DT_U8 || tt.kind == MG_RED_EQ;
+    const bool counts_weights = !discrete && tt.m != nullptr;
+    const bool per_frame = !discrete && (tt.m != nullptr || tt.kind == MG_RED_ROOT_SQDIFF);
+    double sum_acc = 0., cnt_acc = 0., loss_acc = 0.;
+    for (int bb = threadIdx.x; bb < prm.B; bb += kRedThreads) {
+      const int64_t n_b = valid_frames(prm.seq_len, bb, T);
+      const int64_t used = min(static_cast<int64_t>(prm.n_chunks[t]), (n_b + R - 1) / R);
+      const double2* slot = prm.partials + (static_cast<int64_t>(t) * prm.B + bb) * kMaxChunks;
+      double s = 0., c = 0.;
+      for (int64_t k = 0; k < used; ++k) {
+        const double2 v = __ldcg(slot + k);
+        s += v.x;
+        c += v.y;
+      }
+      sum_acc += s;
+      loss_acc += s / static_cast<double>(n_b);   // losses.py:39 (0/0 -> nan for an empty utterance, as the reference)
+      if (counts_weights) cnt_acc += c;
+      else if (prm.seq_len != nullptr) cnt_acc += static_cast<double>(n_b);            // frames (metrics.py:393-394)
+      else cnt_acc += static_cast<double>(T) * (per_frame ? 1. : static_cast<double>(tt.D));  // numel (metrics.py:390)
+    }
+    sum_acc = mg_warp_sum(sum_acc);
+    cnt_acc = mg_warp_sum(cnt_acc);
+    loss_acc = mg_warp_sum(loss_acc);
+    __syncthreads();
+    if (lane == 0) { s_a[warp] = sum_acc; s_b[warp] = cnt_acc; s_c[warp] = loss_acc; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      double s = 0., c = 0., l = 0.;
+#pragma unroll
+      for (int i = 0; i < kRedWarps; ++i) { s += s_a[i]; c += s_b[i]; l += s_c[i]; }
+      l /= static_cast<double>(prm.B) * static_cast<double>(tt.D);   // torch.mean over (B, D), losses.py:42
+      mg_term_result res;
+      if (tt.accumulate) {   // running state of a streaming metric: self.sum += ..., self.count += ...
+        const mg_term_result old = *tt.result;
+        s += old.sum;
+        c += old.count;
+      }
+      res.sum = s;
+      res.count = c;
+      res.loss = l;
+      res.isum = static_cast<int64_t>(s);
+      res.sum_f32 = static_cast<float>(s);
+      res.count_f32 = static_cast<float>(c);
+      res.loss_f32 = static_cast<float>(l);
+      res.weighted_loss_f32 = 0.f;
+      *tt.result = res;
+      if (tt.flags & MG_FLAG_IN_TOTAL) weighted_total += static_cast<double>(tt.grad_scale) * l;
+    }
+  }
+  if (threadIdx.x == 0) prm.terms[0].result->weighted_loss_f32 = static_cast<float>(weighted_total);
+  if (threadIdx.x == 0) *prm.ticket = 0u;   // leave the workspace clean for the next launch
+}
+
+int rows_per_cta_for(int D, int B, int64_t T, int sms) {
+  int64_t rows = kTargetElems / (D > 0 ? D : 1);
+  if (rows < 16) rows = 16;
+  if (rows > T) rows = T;
+  // Small batches: split further so the grid covers the machine a few times over.
+  while (rows > 16 && static_cast<int64_t>(B) * ((T + rows - 1) / rows) < 4 * static_cast<int64_t>(sms)) rows = (rows + 1) / 2;
+  const int64_t min_rows = (T + kMaxChunks - 1) / kMaxChunks;
+  if (rows < min_rows) rows = min_rows;
+  if (rows < 1) rows = 1;
+  return static_cast<int>(rows);
+}
+
+}  // namespace
+
+extern "C" int64_t mg_masked_reduce_workspace_bytes(int n_terms, int B, int64_t T) {
+  (void)T;
+  if (n_terms < 0 || B < 0) return MG_ERR_INVALID_ARG;
+  return 256 + static_cast<int64_t>(n_terms) * B * kMaxChunks * static_cast<int64_t>(sizeof(double2));
+}
+
+extern "C" int mg_masked_reduce(const mg_term* terms, int n_terms, const int64_t* seq_len, int B, int64_t T,
+                                void* workspace, int64_t workspace_bytes, mg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MG_REQUIRE(n_terms >= 1 && n_terms <= MG_MAX_TERMS, "mg_masked_reduce: n_terms=%d outside [1, %d]", n_terms, MG_MAX_TERMS);
+  MG_REQUIRE(B >= 1 && B <= 65535, "mg_masked_reduce: B=%d outside [1, 65535]", B);
+  MG_REQUIRE(T >= 0 && T < (int64_t(1) << 31), "mg_masked_reduce: bad T");
+  MG_REQUIRE(terms != nullptr && workspace != nullptr, "mg_masked_reduce: NULL buffer");
+  MG_REQUIRE(workspace_bytes >= mg_masked_reduce_workspace_bytes(n_terms, B, T), "mg_masked_reduce: workspace too small");
+  MG_REQUIRE(mg_aligned(workspace, 16), "mg_masked_reduce: workspace must be 16-byte aligned");
+
+  ReduceParams prm;
+  memset(&prm, 0, sizeof(prm));
+  const int sms = mg_cached_sm_count();
+  int max_chunks = 1;
+  for (int i = 0; i < n_terms; ++i) {
+    const mg_term& tm = terms[i];
+    MG_REQUIRE(tm.D >= 1, "mg_masked_reduce: term %d has D=%d", i, tm.D);
+    MG_REQUIRE(tm.kind >= MG_RED_SQDIFF && tm.kind <= MG_RED_EQ, "mg_masked_reduce: term %d has unknown kind %d", i, tm.kind);
+    MG_REQUIRE(tm.a != nullptr || T == 0, "mg_masked_reduce: term %d has a NULL operand", i);
+    MG_REQUIRE(tm.result != nullptr && mg_aligned(tm.result, 16), "mg_masked_reduce: term %d needs a 16-byte aligned result record", i);
+    const bool discrete = tm.ab_dtype == MG_DT_U8 || tm.kind == MG_RED_EQ;
+    if (discrete) {
+      MG_REQUIRE(tm.kind == MG_RED_XOR || tm.kind == MG_RED_AND || tm.kind == MG_RED_SUM || tm.kind == MG_RED_EQ,
+                 "mg_masked_reduce: term %d: kind %d is not defined for uint8 operands", i, tm.kind);
+      MG_REQUIRE(tm.m == nullptr && tm.grad == nullptr, "mg_masked_reduce: term %d: uint8 kinds take no weight / gradient", i);
+    } else {
+      MG_REQUIRE(tm.kind != MG_RED_XOR && tm.kind != MG_RED_AND, "mg_masked_reduce: term %d: XOR / AND need uint8 operands", i);
+    }
+    MG_REQUIRE(tm.kind == MG_RED_SUM || tm.b != nullptr || T == 0, "mg_masked_reduce: term %d needs a second operand", i);
+    if (tm.grad != nullptr) {
+      MG_REQUIRE(tm.kind == MG_RED_SQDIFF || tm.kind == MG_RED_ABSDIFF || tm.kind == MG_RED_BCE,
+                 "mg_masked_reduce: term %d: kind %d has no gradient", i, tm.kind);
+      MG_REQUIRE(tm.m == nullptr, "mg_masked_reduce: term %d: weighted terms have no gradient", i);
+    }
+    prm.terms[i] = tm;
+    const int rows = rows_per_cta_for(tm.D, B, T, sms);
+    prm.rows_per_cta[i] = rows;
+    prm.n_chunks[i] = T > 0 ? static_cast<int>((T + rows - 1) / rows) : 1;
+    if (prm.n_chunks[i] > max_chunks) max_chunks = prm.n_chunks[i];
+  }
+  prm.seq_len = seq_len;
+  prm.ticket = static_cast<unsigned int*>(workspace);
+  prm.partials = reinterpret_cast<double2*>(static_cast<unsigned char*>(workspace) + 256);
+  prm.T = T;
+  prm.n_terms = n_terms;
+  prm.B = B;
+
+  dim3 grid(static_cast<unsigned>(max_chunks), static_cast<unsigned>(B), static_cast<unsigned>(n_terms));
+  masked_reduce_kernel<<<grid, kRedThreads, 0, stream>>>(prm);
+  MG_LAUNCH_OK();
+  return MG_OK;
+}

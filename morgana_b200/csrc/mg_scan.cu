@@ -1,0 +1,76 @@
+// K1 -- per-utterance inclusive scan of durations (+ max / total / validity summary).
+//
+// Replaces `repeated_lens = sum(repeats, 1)`, `max(repeated_lens).item()` and the host-side np.repeat index build of
+// utils.upsample_to_repetitions (reference morgana/utils.py:198-199, 214-222).  One warp per utterance; lanes take
+// 32 consecutive items at a time, a shuffle scan plus a running carry gives the inclusive sums.  HBM traffic is
+// 8*B*P bytes in + 4*B*P out -- negligible next to K2; the kernel exists to keep the index build on the device.
+#include "mg_common.cuh"
+
+namespace {
+
+constexpr int kScanWarpsPerCta = 8;
+
+template <typename DurT>
+__global__ void __launch_bounds__(kScanWarpsPerCta * 32)
+dur_scan_kernel(const DurT* __restrict__ dur, int64_t dur_stride_b, int B, int P, int32_t* __restrict__ ends,
+                int64_t* __restrict__ n_frames, unsigned long long* __restrict__ summary) {
+  const int lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kScanWarpsPerCta + (threadIdx.x >> 5);
+  if (b >= B) return;
+  const DurT* row = dur + static_cast<int64_t>(b) * dur_stride_b;
+  int32_t* ends_row = ends + static_cast<int64_t>(b) * P;
+
+  long long carry = 0;
+  int negatives = 0;
+  for (int p0 = 0; p0 < P; p0 += 32) {
+    const int p = p0 + lane;
+    long long d = (p < P) ? static_cast<long long>(row[p]) : 0;
+    if (d < 0) {  // counted and treated as 0 so the scan stays monotone; the host raises ValueError
+      negatives += 1;
+      d = 0;
+    }
+    long long s = d;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const long long up = __shfl_up_sync(MG_FULL_MASK, s, o);
+      if (lane >= o) s += up;
+    }
+    s += carry;
+    if (p < P) ends_row[p] = static_cast<int32_t>(s > 2147483647LL ? 2147483647LL : s);
+    carry = __shfl_sync(MG_FULL_MASK, s, 31);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) negatives += __shfl_xor_sync(MG_FULL_MASK, negatives, o);
+
+  if (lane == 0) {
+    n_frames[b] = carry;
+    // Integer atomics: exact and order-independent.
+    atomicMax(summary + 0, static_cast<unsigned long long>(carry));
+    if (negatives) atomicAdd(summary + 1, static_cast<unsigned long long>(negatives));
+    atomicAdd(summary + 2, static_cast<unsigned long long>(carry));
+    if (carry > 2147483647LL) atomicAdd(summary + 3, 1ull);
+  }
+}
+
+}  // namespace
+
+extern "C" int mg_dur_scan(const void* dur, int dur_is_i32, int64_t dur_stride_b, int B, int P, int32_t* ends,
+                           int64_t* n_frames, int64_t* summary, mg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MG_REQUIRE(B >= 0 && P >= 0, "mg_dur_scan: negative shape (B=%d, P=%d)", B, P);
+  MG_REQUIRE(summary != nullptr, "mg_dur_scan: summary is NULL");
+  MG_CUDA_OK(cudaMemsetAsync(summary, 0, 4 * sizeof(int64_t), stream));
+  if (B == 0) return MG_OK;
+  MG_REQUIRE(n_frames != nullptr && (P == 0 || (dur != nullptr && ends != nullptr)), "mg_dur_scan: NULL buffer");
+  const int grid = (B + kScanWarpsPerCta - 1) / kScanWarpsPerCta;
+  auto* summary_u = reinterpret_cast<unsigned long long*>(summary);
+  if (dur_is_i32) {
+    dur_scan_kernel<int32_t><<<grid, kScanWarpsPerCta * 32, 0, stream>>>(static_cast<const int32_t*>(dur), dur_stride_b,
+                                                                        B, P, ends, n_frames, summary_u);
+  } else {
+    dur_scan_kernel<long long><<<grid, kScanWarpsPerCta * 32, 0, stream>>>(static_cast<const long long*>(dur),
+                                                                          dur_stride_b, B, P, ends, n_frames, summary_u);
+  }
+  MG_LAUNCH_OK();
+  return MG_OK;
+}

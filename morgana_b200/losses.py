@@ -1,0 +1,22 @@
+"""Drop-in counterparts of the reference's masked sequence losses (``morgana/losses.py:9-56``).
+
+``mse(predictions, targets, seq_len=None)`` and ``bce(...)`` keep the reference's signature and semantics --
+``mean over (batch, feature) of [ sum over valid frames / number of valid frames ]`` -- and return a 0-dim float32 tensor
+that supports ``.backward()``.  ``l1`` is the same wrapper around the absolute error.
+"""
+from morgana_b200 import ops
+
+
+def mse(predictions, targets, seq_len=None):
+    """Masked mean-squared error (morgana/losses.py:49-51)."""
+    return ops.masked_loss(predictions, targets, seq_len, 'mse')
+
+
+def bce(predictions, targets, seq_len=None):
+    """Masked binary cross-entropy on probabilities, logs clamped at -100 (morgana/losses.py:54-56)."""
+    return ops.masked_loss(predictions, targets, seq_len, 'bce')
+
+
+def l1(predictions, targets, seq_len=None):
+    """Masked mean-absolute error: ``sequence_loss`` applied to ``F.l1_loss(reduction='none')``."""
+    return ops.masked_loss(predictions, targets, seq_len, 'l1')

@@ -1,0 +1,475 @@
+"""Torch-facing layer over the C ABI: checks tensors, allocates outputs, passes raw device pointers + the current stream.
+
+PyTorch is plumbing here (device memory, streams, autograd bookkeeping); every byte of arithmetic on the path is done
+by the kernels in ``csrc/``.  There is no CPU or eager fallback: non-CUDA tensors raise.
+"""
+import ctypes
+
+import torch
+
+from morgana_b200 import _lib
+from morgana_b200._lib import lib, check, Term
+
+_NORM_MODES = {None: _lib.NORM_NONE, 'none': _lib.NORM_NONE, 'mvn': _lib.NORM_MVN, 'minmax': _lib.NORM_MINMAX}
+_PATHS = {'auto': _lib.PATH_AUTO, 'bulk': _lib.PATH_BULK, 'direct': _lib.PATH_DIRECT}
+_INT_DTYPES = (torch.int64, torch.int32, torch.int16, torch.int8, torch.uint8)
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(tensor, what):
+    if not isinstance(tensor, torch.Tensor):
+        raise TypeError('{} must be a torch.Tensor, got {}'.format(what, type(tensor).__name__))
+    if not tensor.is_cuda:
+        raise RuntimeError('morgana_b200 has no CPU path: {} is on {} (move it to a CUDA device, or use the '
+                           'unpatched reference for CPU runs)'.format(what, tensor.device))
+
+
+class _device_of(object):
+    """Make `tensor`'s device current for the duration of a launch (no-op when it already is)."""
+    def __init__(self, tensor):
+        self.idx = tensor.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and self.idx != cur:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+
+
+def _ptr(tensor):
+    return tensor.data_ptr() if tensor is not None else None
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K1 + K2: duration scan and fused normalise + expansion
+# ----------------------------------------------------------------------------------------------------------------------
+
+def _prepare_repeats(repeats, batch_size):
+    _require_cuda(repeats, 'repeats')
+    if repeats.dtype.is_floating_point or repeats.dtype == torch.bool or repeats.dtype.is_complex:
+        # The reference fails with TypeError for non-integer repeats (morgana/utils.py:211).
+        raise TypeError('repeats must be an integer tensor, got {}'.format(repeats.dtype))
+    repeats = repeats.reshape(batch_size, -1)
+    if repeats.dtype not in (torch.int64, torch.int32):
+        repeats = repeats.to(torch.int64)
+    if repeats.shape[1] > 0 and repeats.stride(1) != 1:
+        repeats = repeats.contiguous()
+    return repeats
+
+
+def dur_scan(repeats):
+    """K1.  Returns ``(ends int32 (B, P), n_frames int64 (B,), summary int64 (4,))``, all on the device."""
+    repeats = _prepare_repeats(repeats, repeats.shape[0])
+    B, P = repeats.shape
+    dev = repeats.device
+    ends = torch.empty((B, P), dtype=torch.int32, device=dev)
+    n_frames = torch.empty((B,), dtype=torch.int64, device=dev)
+    summary = torch.empty((4,), dtype=torch.int64, device=dev)
+    with _device_of(repeats):
+        check(lib.mg_dur_scan(_ptr(repeats), int(repeats.dtype == torch.int32), repeats.stride(0) if B else 0, B, P,
+                              _ptr(ends), _ptr(n_frames), _ptr(summary), _stream()), 'mg_dur_scan')
+    return ends, n_frames, summary
+
+
+def _norm_args(norm, feat_dim, batch_size, device):
+    """-> (mode, p0, p1, param_stride_b).  `norm` is None or (kind, p0, p1) with (D,) or (B, D) fp32 parameters."""
+    if norm is None:
+        return _lib.NORM_NONE, None, None, 0
+    kind, p0, p1 = norm
+    mode = _NORM_MODES[kind]
+    if mode == _lib.NORM_NONE:
+        return mode, None, None, 0
+    for name, p in (('p0', p0), ('p1', p1)):
+        _require_cuda(p, 'normaliser parameter ' + name)
+        if p.dtype != torch.float32:
+            raise TypeError('normaliser parameters must be float32, got {}'.format(p.dtype))
+        if p.requires_grad:
+            raise NotImplementedError('gradients w.r.t. normaliser parameters are not provided')
+    if p0.shape != p1.shape or p0.shape[-1] != feat_dim or p0.dim() not in (1, 2):
+        raise ValueError('normaliser parameters must both be (D,) or (B, D) with D={}; got {} and {}'.format(
+            feat_dim, tuple(p0.shape), tuple(p1.shape)))
+    p0, p1 = p0.contiguous(), p1.contiguous()
+    if p0.dim() == 2:
+        if p0.shape[0] != batch_size:
+            raise ValueError('per-utterance parameters need one row per batch item')
+        return mode, p0, p1, feat_dim
+    return mode, p0, p1, 0
+
+
+def _upsample_forward(x, repeats, norm, max_len, path):
+    _require_cuda(x, 'sequence_feature')
+    if x.dim() != 3:
+        raise IndexError('sequence_feature must have shape (batch_size, max_seq_len, feat_dim)')  # utils.py:196
+    B, P, D = x.shape
+    repeats = _prepare_repeats(repeats, B)
+    if repeats.shape[1] != P:
+        raise ValueError('repeats has {} items per utterance, sequence_feature has {}'.format(repeats.shape[1], P))
+    if repeats.device != x.device:
+        raise RuntimeError('repeats and sequence_feature are on different devices')
+    ends, n_frames, summary = dur_scan(repeats)
+    if max_len is None:
+        # The one permitted device->host read: 32 bytes that size the output (the reference syncs here too,
+        # morgana/utils.py:199) and carry the validity flags.
+        max_frames, n_negative, _, n_overflow = summary.tolist()
+        if n_negative:
+            raise ValueError('repeats may not contain negative values.')  # np.repeat's message, utils.py:220
+        if n_overflow:
+            raise OverflowError('an utterance expands to more than 2**31 - 1 frames')
+        T = int(max_frames)
+    else:
+        T = int(max_len)   # caller-supplied bound (e.g. features['n_frames'].max() known on the host): no sync
+
+    mode, p0, p1, p_sb = _norm_args(norm, D, B, x.device)
+    if x.stride(2) != 1 and D > 1:
+        x = x.contiguous()
+    out = torch.empty((B, T, D), dtype=x.dtype, device=x.device)
+    with _device_of(x):
+        if x.dtype == torch.float32:
+            check(lib.mg_upsample_norm_f32(_ptr(x), x.stride(0), x.stride(1), _ptr(ends), _ptr(p0), _ptr(p1), p_sb, mode,
+                                           _ptr(out), B, P, D, T, _PATHS[path], _stream()), 'mg_upsample_norm_f32')
+        else:
+            if mode != _lib.NORM_NONE:
+                raise TypeError('fused normalisation needs float32 features, got {}'.format(x.dtype))
+            es = x.element_size()
+            check(lib.mg_upsample_bytes(_ptr(x), x.stride(0) * es, x.stride(1) * es, _ptr(ends), _ptr(out), B, P, D * es,
+                                        T, _PATHS[path], _stream()), 'mg_upsample_bytes')
+    return out, ends, n_frames, (mode, p0, p1, p_sb)
+
+
+class _UpsampleFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, repeats, norm, max_len, path):
+        out, ends, n_frames, norm_args = _upsample_forward(x, repeats, norm, max_len, path)
+        ctx.ends, ctx.norm_args, ctx.in_shape, ctx.in_dtype = ends, norm_args, tuple(x.shape), x.dtype
+        ctx.mark_non_differentiable(n_frames)
+        return out, n_frames
+
+    @staticmethod
+    def backward(ctx, grad_out, _grad_n_frames):
+        if ctx.in_dtype != torch.float32:
+            raise NotImplementedError('backward of upsample_to_repetitions is provided for float32 features only')
+        B, P, D = ctx.in_shape
+        mode, p0, p1, p_sb = ctx.norm_args
+        grad_out = grad_out.contiguous()
+        grad_x = torch.empty((B, P, D), dtype=torch.float32, device=grad_out.device)
+        with _device_of(grad_out):
+            check(lib.mg_upsample_norm_bwd_f32(_ptr(grad_out), _ptr(ctx.ends), _ptr(p0), _ptr(p1), p_sb, mode, _ptr(grad_x),
+                                               B, P, D, grad_out.shape[1], _stream()), 'mg_upsample_norm_bwd_f32')
+        return grad_x, None, None, None, None
+
+
+def upsample(x, repeats, norm=None, max_len=None, path='auto', return_lengths=False):
+    """``out[b, t] = norm(x[b, item(b, t)])`` zero-padded to the longest utterance; optionally also ``n_frames``."""
+    if isinstance(x, torch.Tensor) and x.requires_grad and torch.is_grad_enabled():
+        out, n_frames = _UpsampleFn.apply(x, repeats, norm, max_len, path)
+    else:
+        out, _, n_frames, _ = _upsample_forward(x, repeats, norm, max_len, path)
+    return (out, n_frames) if return_lengths else out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K3: standalone normalise / denormalise
+# ----------------------------------------------------------------------------------------------------------------------
+
+def _normalise_launch(x, p0, p1, mode, inverse, rows_per_param):
+    x = x.contiguous()
+    out = torch.empty_like(x)
+    D = x.shape[-1]
+    rows = x.numel() // D if D else 0
+    with _device_of(x):
+        check(lib.mg_normalise_f32(_ptr(x), _ptr(p0), _ptr(p1), mode, int(inverse), _ptr(out), rows, D, rows_per_param,
+                                   _stream()), 'mg_normalise_f32')
+    return out
+
+
+def _scale_vector(mode, p0, p1):
+    """The multiplier the (de)normaliser applies, for the backward pass only (D-sized; not on the forward path)."""
+    if mode == _lib.NORM_MVN:
+        return p1
+    scale = p1 - p0
+    return torch.where(scale.abs() <= 1e-8, torch.ones_like(scale), scale)
+
+
+class _NormaliseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p0, p1, mode, inverse, rows_per_param):
+        ctx.save_for_backward(p0, p1)
+        ctx.mode, ctx.inverse, ctx.rows_per_param = mode, inverse, rows_per_param
+        return _normalise_launch(x, p0, p1, mode, inverse, rows_per_param)
+
+    @staticmethod
+    def backward(ctx, grad):
+        p0, p1 = ctx.saved_tensors
+        scale = _scale_vector(ctx.mode, p0, p1).contiguous()
+        zero = torch.zeros_like(scale)
+        # d/dx (x - a) / s = 1 / s and d/dx (x * s + a) = s: the same kernel with a = 0 and the scale as p1.
+        grad_x = _normalise_launch(grad, zero, scale, ctx.mode, ctx.inverse, ctx.rows_per_param)
+        return grad_x, None, None, None, None, None
+
+
+def normalise(feature, p0, p1, kind, inverse=False):
+    """mvn / minmax (de)normalisation of ``(..., T, D)`` features with ``(D,)`` or ``(..., D)`` parameters."""
+    _require_cuda(feature, 'feature')
+    if feature.dtype != torch.float32:
+        raise TypeError('morgana_b200 normalisers take float32 features, got {}'.format(feature.dtype))
+    mode = _NORM_MODES[kind]
+    if mode == _lib.NORM_NONE:
+        raise ValueError('kind must be "mvn" or "minmax"')
+    D = feature.shape[-1]
+    for p in (p0, p1):
+        _require_cuda(p, 'normaliser parameter')
+        if p.dtype != torch.float32:
+            raise TypeError('normaliser parameters must be float32, got {}'.format(p.dtype))
+        if p.requires_grad:
+            raise NotImplementedError('gradients w.r.t. normaliser parameters are not provided')
+    if p0.shape != p1.shape or p0.shape[-1] != D:
+        raise ValueError('parameter shapes {} / {} do not match feature dim {}'.format(tuple(p0.shape), tuple(p1.shape), D))
+    if p0.dim() == 1:
+        rows_per_param = 0
+    else:
+        # Parameters broadcast as p[..., None, :] (morgana/data.py:534): one row per leading index, shared over time.
+        if feature.dim() < 2 or tuple(p0.shape[:-1]) != tuple(feature.shape[:-2]):
+            raise ValueError('parameters of shape {} do not broadcast over features of shape {} as p[..., None, :]'
+                             .format(tuple(p0.shape), tuple(feature.shape)))
+        rows_per_param = feature.shape[-2]
+        if rows_per_param == 0:
+            return torch.empty_like(feature)
+    p0, p1 = p0.contiguous(), p1.contiguous()
+    if feature.requires_grad and torch.is_grad_enabled():
+        return _NormaliseFn.apply(feature, p0, p1, mode, bool(inverse), rows_per_param)
+    return _normalise_launch(feature, p0, p1, mode, bool(inverse), rows_per_param)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K4 / K5: masked reductions
+# ----------------------------------------------------------------------------------------------------------------------
+
+RESULT_BYTES = _lib.TERM_RESULT_BYTES
+# Views of one 48-byte result record.
+F64_SUM, F64_COUNT, F64_LOSS, I64_ISUM = 0, 1, 2, 3
+F32_SUM, F32_COUNT, F32_LOSS, F32_TOTAL = 8, 9, 10, 11
+
+_workspaces = {}
+
+
+def _workspace(device, n_terms, batch_size, max_len):
+    """Zero-initialised scratch per (device, stream); the kernel leaves it clean, so it is zeroed only when (re)made."""
+    need = lib.mg_masked_reduce_workspace_bytes(n_terms, batch_size, max_len)
+    key = (device.index, _stream())
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < need:
+        ws = torch.zeros((max(need, 1 << 20),), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def new_result_records(n, device):
+    """``n`` zeroed ``mg_term_result`` records; row i viewed as float32 / float64 / int64 gives its fields."""
+    return torch.zeros((n, RESULT_BYTES), dtype=torch.uint8, device=device)
+
+
+def _view3(t):
+    """(B, T, D) view with unit inner stride -> (tensor, stride_b, stride_t)."""
+    if t.dim() != 3:
+        raise ValueError('expected a (batch_size, seq_len, feat_dim) tensor, got shape {}'.format(tuple(t.shape)))
+    if t.shape[2] > 1 and t.stride(2) != 1:
+        t = t.contiguous()
+    return t, t.stride(0), t.stride(1)
+
+
+def _dtype_code(t):
+    if t.dtype == torch.float32:
+        return _lib.DT_F32
+    if t.dtype in (torch.uint8, torch.bool):
+        return _lib.DT_U8
+    raise TypeError('morgana_b200 reductions take float32 or uint8/bool tensors, got {}'.format(t.dtype))
+
+
+def make_term(kind, a, b=None, m=None, result=None, accumulate=False, grad=None, grad_scale=1.0, grad_scale_dev=None,
+              flags=0):
+    """Describe one reduction for :func:`masked_reduce`.  Returns ``(Term, keepalive)``."""
+    _require_cuda(a, 'tensor')
+    a, a_sb, a_st = _view3(a)
+    B, T, D = a.shape
+    keep = [a, result]
+    term = Term()
+    term.kind, term.D = kind, D
+    term.a, term.a_sb, term.a_st = _ptr(a), a_sb, a_st
+    term.ab_dtype = _dtype_code(a)
+    if b is not None:
+        _require_cuda(b, 'tensor')
+        if tuple(b.shape) != (B, T, D):
+            raise RuntimeError('operand shapes differ: {} vs {}'.format(tuple(a.shape), tuple(b.shape)))
+        b, b_sb, b_st = _view3(b)
+        b_code = _dtype_code(b)
+        if kind == _lib.RED_EQ:
+            term.b_is_u8 = int(b_code == _lib.DT_U8)
+        elif b_code != term.ab_dtype:
+            raise TypeError('operands must share a dtype, got {} and {}'.format(a.dtype, b.dtype))
+        term.b, term.b_sb, term.b_st = _ptr(b), b_sb, b_st
+        keep.append(b)
+    if m is not None:
+        _require_cuda(m, 'weight')
+        if m.dim() == 3 and m.shape[2] == 1:
+            m = m[:, :, 0]
+        if tuple(m.shape) != (B, T):
+            raise RuntimeError('per-frame weight must have shape (B, T) or (B, T, 1), got {}'.format(tuple(m.shape)))
+        term.m, term.m_sb, term.m_st, term.m_dtype = _ptr(m), m.stride(0), m.stride(1), _dtype_code(m)
+        keep.append(m)
+    if grad is not None:
+        term.grad, term.g_sb, term.g_st = _ptr(grad), grad.stride(0), grad.stride(1)
+        term.grad_scale = float(grad_scale)
+        if grad_scale_dev is not None:
+            term.grad_scale_dev = _ptr(grad_scale_dev)
+            keep.append(grad_scale_dev)
+        keep.append(grad)
+    term.result = _ptr(result)
+    term.accumulate = int(bool(accumulate))
+    term.flags = int(flags)
+    return term, keep
+
+
+def _seq_len_arg(seq_len, batch_size, device):
+    if seq_len is None:
+        return None
+    if not isinstance(seq_len, torch.Tensor):
+        seq_len = torch.as_tensor(seq_len, device=device)
+    _require_cuda(seq_len, 'seq_len')
+    if tuple(seq_len.shape) != (batch_size,):
+        # The reference fails to broadcast anything but (batch_size,).
+        raise RuntimeError('seq_len must have shape (batch_size,) = ({},), got {}'.format(batch_size, tuple(seq_len.shape)))
+    if seq_len.dtype.is_floating_point:
+        seq_len = torch.ceil(seq_len)   # arange(T) < seq_len keeps ceil(seq_len) frames (utils.py:140-142)
+    return seq_len.to(torch.int64).contiguous()
+
+
+def masked_reduce(terms, seq_len, batch_size, max_len, device):
+    """One launch over up to 12 terms.  `terms` is a list of (Term, keepalive) from :func:`make_term`."""
+    n = len(terms)
+    if not 1 <= n <= _lib.MAX_TERMS:
+        raise ValueError('between 1 and {} terms per launch, got {}'.format(_lib.MAX_TERMS, n))
+    seq_len = _seq_len_arg(seq_len, batch_size, device)
+    array = (Term * n)(*[t for t, _ in terms])
+    ws = _workspace(device, n, batch_size, max_len)
+    check(lib.mg_masked_reduce(array, n, _ptr(seq_len), batch_size, max_len, _ptr(ws), ws.numel(), _stream()),
+          'mg_masked_reduce')
+
+
+_LOSS_KINDS = {'mse': _lib.RED_SQDIFF, 'l1': _lib.RED_ABSDIFF, 'bce': _lib.RED_BCE}
+
+
+class _MaskedLossFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, predictions, targets, seq_len, kind):
+        B, T, D = predictions.shape
+        record = new_result_records(1, predictions.device)
+        with _device_of(predictions):
+            term = make_term(kind, predictions, targets, result=record[0])
+            masked_reduce([term], seq_len, B, T, predictions.device)
+        ctx.save_for_backward(predictions, targets)
+        ctx.seq_len, ctx.kind = seq_len, kind
+        ctx.set_materialize_grads(False)
+        return record[0].view(torch.float32)[F32_LOSS]
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        predictions, targets = ctx.saved_tensors
+        if grad_output is None:
+            return None, None, None, None
+        B, T, D = predictions.shape
+        grad = torch.empty((B, T, D), dtype=torch.float32, device=predictions.device)
+        scale = grad_output.detach().to(torch.float32).contiguous()
+        record = new_result_records(1, predictions.device)
+        with _device_of(predictions):
+            term = make_term(ctx.kind, predictions, targets, result=record[0], grad=grad, grad_scale=1.0,
+                             grad_scale_dev=scale)
+            masked_reduce([term], ctx.seq_len, B, T, predictions.device)
+        grad_targets = None
+        if ctx.needs_input_grad[1]:
+            if ctx.kind != _lib.RED_SQDIFF:
+                raise NotImplementedError('gradient w.r.t. targets is provided for mse only')
+            grad_targets = -grad
+        return grad, grad_targets, None, None
+
+
+def masked_loss(predictions, targets, seq_len=None, kind='mse'):
+    """``mean_{b,d} [ sum_{t < n_b} l(p, y) / n_b ]`` as a 0-dim float32 tensor with autograd."""
+    _require_cuda(predictions, 'predictions')
+    _require_cuda(targets, 'targets')
+    if predictions.dtype != torch.float32 or targets.dtype != torch.float32:
+        raise TypeError('morgana_b200 losses take float32 tensors, got {} and {}'.format(predictions.dtype, targets.dtype))
+    if predictions.dim() != 3 or predictions.shape != targets.shape:
+        raise RuntimeError('predictions and targets must share a (batch_size, seq_len, feat_dim) shape, got {} and {}'
+                           .format(tuple(predictions.shape), tuple(targets.shape)))
+    if predictions.shape[0] == 0 or predictions.shape[2] == 0:
+        return torch.full((), float('nan'), dtype=torch.float32, device=predictions.device)
+    seq_len = _seq_len_arg(seq_len, predictions.shape[0], predictions.device)
+    return _MaskedLossFn.apply(predictions, targets, seq_len, _LOSS_KINDS[kind])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K6: multi-tensor EMA
+# ----------------------------------------------------------------------------------------------------------------------
+
+class EmaPlan(object):
+    """Pointer tables for one (shadow, param) pairing, rebuilt only when a storage moves."""
+    def __init__(self):
+        self.key = None
+        self.n = 0
+        self.shadow = self.param = self.numel = None
+
+    def update(self, pairs):
+        key = tuple((s.data_ptr(), p.data_ptr(), s.numel()) for s, p in pairs)
+        if key != self.key:
+            n = len(key)
+            self.shadow = (ctypes.c_void_p * n)(*[k[0] for k in key])
+            self.param = (ctypes.c_void_p * n)(*[k[1] for k in key])
+            self.numel = (ctypes.c_int64 * n)(*[k[2] for k in key])
+            self.key, self.n = key, n
+        return self
+
+
+def ema_update(pairs, one_minus_decay, plan=None):
+    """``shadow -= fl32(one_minus_decay) * (shadow - param)`` in place for every (shadow, param) pair, one launch per 64."""
+    if not pairs:
+        return
+    for s, p in pairs:
+        _require_cuda(s, 'EMA shadow')
+        _require_cuda(p, 'EMA parameter')
+        if s.dtype != torch.float32 or p.dtype != torch.float32:
+            raise TypeError('morgana_b200 EMA takes float32 parameters, got {} / {}'.format(s.dtype, p.dtype))
+        if s.shape != p.shape:
+            raise RuntimeError('EMA shadow {} and parameter {} differ in shape'.format(tuple(s.shape), tuple(p.shape)))
+        if not s.is_contiguous() or not p.is_contiguous():
+            raise NotImplementedError('EMA needs contiguous parameters (the update is in place on their storage)')
+    plan = (plan or EmaPlan()).update(pairs)
+    with _device_of(pairs[0][0]):
+        check(lib.mg_ema_update_f32(plan.shadow, plan.param, plan.numel, plan.n, ctypes.c_float(one_minus_decay),
+                                    _stream()), 'mg_ema_update_f32')
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K7: dense layers
+# ----------------------------------------------------------------------------------------------------------------------
+
+def cast_pad_bf16(x, k_padded=None):
+    """fp32 (rows, K) -> bf16 (rows, k_padded) with zero-filled tail columns."""
+    _require_cuda(x, 'x')
+    if x.dtype != torch.float32 or x.dim() != 2:
+        raise TypeError('cast_pad_bf16 takes a 2-D float32 tensor')
+    if x.shape[1] > 1 and x.stride(1) != 1:
+        x = x.contiguous()
+    rows, K = x.shape
+    k_padded = k_padded or ((K + 7) // 8) * 8
+    out = torch.empty((rows, k_padded), dtype=torch.bfloat16, device=x.device)
+    with _device_of(x):
+        check(lib.mg_cast_pad_bf16(_ptr(x), x.stride(0), _ptr(out), k_padded, rows, K, _stream()), 'mg_cast_pad_bf16')
+    return out

@@ -1,0 +1,73 @@
+"""Drop-in counterparts of the hot-path callables in the reference's ``morgana/utils.py`` (same names and arguments).
+
+* :func:`upsample_to_repetitions` -- morgana/utils.py:175-228
+* :func:`sequence_mask` -- morgana/utils.py:115-144 (kept for API completeness; the kernels never build a mask)
+* :class:`ExponentialMovingAverage` -- morgana/utils.py:421-456
+"""
+import torch
+
+from morgana_b200 import ops
+
+
+def upsample_to_repetitions(sequence_feature, repeats, normaliser=None, deltas=False, max_len=None,
+                            return_lengths=False, path='auto'):
+    r"""Copies sequence items according to ``repeats`` (per-utterance ``np.repeat``), zero-padded to the longest result.
+
+    The first two arguments are the reference's (morgana/utils.py:175).  The keyword arguments are additive:
+
+    normaliser : a normaliser exposing ``normalise``-style parameters (see :mod:`morgana_b200.data`), or a
+        ``(kind, p0, p1)`` tuple.  The normalisation is fused into the gather: equal, bit for bit, to
+        ``upsample_to_repetitions(normaliser.normalise(sequence_feature), repeats)`` (padding stays 0).
+    max_len : int, known upper bound of the output length; skips the 32-byte device->host read (no sync at all).
+    return_lengths : also return ``n_frames`` (``sum(repeats, dim=1)``, int64, on the device).
+
+    Returns ``(batch_size, max_repeated_len, feat_dim)``, same dtype, contiguous.  Raises ``TypeError`` for non-integer
+    ``repeats`` and ``ValueError`` for negative ones, like the reference.
+    """
+    norm = None
+    if normaliser is not None:
+        norm = normaliser if isinstance(normaliser, tuple) else normaliser.fused_params(deltas=deltas)
+    return ops.upsample(sequence_feature, repeats, norm=norm, max_len=max_len, path=path, return_lengths=return_lengths)
+
+
+def sequence_mask(seq_len, max_len=None, dtype=torch.ByteTensor, device=None):
+    r"""``mask[b, t, 0] = t < seq_len[b]`` as ``(batch_size, max_len, 1)`` (morgana/utils.py:115-144).
+
+    Off the hot path: the masked kernels index rows below ``seq_len`` directly and never read a mask.  Provided so code
+    that calls ``utils.sequence_mask`` keeps working; it is three small ATen ops, as in the reference.
+    """
+    if max_len is None:
+        max_len = int(torch.max(seq_len).item())
+    if device is None:
+        device = seq_len.device
+    positions = torch.arange(max_len, device=device).type(seq_len.dtype)
+    mask = positions[None, :] < seq_len.to(device)[:, None]
+    return mask[:, :, None].type(dtype)
+
+
+class ExponentialMovingAverage(object):
+    """EMA of a model's trainable parameters, updated by one multi-tensor kernel (morgana/utils.py:421-456).
+
+    ``shadow[name]`` aliases ``model``'s own ``param.data`` and is updated in place, exactly like the reference, so the
+    averaged model's ``state_dict()`` is always current.
+    """
+    def __init__(self, model, decay):
+        self.model = model
+        self.decay = decay
+        self.shadow = {}
+        for name, param in self.model.named_parameters():
+            if param.requires_grad:
+                self.shadow[name] = param.data
+        self._plan = ops.EmaPlan()
+
+    def _update_param(self, name, x):
+        """One tensor: ``shadow -= (1 - decay) * (shadow - x)``."""
+        assert name in self.shadow
+        ops.ema_update([(self.shadow[name], x)], 1.0 - self.decay)
+
+    def update_params(self, other_model):
+        """All tensors of ``other_model`` that have a shadow, in one launch per 64 tensors."""
+        assert other_model is not self.model
+        pairs = [(self.shadow[name], param.data) for name, param in other_model.named_parameters()
+                 if name in self.shadow]
+        ops.ema_update(pairs, 1.0 - self.decay, plan=self._plan)

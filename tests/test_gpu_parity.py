@@ -1,0 +1,370 @@
+"""Parity of the CUDA path (through the C ABI) against the golden fixtures and the CPU oracle.  Needs a B200."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6   # north-star tolerance for fp32 reductions; index / layout / elementwise work is bit-exact
+
+
+@pytest.fixture(scope='module')
+def mg():
+    import morgana_b200
+    return morgana_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel_err(got, want):
+    want = float(want)
+    return abs(float(got) - want) / max(abs(want), 1e-30)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# a1 upsample_to_repetitions
+# ----------------------------------------------------------------------------------------------------------------------
+UPSAMPLE_CASES = ['tiny_f32', 'odd_f32', 'lab600_f32', 'wide609_f32', 'd1_f32', 'f64', 'i64', 'f16', 'u8',
+                  'emptyrow', 'allzero', 'int32dur']
+
+
+@pytest.mark.parametrize('case', UPSAMPLE_CASES)
+@pytest.mark.parametrize('path', ['auto', 'direct'])
+def test_upsample_golden_bit_exact(mg, golden, case, path):
+    g = golden('upsample')
+    x, dur, want = g['ups_%s_x' % case], g['ups_%s_dur' % case], g['ups_%s_out' % case]
+    got = mg.utils.upsample_to_repetitions(dev(x), dev(dur)[:, :, None], path=path)
+    assert got.is_contiguous() and tuple(got.shape) == want.shape
+    assert got.cpu().numpy().dtype == want.dtype
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_upsample_2d_repeats_and_lengths(mg, golden):
+    g = golden('upsample')
+    x, dur = g['ups_odd_f32_x'], g['ups_odd_f32_dur']
+    got, n_frames = mg.utils.upsample_to_repetitions(dev(x), dev(dur), return_lengths=True)
+    assert np.array_equal(got.cpu().numpy(), g['ups_odd_f32_out'])
+    assert np.array_equal(n_frames.cpu().numpy(), dur.sum(axis=1))
+
+
+def test_upsample_errors(mg):
+    x = torch.zeros(2, 3, 4, device='cuda')
+    with pytest.raises(TypeError):
+        mg.utils.upsample_to_repetitions(x, torch.ones(2, 3, 1, device='cuda'))
+    with pytest.raises(ValueError, match='negative'):
+        mg.utils.upsample_to_repetitions(x, torch.tensor([[1, -1, 2], [0, 0, 0]], device='cuda'))
+    with pytest.raises(IndexError):
+        mg.utils.upsample_to_repetitions(torch.zeros(2, 3, device='cuda'), torch.ones(2, 3, dtype=torch.long, device='cuda'))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        mg.utils.upsample_to_repetitions(torch.zeros(2, 3, 4), torch.ones(2, 3, 1, dtype=torch.long))
+
+
+def test_upsample_non_contiguous_input(mg):
+    rng = np.random.default_rng(0)
+    base = rng.standard_normal((4, 9, 2 * 8)).astype(np.float32)
+    dur = rng.integers(0, 5, (4, 9))
+    xt = dev(base)[:, ::2, :8]          # strided in the item axis, sliced in the feature axis
+    want = O.upsample_to_repetitions(base[:, ::2, :8], dur[:, ::2])
+    got = mg.utils.upsample_to_repetitions(xt, dev(dur[:, ::2].copy()))
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_upsample_max_len_hint_pads_with_zeros(mg, golden):
+    g = golden('upsample')
+    x, dur, want = g['ups_lab600_f32_x'], g['ups_lab600_f32_dur'], g['ups_lab600_f32_out']
+    T = want.shape[1]
+    got = mg.utils.upsample_to_repetitions(dev(x), dev(dur), max_len=T + 5)
+    assert tuple(got.shape) == (x.shape[0], T + 5, x.shape[2])
+    assert np.array_equal(got[:, :T].cpu().numpy(), want)
+    assert not got[:, T:].any()
+
+
+@pytest.mark.parametrize('kind', ['minmax', 'mvn'])
+@pytest.mark.parametrize('path', ['bulk', 'direct'])
+def test_fused_normalise_upsample_golden(mg, golden, kind, path):
+    g = golden('normalise')
+    p0, p1 = (g['fused_mmin'], g['fused_mmax']) if kind == 'minmax' else (g['fused_mean'], g['fused_std'])
+    got = mg.utils.upsample_to_repetitions(dev(g['fused_x']), dev(g['fused_dur']), normaliser=(kind, dev(p0), dev(p1)),
+                                           path=path)
+    assert np.array_equal(got.cpu().numpy(), g['fused_%s_out' % kind])
+
+
+@pytest.mark.parametrize('B,P,D,max_dur', [(7, 33, 600, 30), (3, 70, 187, 12), (16, 5, 4, 300), (2, 300, 64, 3),
+                                             (5, 20, 609, 9), (1, 1, 8, 1)])
+@pytest.mark.parametrize('kind', [None, 'minmax', 'mvn'])
+def test_fused_vs_oracle_random(mg, B, P, D, max_dur, kind):
+    rng = np.random.default_rng(B * 1000 + P + D)
+    x = rng.random((B, P, D), dtype=np.float32)
+    dur = rng.integers(0, max_dur + 1, (B, P))
+    dur[rng.random((B, P)) < 0.15] = 0
+    n_items = rng.integers(0, P + 1, B)
+    dur[np.arange(P)[None, :] >= n_items[:, None]] = 0
+    p0 = rng.standard_normal(D).astype(np.float32)
+    p1 = (np.abs(rng.standard_normal(D)) + 0.1).astype(np.float32)
+    if kind == 'minmax':
+        p1 = p0 + p1
+        p1[::3] = p0[::3]
+    if kind is None:
+        want = O.upsample_to_repetitions(x, dur)
+        norm = None
+    else:
+        want = O.normalise_upsample(x, dur, kind, p0, p1)
+        norm = (kind, dev(p0), dev(p1))
+    got = mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=norm)
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_fused_speaker_dependent_params(mg):
+    rng = np.random.default_rng(5)
+    B, P, D = 4, 6, 8
+    x = rng.random((B, P, D), dtype=np.float32)
+    dur = rng.integers(0, 4, (B, P))
+    mean = rng.standard_normal((B, D)).astype(np.float32)
+    std = (rng.random((B, D)) + 0.2).astype(np.float32)
+    want = O.upsample_to_repetitions(O.normalise_mvn(x, mean, std), dur)
+    got = mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=('mvn', dev(mean), dev(std)))
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_upsample_backward_golden_and_deterministic(mg, golden):
+    g = golden('upsample')
+    x = dev(g['upsbwd_x']).requires_grad_()
+    out = mg.utils.upsample_to_repetitions(x, dev(g['upsbwd_dur']))
+    out.backward(dev(g['upsbwd_grad_out']))
+    np.testing.assert_allclose(x.grad.cpu().numpy(), g['upsbwd_grad_x'], rtol=REL, atol=1e-6)
+    first = x.grad.clone()
+    x.grad = None
+    mg.utils.upsample_to_repetitions(x, dev(g['upsbwd_dur'])).backward(dev(g['upsbwd_grad_out']))
+    assert torch.equal(first, x.grad)
+
+
+def test_upsample_backward_through_normaliser(mg):
+    rng = np.random.default_rng(11)
+    B, P, D = 3, 10, 600
+    x = rng.random((B, P, D), dtype=np.float32)
+    dur = rng.integers(0, 6, (B, P))
+    mean = rng.standard_normal(D).astype(np.float32)
+    std = (rng.random(D) + 0.2).astype(np.float32)
+    xt = dev(x).requires_grad_()
+    out = mg.utils.upsample_to_repetitions(xt, dev(dur), normaliser=('mvn', dev(mean), dev(std)))
+    grad_out = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+    out.backward(dev(grad_out))
+    want = O.upsample_backward(grad_out, dur).astype(np.float64) / (std + np.float32(1e-8)).astype(np.float64)
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), want, rtol=2e-6, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# a3 / a4 normalisers
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', ['btd', 'td', 'btd187', 'sd'])
+def test_normalisers_golden_bit_exact(mg, golden, case):
+    g = golden('normalise')
+    x = dev(g['norm_%s_x' % case])
+    mean, std = dev(g['norm_%s_mean' % case]), dev(g['norm_%s_std' % case])
+    mmin, mmax = dev(g['norm_%s_mmin' % case]), dev(g['norm_%s_mmax' % case])
+    D = mg.data
+    for fn, args, key in [(D.normalise_mvn, (mean, std), 'mvn'), (D.denormalise_mvn, (mean, std), 'demvn'),
+                          (D.normalise_minmax, (mmin, mmax), 'minmax'), (D.denormalise_minmax, (mmin, mmax), 'deminmax')]:
+        got = fn(x, *args).cpu().numpy()
+        assert np.array_equal(got, g['norm_%s_%s' % (case, key)]), key
+
+
+def test_normaliser_classes_and_autograd(mg):
+    rng = np.random.default_rng(2)
+    D = 187
+    norm = mg.data.MeanVarianceNormaliser('mcep', use_deltas=True).set_params(
+        {'mean': rng.standard_normal(D), 'std_dev': rng.random(D) + 0.3},
+        {'mean': rng.standard_normal(D), 'std_dev': rng.random(D) + 0.3})
+    x = rng.standard_normal((3, 50, D)).astype(np.float32)
+    for deltas in (False, True):
+        p = norm.fetch_params(np.ndarray, deltas=deltas)
+        want = O.denormalise_mvn(x, p['mean'], p['std_dev'])
+        assert np.array_equal(norm.denormalise(dev(x), deltas=deltas).cpu().numpy(), want)
+        assert np.allclose(norm.denormalise(x, deltas=deltas), want)   # NumPy inputs stay in NumPy
+    xt = dev(x).requires_grad_()
+    norm.normalise(xt).sum().backward()
+    want_grad = np.broadcast_to(1. / (norm.params['std_dev'] + np.float32(1e-8)), x.shape)
+    np.testing.assert_allclose(xt.grad.cpu().numpy(), want_grad, rtol=1e-6)
+
+
+def test_normalise_large_odd_shape(mg):
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((37, 211, 187)).astype(np.float32)
+    mmin = rng.standard_normal(187).astype(np.float32)
+    mmax = (mmin + rng.random(187) + 0.01).astype(np.float32)
+    got = mg.data.normalise_minmax(dev(x), dev(mmin), dev(mmax)).cpu().numpy()
+    assert np.array_equal(got, O.normalise_minmax(x, mmin, mmax))
+    got = mg.data.denormalise_minmax(dev(x)[:, :, :], dev(mmin), dev(mmax)).cpu().numpy()
+    assert np.array_equal(got, O.denormalise_minmax(x, mmin, mmax))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# a6 / a7 losses
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('case', ['small', 'wide', 'd1'])
+@pytest.mark.parametrize('masked', [True, False])
+def test_losses_golden(mg, golden, case, masked):
+    g = golden('losses')
+    tag = 'masked' if masked else 'full'
+    seq_len = dev(g['loss_%s_seq_len' % case]) if masked else None
+    for kind, fn, a, b in [('mse', mg.losses.mse, 'pred', 'tgt'), ('bce', mg.losses.bce, 'prob', 'label')]:
+        p = dev(g['loss_%s_%s' % (case, a)]).requires_grad_()
+        y = dev(g['loss_%s_%s' % (case, b)])
+        value = fn(p, y, seq_len)
+        assert value.dim() == 0 and value.dtype == torch.float32
+        want = g['loss_%s_%s_%s' % (case, kind, tag)]
+        assert rel_err(value.item(), want) <= REL, (kind, value.item(), float(want))
+        (value * 0.25).backward()     # a non-trivial upstream gradient, as in `loss / 4.` (models/RNN_SPSS.py:139)
+        np.testing.assert_allclose(p.grad.cpu().numpy(), 0.25 * g['loss_%s_%s_%s_grad' % (case, kind, tag)],
+                                   rtol=2e-6, atol=1e-10)
+
+
+def test_loss_semantics(mg):
+    pred = torch.randn(2, 4, 3, device='cuda')
+    tgt = torch.randn(2, 4, 3, device='cuda')
+    assert torch.isnan(mg.losses.mse(pred, tgt, torch.tensor([0, 3], device='cuda')))   # 0/0, SURVEY.md Q6
+    with pytest.raises(RuntimeError):
+        mg.losses.mse(pred, tgt, torch.tensor([[1], [3]], device='cuda'))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        mg.losses.mse(pred.cpu(), tgt.cpu())
+    # seq_len longer than T behaves like T (mask is arange(T) < seq_len)
+    a = mg.losses.mse(pred, tgt, torch.tensor([9, 4], device='cuda')).item()
+    b = mg.losses.mse(pred, tgt).item()
+    assert a == b
+
+
+@pytest.mark.parametrize('B,T,D', [(8, 301, 187), (5, 1000, 3), (3, 77, 180), (64, 50, 1)])
+@pytest.mark.parametrize('kind', ['mse', 'l1', 'bce'])
+def test_losses_vs_oracle_random_and_strided(mg, B, T, D, kind):
+    rng = np.random.default_rng(B + T + D)
+    seq_len = rng.integers(1, T + 1, B)
+    wide = rng.random((B, T, D + 7), dtype=np.float32) * 0.98 + 0.01
+    y = (rng.random((B, T, D)) < 0.5).astype(np.float32) if kind == 'bce' else rng.standard_normal((B, T, D)).astype(np.float32)
+    fn = getattr(mg.losses, kind)
+    wide_t = dev(wide).requires_grad_()
+    value = fn(wide_t[:, :, 3:3 + D], dev(y), dev(seq_len))     # a column slice: strided rows, no copy
+    want = O.masked_loss(wide[:, :, 3:3 + D], y, seq_len, kind)
+    assert rel_err(value.item(), want) <= REL
+    value.backward()
+    want_grad = np.zeros_like(wide)
+    want_grad[:, :, 3:3 + D] = O.masked_loss_grad(wide[:, :, 3:3 + D], y, seq_len, kind)
+    np.testing.assert_allclose(wide_t.grad.cpu().numpy(), want_grad, rtol=3e-6, atol=1e-12)
+    # contiguous operands take the vector path; same answer to the bit across runs
+    c = dev(np.ascontiguousarray(wide[:, :, 3:3 + D]))
+    v1, v2 = fn(c, dev(y), dev(seq_len)), fn(c, dev(y), dev(seq_len))
+    assert rel_err(v1.item(), want) <= REL and v1.item() == v2.item()
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# a8 - a12 metrics
+# ----------------------------------------------------------------------------------------------------------------------
+def _metric_batches(g):
+    keys = ['seq_len', 'tgt', 'pred', 'lf0_t', 'lf0_p', 'voiced', 'bits_t', 'bits_p']
+    return [{k: dev(g['met_b%d_%s' % (i, k)]) for k in keys} for i in range(2)]
+
+
+def _metric_specs(M):
+    return {
+        'mean': (M.Mean, lambda b: (b['tgt'],)),
+        'rmse': (M.RMSE, lambda b: (b['tgt'], b['pred'])),
+        'mae': (M.MAE, lambda b: (b['tgt'], b['pred'])),
+        'melcep': (M.MelCepDistortion, lambda b: (b['tgt'], b['pred'])),
+        'distortion': (M.Distortion, lambda b: (b['tgt'], b['pred'])),
+        'f0': (M.F0Distortion, lambda b: (b['lf0_t'].exp(), b['lf0_p'].exp(), b['voiced'])),
+        'lf0': (M.LF0Distortion, lambda b: (b['lf0_t'], b['lf0_p'], b['voiced'])),
+        'lf0_floatmask': (M.LF0Distortion, lambda b: (b['lf0_t'], b['lf0_p'], b['voiced'].float())),
+        'error': (M.Error, lambda b: (b['bits_t'], b['bits_p'])),
+        'accuracy': (M.Accuracy, lambda b: (b['bits_t'], b['bits_p'])),
+        'error_u8': (M.Error, lambda b: (b['bits_t'].to(torch.uint8), b['bits_p'].to(torch.uint8))),
+        'vuvacc': (M.Mean, lambda b: ((b['bits_t'] == b['bits_p']).type(torch.float),)),
+    }
+
+
+@pytest.mark.parametrize('name', ['mean', 'rmse', 'mae', 'melcep', 'distortion', 'f0', 'lf0', 'lf0_floatmask', 'error',
+                                  'accuracy', 'error_u8', 'vuvacc'])
+@pytest.mark.parametrize('masked', [True, False])
+def test_metrics_golden(mg, golden, name, masked):
+    g = golden('metrics')
+    cls, args_of = _metric_specs(mg.metrics)[name]
+    metric = cls()
+    metric.reset_state()
+    voiced_before = [b['voiced'].clone() for b in _metric_batches(g)]
+    batches = _metric_batches(g)
+    for b in batches:
+        metric.accumulate(*args_of(b), seq_len=b['seq_len'] if masked else None)
+    key = 'met_%s_%s' % (name, 'masked' if masked else 'full')
+    assert float(metric.count) == float(g[key + '_count'])
+    if name in ('error', 'accuracy', 'error_u8'):
+        assert int(metric.sum) == int(g[key + '_sum'])            # integer work: exact
+    else:
+        assert rel_err(metric.sum, g[key + '_sum']) <= REL
+    assert rel_err(metric.result(), g[key + '_result']) <= REL
+    for b, before in zip(batches, voiced_before):                 # inputs are never mutated
+        assert torch.equal(b['voiced'], before)
+
+
+def test_metrics_full_size_vs_oracle(mg):
+    """Config 3 shape (reduced batch): 187-dim targets, static-column metrics of models/RNN_SPSS.py:124-129."""
+    rng = np.random.default_rng(7)
+    B, T, D = 48, 1200, 187
+    seq_len = rng.integers(300, T + 1, B)
+    tgt = rng.standard_normal((B, T, D)).astype(np.float32)
+    pred = (tgt + 0.1 * rng.standard_normal((B, T, D))).astype(np.float32)
+    tgt[:, :, 0] = 5 + 0.3 * tgt[:, :, 0]
+    pred[:, :, 0] = tgt[:, :, 0] + 0.05 * pred[:, :, 0]
+    voiced = rng.random((B, T, 1)) < 0.6
+    tgt_t, pred_t, seq_t, voiced_t = dev(tgt), dev(pred), dev(seq_len), dev(voiced)
+    M = mg.metrics
+    checks = [
+        (M.LF0Distortion(), (tgt_t[:, :, 0:1], pred_t[:, :, 0:1], voiced_t), O.lf0_acc(tgt[:, :, 0:1], pred[:, :, 0:1], voiced, seq_len)),
+        (M.MelCepDistortion(), (tgt_t[:, :, 4:64], pred_t[:, :, 4:64]), O.melcep_acc(tgt[:, :, 4:64], pred[:, :, 4:64], seq_len)),
+        (M.Distortion(), (tgt_t[:, :, 184:185], pred_t[:, :, 184:185]), O.distortion_acc(tgt[:, :, 184:185], pred[:, :, 184:185], seq_len)),
+        (M.RMSE(), (tgt_t, pred_t), O.rmse_acc(tgt, pred, seq_len)),
+    ]
+    for metric, args, (want_sum, want_count) in checks:
+        metric.reset_state()
+        metric.accumulate(*args, seq_len=seq_t)
+        assert float(metric.count) == want_count
+        assert rel_err(metric.sum, want_sum) <= REL, type(metric).__name__
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# a13 EMA
+# ----------------------------------------------------------------------------------------------------------------------
+def test_ema_golden_bit_exact(mg, golden):
+    g = golden('ema')
+    n, decay = int(g['ema_n']), float(g['ema_decay'])
+    model = torch.nn.ParameterList([torch.nn.Parameter(dev(g['ema_param0_%d' % i])) for i in range(n)])
+    ema_model = torch.nn.ParameterList([torch.nn.Parameter(dev(g['ema_shadow0_%d' % i])) for i in range(n)])
+    ema = mg.utils.ExponentialMovingAverage(ema_model, decay)
+    for step in range(3):
+        with torch.no_grad():
+            for i, p in enumerate(model):
+                p.copy_(dev(g['ema_param%d_%d' % (step, i)]))
+        ema.update_params(model)
+        for i, p in enumerate(ema_model):
+            assert np.array_equal(p.detach().cpu().numpy(), g['ema_shadow%d_%d' % (step + 1, i)])
+    with pytest.raises(AssertionError):
+        ema.update_params(ema_model)
+
+
+def test_ema_many_tensors_bit_exact(mg):
+    """More than 64 tensors (several launches), odd sizes, a misaligned view; against the NumPy restatement."""
+    rng = np.random.default_rng(9)
+    sizes = [1, 3, 4, 5, 8191, 8192, 8193, 100003] + [int(s) for s in rng.integers(1, 3000, 70)]
+    shadow = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+    param = [rng.standard_normal(s).astype(np.float32) for s in sizes]
+    flat = torch.zeros(sum(sizes) + 1, device='cuda')
+    views, off = [], 1                                   # offset by one float: most views are not 16-byte aligned
+    for s, arr in zip(sizes, shadow):
+        views.append(flat[off:off + s])
+        views[-1].copy_(dev(arr))
+        off += s
+    pairs = [(v, dev(p)) for v, p in zip(views, param)]
+    mg.ops.ema_update(pairs, 1.0 - 0.9999)
+    for v, s, p in zip(views, shadow, param):
+        assert np.array_equal(v.cpu().numpy(), O.ema_update(s.copy(), p, 0.9999))

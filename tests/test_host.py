@@ -1,0 +1,133 @@
+"""CPU-side checks: the C-ABI library loads and exports what the header declares; host logic; no CPU path."""
+import ctypes
+import os
+import re
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+REPO_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def mg():
+    sys.path.insert(0, REPO_ROOT)
+    import __graft_entry__
+    __graft_entry__.build()
+    import morgana_b200
+    return morgana_b200
+
+
+def header_symbols():
+    with open(os.path.join(REPO_ROOT, 'include', 'morgana_b200.h')) as f:
+        text = re.sub(r'/\*.*?\*/', '', f.read(), flags=re.S)
+    return sorted(set(re.findall(r'\b(mg_[a-z0-9_]+)\s*\(', text)))
+
+
+def test_library_exports_every_declared_symbol(mg):
+    from morgana_b200 import _lib
+    names = header_symbols()
+    assert len(names) >= 13
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in names:
+        assert hasattr(raw, name), 'libmorgana_b200.so does not export ' + name
+    assert sorted(_lib.PROTOTYPES) == names       # the ctypes table binds exactly the header's entry points
+    assert raw.mg_abi_version() == 1
+
+
+def test_struct_layouts_match_header(mg):
+    from morgana_b200 import _lib
+    assert ctypes.sizeof(_lib.Term) == 144
+    assert ctypes.sizeof(_lib.TermResult) == 48
+    assert _lib.TermResult.sum_f32.offset == 32 and _lib.TermResult.weighted_loss_f32.offset == 44
+
+
+def test_sass_uses_bulk_copy_engine(mg):
+    """The upsample kernel's stores go through the TMA engine: SASS shows UBLKCP (B200_PROFILING.md)."""
+    from morgana_b200 import _lib
+    import shutil
+    import subprocess
+    cuobjdump = shutil.which('cuobjdump') or '/usr/local/cuda/bin/cuobjdump'
+    if not os.path.exists(cuobjdump):
+        pytest.skip('cuobjdump not available')
+    sass = subprocess.run([cuobjdump, '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert 'sm_100a' in sass
+    assert 'UBLKCP' in sass
+
+
+def test_no_cpu_path(mg):
+    x = torch.zeros(2, 3, 4)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        mg.utils.upsample_to_repetitions(x, torch.ones(2, 3, 1, dtype=torch.long))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        mg.losses.mse(x, x)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        mg.data.normalise_mvn(x, torch.zeros(4), torch.ones(4))
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        mg.metrics.RMSE().accumulate(x, x)
+    with pytest.raises(RuntimeError, match='no CPU path'):
+        mg.ops.ema_update([(torch.zeros(3), torch.ones(3))], 0.1)
+
+
+def test_numpy_normalisers_stay_numpy(mg):
+    """DataLoader workers normalise NumPy arrays (reference data.py:119-127); that path must not touch CUDA."""
+    from oracle import np_oracle as O
+    rng = np.random.default_rng(0)
+    x = rng.standard_normal((7, 5)).astype(np.float32)
+    mean, std = rng.standard_normal(5).astype(np.float32), (rng.random(5) + 0.1).astype(np.float32)
+    norm = mg.data.MeanVarianceNormaliser('lf0').set_params({'mean': mean, 'std_dev': std}, device='cpu')
+    np.testing.assert_allclose(norm.normalise(x), O.normalise_mvn(x, mean, std), rtol=1e-6)
+    np.testing.assert_allclose(norm.denormalise(x), O.denormalise_mvn(x, mean, std), rtol=1e-6)
+    mmin = rng.standard_normal(5).astype(np.float32)
+    mmax = mmin.copy()
+    mmax[1:] += 1.
+    mm = mg.data.MinMaxNormaliser('lab').set_params({'mmin': mmin, 'mmax': mmax}, device='cpu')
+    np.testing.assert_allclose(mm.normalise(x), O.normalise_minmax(x, mmin, mmax), rtol=1e-6)
+    assert mm.fused_params()[0] == 'minmax'
+
+
+def test_normaliser_json_loading(mg, tmp_path):
+    import json
+    (tmp_path / 'norm').mkdir()
+    with open(tmp_path / 'norm' / 'lf0_mvn.json', 'w') as f:
+        json.dump({'mean': [1., 2.], 'std_dev': [3., 4.]}, f)
+    with open(tmp_path / 'norm' / 'lf0_deltas_mvn.json', 'w') as f:
+        json.dump({'mean': [0., 0.], 'std_dev': [1., 1.]}, f)
+    norm = mg.data.MeanVarianceNormaliser('lf0', use_deltas=True)
+    norm.load_params('norm', data_root=str(tmp_path), device='cpu')
+    assert norm.params['std_dev'].dtype == np.float32 and norm.delta_params_torch['mean'].shape == (2,)
+
+
+def test_patch_and_unpatch_rebind_reference_names(mg):
+    """patch() swaps exactly the hot-path callables of a `morgana`-shaped package and unpatch() restores them."""
+    fake = types.ModuleType('morgana')
+    for sub in ('utils', 'losses', 'data', 'metrics'):
+        setattr(fake, sub, types.ModuleType('morgana.' + sub))
+    sentinel = object()
+    fake.utils.upsample_to_repetitions = fake.utils.ExponentialMovingAverage = sentinel
+    fake.losses.mse = fake.losses.bce = sentinel
+    for name in ('normalise_mvn', 'denormalise_mvn', 'normalise_minmax', 'denormalise_minmax'):
+        setattr(fake.data, name, sentinel)
+
+    def ref_accumulate(self, *a, **k):
+        return 'reference'
+    for cls in mg.metrics.ACCUMULATORS:
+        setattr(fake.metrics, cls.__name__, type(cls.__name__, (object,), {'accumulate': ref_accumulate}))
+    mg.patch(fake)
+    assert fake.utils.upsample_to_repetitions is mg.utils.upsample_to_repetitions
+    assert fake.losses.mse is mg.losses.mse and fake.data.normalise_minmax is mg.data.normalise_minmax
+    assert fake.metrics.RMSE.accumulate is mg.metrics.RMSE.__dict__['accumulate']
+    mg.unpatch()
+    assert fake.utils.upsample_to_repetitions is sentinel and fake.losses.bce is sentinel
+    assert fake.metrics.RMSE.accumulate is ref_accumulate
+    assert not hasattr(fake.metrics.RMSE, 'result')
+
+
+def test_sequence_mask_matches_golden(mg, golden):
+    g = golden('sequence_mask')
+    seq_len = torch.from_numpy(g['mask_seq_len'])
+    assert np.array_equal(mg.utils.sequence_mask(seq_len).numpy(), g['mask_default'])
+    assert np.array_equal(mg.utils.sequence_mask(seq_len, max_len=7, dtype=torch.float32).numpy(), g['mask_len7_f32'])

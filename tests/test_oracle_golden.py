@@ -172,3 +172,73 @@ def test_linear(golden, case):
     x, w, b = g['lin_%s_x' % case], g['lin_%s_w' % case], g['lin_%s_b' % case]
     np.testing.assert_allclose(O.linear(x, w, b), g['lin_%s_y' % case], rtol=1e-5, atol=1e-5)
     np.testing.assert_allclose(O.linear(x, w, b, 'sigmoid'), g['lin_%s_sig' % case], rtol=1e-5, atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The torch-CPU op chain used as the timed CPU baseline (oracle/aten_chain.py) is held to the same fixtures.
+# ----------------------------------------------------------------------------------------------------------------------
+def test_aten_chain_matches_reference_outputs(golden):
+    import torch
+    from oracle import aten_chain as C
+    g = golden('upsample')
+    for case in ['tiny_f32', 'odd_f32', 'lab600_f32', 'emptyrow', 'i64']:
+        got = C.upsample_chain(torch.from_numpy(g['ups_%s_x' % case]), torch.from_numpy(g['ups_%s_dur' % case])[:, :, None])
+        assert np.array_equal(got.numpy(), g['ups_%s_out' % case])
+    g = golden('normalise')
+    x, mmin, mmax = (torch.from_numpy(g['norm_btd_' + k]) for k in ('x', 'mmin', 'mmax'))
+    assert np.array_equal(C.normalise_minmax_chain(x, mmin, mmax).numpy(), g['norm_btd_minmax'])
+    mean, std = torch.from_numpy(g['norm_btd_mean']), torch.from_numpy(g['norm_btd_std'])
+    assert np.array_equal(C.normalise_mvn_chain(x, mean, std).numpy(), g['norm_btd_mvn'])
+    assert np.array_equal(C.denormalise_mvn_chain(x, mean, std).numpy(), g['norm_btd_demvn'])
+    g = golden('losses')
+    for case in ['small', 'wide', 'd1']:
+        seq_len = torch.from_numpy(g['loss_%s_seq_len' % case])
+        pred, tgt = torch.from_numpy(g['loss_%s_pred' % case]), torch.from_numpy(g['loss_%s_tgt' % case])
+        assert C.mse_chain(pred, tgt, seq_len).item() == float(g['loss_%s_mse_masked' % case])
+        assert C.mse_chain(pred, tgt).item() == float(g['loss_%s_mse_full' % case])
+        prob, label = torch.from_numpy(g['loss_%s_prob' % case]), torch.from_numpy(g['loss_%s_label' % case])
+        assert C.bce_chain(prob, label, seq_len).item() == float(g['loss_%s_bce_masked' % case])
+    g = golden('metrics')
+    totals = {'rmse': [0., 0.], 'melcep': [0., 0.], 'distortion': [0., 0.], 'lf0': [0., 0.]}
+    for i in range(2):
+        b = {k: torch.from_numpy(v) for k, v in _metric_inputs(g, i).items()}
+        for name, (s, c) in [('rmse', C.rmse_increment(b['tgt'], b['pred'], b['seq_len'])),
+                             ('melcep', C.melcep_increment(b['tgt'], b['pred'], b['seq_len'])),
+                             ('distortion', C.distortion_increment(b['tgt'], b['pred'], b['seq_len'])),
+                             ('lf0', C.lf0_increment(b['lf0_t'], b['lf0_p'], b['voiced'], b['seq_len']))]:
+            totals[name][0] += s
+            totals[name][1] += c
+    for name, (s, c) in totals.items():
+        assert float(s) == pytest.approx(float(g['met_%s_masked_sum' % name]), rel=1e-7)
+        assert c == float(g['met_%s_masked_count' % name])
+    g = golden('ema')
+    n, decay = int(g['ema_n']), float(g['ema_decay'])
+    shadows = [torch.from_numpy(g['ema_shadow0_%d' % i].copy()) for i in range(n)]
+    for step in range(3):
+        C.ema_chain(shadows, [torch.from_numpy(g['ema_param%d_%d' % (step, i)]) for i in range(n)], decay)
+        for i in range(n):
+            assert np.array_equal(shadows[i].numpy(), g['ema_shadow%d_%d' % (step + 1, i)])
+
+
+def test_aten_chain_objective_matches_numpy_oracle():
+    """The composite the benchmark times on the CPU equals the oracle's numbers for the same batch."""
+    import torch
+    from morgana_b200 import workloads
+    from oracle import aten_chain as C
+    ling = workloads.linguistic_batch(batch_size=6, min_phones=5, max_phones=12, max_dur=9, seed=3)
+    ac = workloads.acoustic_batch(ling['n_frames'], seed=3)
+    loss, grad, increments = C.acoustic_loss_and_metrics(ac['pred'], ac['target'], ac['voiced'], ling['n_frames'])
+    p, t, n = ac['pred'].numpy(), ac['target'].numpy(), ling['n_frames'].numpy()
+    want = (O.masked_loss(p[..., 0:3], t[..., 0:3], n) + O.masked_loss(p[..., 4:184], t[..., 4:184], n) +
+            O.masked_loss(p[..., 184:187], t[..., 184:187], n) + O.masked_loss(p[..., 3:4], t[..., 3:4], n, 'bce')) / 4.
+    assert loss.item() == pytest.approx(want, rel=REL)
+    want_grad = np.zeros_like(p)
+    for sl, kind in [(slice(0, 3), 'mse'), (slice(4, 184), 'mse'), (slice(184, 187), 'mse'), (slice(3, 4), 'bce')]:
+        want_grad[..., sl] = 0.25 * O.masked_loss_grad(p[..., sl], t[..., sl], n, kind)
+    np.testing.assert_allclose(grad.numpy(), want_grad, rtol=3e-6, atol=1e-10)
+    voiced_pred = p[..., 3:4] > 0.5
+    wants = [O.lf0_acc(t[..., 0:1], p[..., 0:1], voiced_pred, n),
+             O.mean_acc((ac['voiced'].numpy() == voiced_pred).astype(np.float32), n),
+             O.melcep_acc(t[..., 4:64], p[..., 4:64], n), O.distortion_acc(t[..., 184:185], p[..., 184:185], n)]
+    for (s, c), (ws, wc) in zip(increments, wants):
+        assert c == wc and float(s) == pytest.approx(ws, rel=REL)
