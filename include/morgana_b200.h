@@ -180,6 +180,50 @@ int mg_masked_reduce(const mg_term* terms /* host array */, int n_terms, const i
                      int B, int64_t T, void* workspace, int64_t workspace_bytes, mg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * K4b  whole-row masked objective -- the fused form of K4/K5 for an acoustic model's loss() (reference
+ *      models/RNN_SPSS.py:120-139: 4 metric accumulations + 3 x losses.mse + losses.bce over column groups of ONE
+ *      (B, T, D) prediction / target pair).  One pass: every valid row is read once, whole, by a CTA whose thread c owns
+ *      column c; the per-column program `cols[c]` says which loss slot and which metric slot the column feeds, so each
+ *      byte of pred / target is read once and the gradient is written once, coalesced.
+ *      Algorithmic HBM bytes: 8*D*sum_b n_b (+ 4*D*B*T with a gradient).
+ *
+ * pred, target   (B, T, D) fp32 views, unit inner stride, strides in elements.
+ * grad           NULL, or (B, T, D) fp32: d(total loss)/d(pred) = l'(p, y) * cols[c].loss_weight * (*grad_scale_dev or 1)
+ *                / (n_b * B) for valid rows, 0 elsewhere and for columns without a loss.
+ * cols           DEVICE array of D column programs.
+ * slots          HOST array of n_slots (<= MG_MAX_TERMS) slot descriptors; slot ids in `cols` index it.
+ * workspace      as for mg_masked_reduce (mg_masked_reduce_workspace_bytes(n_slots, B, T)).
+ */
+#define MG_COL_NONE (-1)
+typedef struct mg_column {
+  int8_t loss_kind;   /* MG_COL_NONE, MG_RED_SQDIFF, MG_RED_ABSDIFF or MG_RED_BCE (pred = probability, target = label) */
+  int8_t loss_slot;
+  int8_t metric_kind; /* MG_COL_NONE, MG_RED_SQDIFF, MG_RED_ABSDIFF, MG_RED_SQDIFF_EXP, MG_RED_EQ ((pred > 0.5) == (target != 0))
+                         or MG_RED_ROOT_SQDIFF (this column LEADS a group of `width` columns: sqrt of the group's squared error) */
+  int8_t metric_slot;
+  int16_t mask_col;   /* MG_COL_NONE, or the metric is weighted per frame by (pred[row, mask_col] > 0.5): F0Distortion's
+                         is_voiced as models/RNN_SPSS.py:122 derives it */
+  int16_t width;      /* MG_RED_ROOT_SQDIFF group width (>= 1) */
+  float loss_weight;  /* term weight / term width, e.g. 0.25 / 180 for the mcep stream of `loss / 4` */
+} mg_column;
+
+typedef struct mg_slot {
+  struct mg_term_result* result; /* device record written (or added to) by the last CTA */
+  int32_t D;          /* number of columns feeding the slot (loss: mean over D; metric without seq_len: numel = B*T*D) */
+  int32_t per_frame;  /* 1: the slot holds one value per frame (ROOT_SQDIFF, weighted metrics) */
+  int32_t weighted;   /* 1: count = sum of the per-frame weights (mask_col metrics) */
+  int32_t accumulate; /* 1: streaming-metric state, result += batch */
+  int32_t in_total;   /* 1: weight * loss is added to slots[0].result->weighted_loss_f32 */
+  float weight;
+} mg_slot;
+
+int mg_masked_objective_f32(const float* pred, int64_t p_sb, int64_t p_st, const float* target, int64_t t_sb, int64_t t_st,
+                            float* grad, int64_t g_sb, int64_t g_st, const float* grad_scale_dev,
+                            const mg_column* cols, int D, const mg_slot* slots, int n_slots,
+                            const int64_t* seq_len, int B, int64_t T, void* workspace, int64_t workspace_bytes,
+                            mg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * K6  multi-tensor EMA -- replaces utils.ExponentialMovingAverage._update_param / update_params (utils.py:443-456):
  *     shadow[i] = shadow[i] - one_minus_decay * (shadow[i] - param[i]), two roundings then the subtract (bit-exact
  *     with the reference's two ATen kernels; not the FMA / decay*s + (1-decay)*x form).

@@ -39,6 +39,21 @@ class TermResult(ctypes.Structure):
                 ('sum_f32', c_f32), ('count_f32', c_f32), ('loss_f32', c_f32), ('weighted_loss_f32', c_f32)]
 
 
+class Column(ctypes.Structure):
+    """``mg_column``: the per-column program of the whole-row objective kernel."""
+    _fields_ = [('loss_kind', ctypes.c_int8), ('loss_slot', ctypes.c_int8), ('metric_kind', ctypes.c_int8),
+                ('metric_slot', ctypes.c_int8), ('mask_col', ctypes.c_int16), ('width', ctypes.c_int16),
+                ('loss_weight', c_f32)]
+
+
+class Slot(ctypes.Structure):
+    """``mg_slot``."""
+    _fields_ = [('result', c_void_p), ('D', c_i32), ('per_frame', c_i32), ('weighted', c_i32), ('accumulate', c_i32),
+                ('in_total', c_i32), ('weight', c_f32)]
+
+
+COL_NONE = -1
+assert ctypes.sizeof(Column) == 12 and ctypes.sizeof(Slot) == 32
 TERM_RESULT_BYTES = ctypes.sizeof(TermResult)
 assert TERM_RESULT_BYTES == 48 and ctypes.sizeof(Term) == 144
 
@@ -57,6 +72,9 @@ PROTOTYPES = {
     'mg_normalise_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_i64, c_int, c_i64, c_void_p]),
     'mg_masked_reduce_workspace_bytes': (c_i64, [c_int, c_int, c_i64]),
     'mg_masked_reduce': (c_int, [ctypes.POINTER(Term), c_int, c_void_p, c_int, c_i64, c_void_p, c_i64, c_void_p]),
+    'mg_masked_objective_f32': (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64, c_i64, c_void_p,
+                                        c_void_p, c_int, ctypes.POINTER(Slot), c_int, c_void_p, c_int, c_i64, c_void_p,
+                                        c_i64, c_void_p]),
     'mg_ema_update_f32': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_i64), c_int,
                                   c_f32, c_void_p]),
     'mg_linear_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int,

@@ -14,18 +14,18 @@
 #include <string.h>
 
 #include "mg_common.cuh"
+#include "mg_finish.cuh"
 
 namespace {
 
 constexpr int kRedThreads = 256;
 constexpr int kRedWarps = kRedThreads / 32;
-constexpr int kMaxChunks = 64;          // chunks (CTAs) per utterance per term: bounds the workspace
+constexpr int kMaxChunks = kMgMaxChunks;
 constexpr int64_t kTargetElems = 32768; // elements of one operand per CTA
 
 struct ReduceParams {
   mg_term terms[MG_MAX_TERMS];
-  int rows_per_cta[MG_MAX_TERMS];
-  int n_chunks[MG_MAX_TERMS];
+  MgFinishSlot slots[MG_MAX_TERMS];
   const int64_t* seq_len;
   double2* partials;       // [term][b][kMaxChunks] (sum, count)
   unsigned int* ticket;
@@ -273,25 +273,21 @@ __device__ __forceinline__ void run_float_term(const mg_term& tm, int b, int64_t
   else run_strided<KIND, false>(a, tm.a_st, bb, tm.b_st, nullptr, 0, n_valid, D, 0.f, sum);
 }
 
-__device__ __forceinline__ int64_t valid_frames(const int64_t* seq_len, int b, int64_t T) {
-  if (seq_len == nullptr) return T;
-  const int64_t n = __ldg(seq_len + b);
-  return n < 0 ? 0 : (n > T ? T : n);   // mask = arange(T) < seq_len  (utils.py:140-142)
-}
-
 __global__ void __launch_bounds__(kRedThreads)
 masked_reduce_kernel(const __grid_constant__ ReduceParams prm) {
-  __shared__ double s_a[kRedWarps], s_b[kRedWarps], s_c[kRedWarps];
+  __shared__ double s_red[96];
   __shared__ bool s_is_last;
+  double* s_a = s_red;
+  double* s_b = s_red + 32;
 
   const int term_idx = blockIdx.z, b = blockIdx.y, chunk = blockIdx.x;
   const mg_term& tm = prm.terms[term_idx];
   const int64_t T = prm.T;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  if (chunk < prm.n_chunks[term_idx]) {
-    const int64_t n_b = valid_frames(prm.seq_len, b, T);
-    const int64_t R = prm.rows_per_cta[term_idx];
+  if (chunk < prm.slots[term_idx].n_chunks) {
+    const int64_t n_b = mg_valid_frames(prm.seq_len, b, T);
+    const int64_t R = prm.slots[term_idx].rows_per_cta;
     const int64_t r0 = chunk * R;
     const int64_t r1 = min(r0 + R, T);
     const int64_t n_valid = max(static_cast<int64_t>(0), min(r1, n_b) - r0);   // valid rows of this chunk
@@ -334,71 +330,8 @@ masked_reduce_kernel(const __grid_constant__ ReduceParams prm) {
   }
 
   // ---- ticket: the last CTA of the grid combines all slots in index order --------------------------------------
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    const unsigned total = gridDim.x * gridDim.y * gridDim.z;
-    s_is_last = atomicAdd(prm.ticket, 1u) == total - 1;
-  }
-  __syncthreads();
-  if (!s_is_last) return;
-  __threadfence();
-
-  double weighted_total = 0.;   // meaningful in thread 0 only
-  for (int t = 0; t < prm.n_terms; ++t) {
-    const mg_term& tt = prm.terms[t];
-    const int64_t R = prm.rows_per_cta[t];
-    const bool discrete = tt.ab_dtype == MG_DT_U8 || tt.kind == MG_RED_EQ;
-    const bool counts_weights = !discrete && tt.m != nullptr;
-    const bool per_frame = !discrete && (tt.m != nullptr || tt.kind == MG_RED_ROOT_SQDIFF);
-    double sum_acc = 0., cnt_acc = 0., loss_acc = 0.;
-    for (int bb = threadIdx.x; bb < prm.B; bb += kRedThreads) {
-      const int64_t n_b = valid_frames(prm.seq_len, bb, T);
-      const int64_t used = min(static_cast<int64_t>(prm.n_chunks[t]), (n_b + R - 1) / R);
-      const double2* slot = prm.partials + (static_cast<int64_t>(t) * prm.B + bb) * kMaxChunks;
-      double s = 0., c = 0.;
-      for (int64_t k = 0; k < used; ++k) {
-        const double2 v = __ldcg(slot + k);
-        s += v.x;
-        c += v.y;
-      }
-      sum_acc += s;
-      loss_acc += s / static_cast<double>(n_b);   // losses.py:39 (0/0 -> nan for an empty utterance, as the reference)
-      if (counts_weights) cnt_acc += c;
-      else if (prm.seq_len != nullptr) cnt_acc += static_cast<double>(n_b);            // frames (metrics.py:393-394)
-      else cnt_acc += static_cast<double>(T) * (per_frame ? 1. : static_cast<double>(tt.D));  // numel (metrics.py:390)
-    }
-    sum_acc = mg_warp_sum(sum_acc);
-    cnt_acc = mg_warp_sum(cnt_acc);
-    loss_acc = mg_warp_sum(loss_acc);
-    __syncthreads();
-    if (lane == 0) { s_a[warp] = sum_acc; s_b[warp] = cnt_acc; s_c[warp] = loss_acc; }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      double s = 0., c = 0., l = 0.;
-#pragma unroll
-      for (int i = 0; i < kRedWarps; ++i) { s += s_a[i]; c += s_b[i]; l += s_c[i]; }
-      l /= static_cast<double>(prm.B) * static_cast<double>(tt.D);   // torch.mean over (B, D), losses.py:42
-      mg_term_result res;
-      if (tt.accumulate) {   // running state of a streaming metric: self.sum += ..., self.count += ...
-        const mg_term_result old = *tt.result;
-        s += old.sum;
-        c += old.count;
-      }
-      res.sum = s;
-      res.count = c;
-      res.loss = l;
-      res.isum = static_cast<int64_t>(s);
-      res.sum_f32 = static_cast<float>(s);
-      res.count_f32 = static_cast<float>(c);
-      res.loss_f32 = static_cast<float>(l);
-      res.weighted_loss_f32 = 0.f;
-      *tt.result = res;
-      if (tt.flags & MG_FLAG_IN_TOTAL) weighted_total += static_cast<double>(tt.grad_scale) * l;
-    }
-  }
-  if (threadIdx.x == 0) prm.terms[0].result->weighted_loss_f32 = static_cast<float>(weighted_total);
-  if (threadIdx.x == 0) *prm.ticket = 0u;   // leave the workspace clean for the next launch
+  if (!mg_take_ticket(prm.ticket, &s_is_last)) return;
+  mg_finish(prm.slots, prm.n_terms, prm.seq_len, prm.B, T, prm.partials, prm.ticket, s_red);
 }
 
 int rows_per_cta_for(int D, int B, int64_t T, int sms) {
@@ -457,9 +390,17 @@ extern "C" int mg_masked_reduce(const mg_term* terms, int n_terms, const int64_t
     }
     prm.terms[i] = tm;
     const int rows = rows_per_cta_for(tm.D, B, T, sms);
-    prm.rows_per_cta[i] = rows;
-    prm.n_chunks[i] = T > 0 ? static_cast<int>((T + rows - 1) / rows) : 1;
-    if (prm.n_chunks[i] > max_chunks) max_chunks = prm.n_chunks[i];
+    MgFinishSlot& sl = prm.slots[i];
+    sl.result = tm.result;
+    sl.D = tm.D;
+    sl.rows_per_cta = rows;
+    sl.n_chunks = T > 0 ? static_cast<int>((T + rows - 1) / rows) : 1;
+    sl.per_frame = !discrete && (tm.m != nullptr || tm.kind == MG_RED_ROOT_SQDIFF);
+    sl.weighted = !discrete && tm.m != nullptr;
+    sl.accumulate = tm.accumulate;
+    sl.in_total = (tm.flags & MG_FLAG_IN_TOTAL) != 0;
+    sl.weight = tm.grad_scale;
+    if (sl.n_chunks > max_chunks) max_chunks = sl.n_chunks;
   }
   prm.seq_len = seq_len;
   prm.ticket = static_cast<unsigned int*>(workspace);

@@ -48,12 +48,67 @@ class AcousticObjective(object):
             metric.sum = record.view(torch.float32)[ops.F32_SUM]
             metric.count = record.view(torch.float64)[ops.F64_COUNT]
 
-    def __call__(self, pred, target, n_frames, want_grad=True):
+    def _column_program(self, device):
+        """One :class:`_lib.Column` per feature column: which loss slot (0-3) and metric slot (4-7) it feeds."""
+        (s_lf0, s_vuv, s_mcep, s_bap), (w_lf0, w_vuv, w_mcep, w_bap) = self.starts, self.widths
+        none = _lib.COL_NONE
+        cols = [_lib.Column(none, 0, none, 0, none, 1, 0.) for _ in range(self.total_dim)]
+        for slot, (kind, start, width) in enumerate([(_lib.RED_SQDIFF, s_lf0, w_lf0), (_lib.RED_SQDIFF, s_mcep, w_mcep),
+                                                     (_lib.RED_SQDIFF, s_bap, w_bap), (_lib.RED_BCE, s_vuv, w_vuv)]):
+            for c in range(start, start + width):
+                cols[c].loss_kind, cols[c].loss_slot, cols[c].loss_weight = kind, slot, 0.25 / width
+        # LF0_RMSE_Hz: static log-F0 column, exp fused, weighted by (vuv probability > 0.5)   (RNN_SPSS.py:122, 126)
+        cols[s_lf0].metric_kind, cols[s_lf0].metric_slot, cols[s_lf0].mask_col = _lib.RED_SQDIFF_EXP, 4, s_vuv
+        # VUV_accuracy: (target == (probability > 0.5))                                         (RNN_SPSS.py:127)
+        cols[s_vuv].metric_kind, cols[s_vuv].metric_slot = _lib.RED_EQ, 5
+        # MCEP_distortion: static coefficients 1 .. mcep_static-1                                (metrics.py:690-694)
+        for c in range(s_mcep + 1, s_mcep + self.mcep_static):
+            cols[c].metric_kind, cols[c].metric_slot = _lib.RED_SQDIFF, 6
+        # BAP_distortion: per-frame Euclidean distance over the static band aperiodicities      (metrics.py:657-665)
+        cols[s_bap].metric_kind, cols[s_bap].metric_slot, cols[s_bap].width = _lib.RED_ROOT_SQDIFF, 7, self.bap_static
+        self._slot_dims = [w_lf0, w_mcep, w_bap, w_vuv, 1, 1, self.mcep_static - 1, 1]
+        return ops.column_table(cols, device)
+
+    def __call__(self, pred, target, n_frames, want_grad=True, grad_scale_dev=None):
         """-> ``(loss, grad)``: the 0-dim total loss and d loss / d pred (``None`` unless `want_grad`).
 
         ``pred`` / ``target``: (B, T, total_dim) float32; the vuv column of ``pred`` is a probability and of ``target`` is
         0/1.  ``n_frames``: (B,) lengths.  Metric state is updated in place (see ``self.metrics``).
+        One launch of the whole-row kernel (K4b); ``last_loss_records`` holds the four per-term losses.
         """
+        ops._require_cuda(pred, 'pred')
+        ops._require_cuda(target, 'target')
+        B, T, D = pred.shape
+        if D != self.total_dim or tuple(target.shape) != (B, T, D):
+            raise RuntimeError('expected (B, T, {}) prediction and target, got {} and {}'.format(
+                self.total_dim, tuple(pred.shape), tuple(target.shape)))
+        if pred.dtype != torch.float32 or target.dtype != torch.float32:
+            raise TypeError('AcousticObjective takes float32 tensors')
+        if self._records is None or self._records.device != pred.device:
+            self._bind_metric_records(pred.device)
+            self._cols = self._column_program(pred.device)
+            self._slots = (_lib.Slot * 8)()
+            for i, dim in enumerate(self._slot_dims):
+                sl = self._slots[i]
+                sl.D, sl.weight = dim, 0.25
+                sl.in_total = int(i < 4)
+                sl.accumulate = int(i >= 4)
+                sl.per_frame = int(i in (4, 7))
+                sl.weighted = int(i == 4)
+                if i >= 4:
+                    sl.result = self._records[i - 4].data_ptr()
+        loss_records = ops.new_result_records(4, pred.device)
+        for i in range(4):
+            self._slots[i].result = loss_records[i].data_ptr()
+        grad = torch.empty((B, T, D), dtype=torch.float32, device=pred.device) if want_grad else None
+        with ops._device_of(pred):
+            ops.masked_objective(pred, target, n_frames, self._cols, self._slots, grad=grad, grad_scale_dev=grad_scale_dev)
+        self.last_loss_records = loss_records
+        loss = loss_records[0].view(torch.float32)[ops.F32_TOTAL]
+        return loss, grad
+
+    def call_with_terms(self, pred, target, n_frames, want_grad=True):
+        """The same objective through eight column-slice terms of the general kernel (K4/K5); kept for cross-checking."""
         ops._require_cuda(pred, 'pred')
         ops._require_cuda(target, 'target')
         B, T, D = pred.shape

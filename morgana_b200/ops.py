@@ -363,6 +363,27 @@ def masked_reduce(terms, seq_len, batch_size, max_len, device):
           'mg_masked_reduce')
 
 
+def column_table(columns, device):
+    """Upload a list of :class:`_lib.Column` (one per feature column) as a device byte tensor."""
+    array = (_lib.Column * len(columns))(*columns)
+    raw = torch.frombuffer(bytearray(bytes(array)), dtype=torch.uint8)
+    return raw.to(device)
+
+
+def masked_objective(pred, target, seq_len, cols, slots, grad=None, grad_scale_dev=None):
+    """K4b: one whole-row pass over (B, T, D) `pred` / `target`; `cols` from :func:`column_table`, `slots` a ctypes array."""
+    pred, p_sb, p_st = _view3(pred)
+    target, t_sb, t_st = _view3(target)
+    B, T, D = pred.shape
+    seq_len = _seq_len_arg(seq_len, B, pred.device)
+    n_slots = len(slots)
+    ws = _workspace(pred.device, n_slots, B, T)
+    g_sb, g_st = (grad.stride(0), grad.stride(1)) if grad is not None else (0, 0)
+    check(lib.mg_masked_objective_f32(_ptr(pred), p_sb, p_st, _ptr(target), t_sb, t_st, _ptr(grad), g_sb, g_st,
+                                      _ptr(grad_scale_dev), _ptr(cols), D, slots, n_slots, _ptr(seq_len), B, T, _ptr(ws),
+                                      ws.numel(), _stream()), 'mg_masked_objective_f32')
+
+
 _LOSS_KINDS = {'mse': _lib.RED_SQDIFF, 'l1': _lib.RED_ABSDIFF, 'bce': _lib.RED_BCE}
 
 

@@ -368,3 +368,71 @@ def test_ema_many_tensors_bit_exact(mg):
     mg.ops.ema_update(pairs, 1.0 - 0.9999)
     for v, s, p in zip(views, shadow, param):
         assert np.array_equal(v.cpu().numpy(), O.ema_update(s.copy(), p, 0.9999))
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K4b: the whole-row fused objective (additive API) equals the composition of the drop-in ops and the oracle
+# ----------------------------------------------------------------------------------------------------------------------
+def _objective_oracle(p, t, voiced_t, n, mcep_static=60, bap_static=1):
+    total = (O.masked_loss(p[..., 0:3], t[..., 0:3], n) + O.masked_loss(p[..., 4:184], t[..., 4:184], n) +
+             O.masked_loss(p[..., 184:187], t[..., 184:187], n) + O.masked_loss(p[..., 3:4], t[..., 3:4], n, 'bce')) / 4.
+    grad = np.zeros_like(p)
+    for sl, kind in [(slice(0, 3), 'mse'), (slice(4, 184), 'mse'), (slice(184, 187), 'mse'), (slice(3, 4), 'bce')]:
+        grad[..., sl] = 0.25 * O.masked_loss_grad(p[..., sl], t[..., sl], n, kind)
+    voiced_p = p[..., 3:4] > 0.5
+    metrics = {'LF0_RMSE_Hz': O.lf0_acc(t[..., 0:1], p[..., 0:1], voiced_p, n),
+               'VUV_accuracy': O.mean_acc((voiced_t == voiced_p).astype(np.float32), n),
+               'MCEP_distortion': O.melcep_acc(t[..., 4:4 + mcep_static], p[..., 4:4 + mcep_static], n),
+               'BAP_distortion': O.distortion_acc(t[..., 184:184 + bap_static], p[..., 184:184 + bap_static], n)}
+    return total, grad, metrics
+
+
+@pytest.mark.parametrize('B,min_p,max_p', [(6, 5, 12), (33, 20, 40)])
+@pytest.mark.parametrize('bap_static', [1, 3])
+def test_fused_objective_vs_oracle(mg, B, min_p, max_p, bap_static):
+    from morgana_b200 import workloads
+    from morgana_b200.fused import AcousticObjective
+    ling = workloads.linguistic_batch(batch_size=B, min_phones=min_p, max_phones=max_p, max_dur=20, seed=B)
+    ac = workloads.acoustic_batch(ling['n_frames'], seed=B)
+    p, t, n = ac['pred'].numpy(), ac['target'].numpy(), ling['n_frames'].numpy()
+    want_total, want_grad, want_metrics = _objective_oracle(p, t, ac['voiced'].numpy(), n, bap_static=bap_static)
+    pred, target, n_frames = ac['pred'].cuda(), ac['target'].cuda(), ling['n_frames'].cuda()
+    for which in ('__call__', 'call_with_terms'):
+        objective = AcousticObjective(bap_static=bap_static)
+        for repeat in range(2):          # metric state is a running sum; the loss is per batch
+            total, grad = getattr(objective, which)(pred, target, n_frames)
+        assert rel_err(total.item(), want_total) <= REL, which
+        np.testing.assert_allclose(grad.cpu().numpy(), want_grad, rtol=3e-6, atol=1e-12)
+        for name, (s, c) in want_metrics.items():
+            got = objective.metrics[name]
+            assert float(got.count) == 2 * c, (which, name)
+            assert rel_err(got.sum, 2 * s) <= REL, (which, name)
+        loss_only, no_grad = getattr(objective, which)(pred, target, n_frames, want_grad=False)
+        assert no_grad is None and loss_only.item() == total.item()       # bit-reproducible run to run
+
+
+def test_fused_objective_matches_drop_in_composition(mg):
+    """What models/RNN_SPSS.py:120-139 computes through the drop-in ops == the one-launch objective."""
+    from morgana_b200 import workloads
+    from morgana_b200.fused import AcousticObjective
+    ling = workloads.linguistic_batch(batch_size=9, min_phones=8, max_phones=15, max_dur=15, seed=21)
+    ac = workloads.acoustic_batch(ling['n_frames'], seed=21)
+    pred, target, n_frames = ac['pred'].cuda().requires_grad_(), ac['target'].cuda(), ling['n_frames'].cuda()
+    L, M = mg.losses, mg.metrics
+    loss = (L.mse(pred[..., 0:3], target[..., 0:3], n_frames) + L.mse(pred[..., 4:184], target[..., 4:184], n_frames) +
+            L.mse(pred[..., 184:187], target[..., 184:187], n_frames) + L.bce(pred[..., 3:4], target[..., 3:4], n_frames)) / 4.
+    loss.backward()
+    vuv = pred.detach()[..., 3:4] > 0.5
+    lf0, acc, mcd, bap = M.LF0Distortion(), M.Mean(), M.MelCepDistortion(), M.Distortion()
+    lf0.accumulate(target[..., 0:1], pred.detach()[..., 0:1], vuv, seq_len=n_frames)
+    acc.accumulate((target[..., 3:4] == vuv).type(torch.float), seq_len=n_frames)
+    mcd.accumulate(target[..., 4:64], pred.detach()[..., 4:64], seq_len=n_frames)
+    bap.accumulate(target[..., 184:185], pred.detach()[..., 184:185], seq_len=n_frames)
+    objective = AcousticObjective()
+    total, grad = objective(pred.detach(), target, n_frames)
+    assert rel_err(total.item(), loss.item()) <= REL
+    np.testing.assert_allclose(grad.cpu().numpy(), pred.grad.cpu().numpy(), rtol=3e-6, atol=1e-12)
+    for got, want in zip(objective.metrics.values(), (lf0, acc, mcd, bap)):
+        assert float(got.count) == float(want.count)
+        assert rel_err(got.sum, float(want.sum)) <= REL
+        assert rel_err(got.result(), float(want.result())) <= REL
