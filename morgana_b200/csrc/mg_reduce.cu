@@ -145,24 +145,50 @@ __device__ __forceinline__ void run_flat(const float* __restrict__ a, const floa
   }
 }
 
-// ---- strided rows (column slices of a wider tensor): scalar, (row, col) advanced without division ---------------------
+// ---- strided rows (column slices of a wider tensor) -------------------------------------------------------------------
+// Thread -> (row group, column): consecutive threads read consecutive columns of a row (coalesced 4-byte loads) and each
+// thread keeps 8 rows in flight.  No division in the loop.
 template <int KIND, bool GRAD>
 __device__ __forceinline__ void run_strided(const float* __restrict__ a, int64_t a_st, const float* __restrict__ b,
                                             int64_t b_st, float* __restrict__ g, int64_t g_st, int64_t n_rows, int D,
                                             float w, double& sum) {
   constexpr bool HAS_B = kind_has_b(KIND);
-  int64_t r = threadIdx.x / D;
-  int d = threadIdx.x % D;
-  const int64_t step_r = kRedThreads / D;
-  const int step_d = kRedThreads % D;
-  while (r < n_rows) {
-    const float av = __ldcs(a + r * a_st + d);
-    const float bv = HAS_B ? __ldcs(b + r * b_st + d) : 0.f;
-    sum += static_cast<double>(elem_fwd<KIND>(av, bv));
-    if constexpr (GRAD) g[r * g_st + d] = __fmul_rn(elem_bwd<KIND>(av, bv), w);
-    r += step_r;
-    d += step_d;
-    if (d >= D) { d -= D; ++r; }
+  constexpr int U = 8;
+  const int groups = D >= kRedThreads ? 1 : kRedThreads / D;
+  const int grp = D >= kRedThreads ? 0 : threadIdx.x / D;
+  if (grp >= groups) return;
+  for (int d = D >= kRedThreads ? threadIdx.x : threadIdx.x - grp * D; d < D; d += kRedThreads) {
+    const float* pa = a + grp * a_st + d;
+    const float* pb = HAS_B ? b + grp * b_st + d : nullptr;
+    float* pg = GRAD ? g + grp * g_st + d : nullptr;
+    const int64_t sa = groups * a_st, sb = groups * b_st, sg = groups * g_st;
+    int64_t r = grp;
+    for (; r + static_cast<int64_t>(U - 1) * groups < n_rows; r += static_cast<int64_t>(U) * groups) {
+      float av[U], bv[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        av[u] = __ldcs(pa + u * sa);
+        bv[u] = HAS_B ? __ldcs(pb + u * sb) : 0.f;
+      }
+      float part = 0.f;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        part = __fadd_rn(part, elem_fwd<KIND>(av[u], bv[u]));
+        if constexpr (GRAD) pg[u * sg] = __fmul_rn(elem_bwd<KIND>(av[u], bv[u]), w);
+      }
+      sum += static_cast<double>(part);
+      pa += U * sa;
+      if (HAS_B) pb += U * sb;
+      if (GRAD) pg += U * sg;
+    }
+    for (; r < n_rows; r += groups) {
+      const float av = __ldcs(pa), bv = HAS_B ? __ldcs(pb) : 0.f;
+      sum += static_cast<double>(elem_fwd<KIND>(av, bv));
+      if constexpr (GRAD) *pg = __fmul_rn(elem_bwd<KIND>(av, bv), w);
+      pa += sa;
+      if (HAS_B) pb += sb;
+      if (GRAD) pg += sg;
+    }
   }
 }
 

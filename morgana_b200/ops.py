@@ -326,11 +326,11 @@ def make_term(kind, a, b=None, m=None, result=None, accumulate=False, grad=None,
         keep.append(m)
     if grad is not None:
         term.grad, term.g_sb, term.g_st = _ptr(grad), grad.stride(0), grad.stride(1)
-        term.grad_scale = float(grad_scale)
         if grad_scale_dev is not None:
             term.grad_scale_dev = _ptr(grad_scale_dev)
             keep.append(grad_scale_dev)
         keep.append(grad)
+    term.grad_scale = float(grad_scale)   # also the term's weight in the first record's weighted total
     term.result = _ptr(result)
     term.accumulate = int(bool(accumulate))
     term.flags = int(flags)
