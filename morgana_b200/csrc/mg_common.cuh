@@ -102,6 +102,35 @@ __device__ __forceinline__ void mg_fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// --- bulk async copy global -> shared::cta, completion counted on an mbarrier (TMA engine; SASS UBLKCP) ---------------
+// src and dst 16-byte aligned, bytes a multiple of 16.
+__device__ __forceinline__ void mg_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mg_smem_addr(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mg_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mg_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mg_smem_addr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mg_bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   mg_smem_addr(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(mg_smem_addr(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mg_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(mg_smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 // --- warp / CTA reductions in a fixed order ------------------------------------------------------------------------
 __device__ __forceinline__ double mg_warp_sum(double v) {
 #pragma unroll

@@ -27,8 +27,7 @@ struct ReduceParams {
   mg_term terms[MG_MAX_TERMS];
   MgFinishSlot slots[MG_MAX_TERMS];
   const int64_t* seq_len;
-  double2* partials;       // [term][b][kMaxChunks] (sum, count)
-  unsigned int* ticket;
+  MgWorkspace ws;
   int64_t T;
   int n_terms;
   int B;
@@ -350,14 +349,13 @@ masked_reduce_kernel(const __grid_constant__ ReduceParams prm) {
         double s = 0., c = 0.;
 #pragma unroll
         for (int i = 0; i < kRedWarps; ++i) { s += s_a[i]; c += s_b[i]; }
-        prm.partials[(static_cast<int64_t>(term_idx) * prm.B + b) * kMaxChunks + chunk] = make_double2(s, c);
+        prm.ws.partials[(static_cast<int64_t>(term_idx) * prm.B + b) * kMaxChunks + chunk] = make_double2(s, c);
       }
     }
   }
 
   // ---- ticket: the last CTA of the grid combines all slots in index order --------------------------------------
-  if (!mg_take_ticket(prm.ticket, &s_is_last)) return;
-  mg_finish(prm.slots, prm.n_terms, prm.seq_len, prm.B, T, prm.partials, prm.ticket, s_red);
+  mg_finish(prm.slots, prm.n_terms, prm.seq_len, prm.B, T, prm.ws, b, gridDim.x * gridDim.z, s_red, &s_is_last);
 }
 
 int rows_per_cta_for(int D, int B, int64_t T, int sms) {
@@ -377,7 +375,7 @@ int rows_per_cta_for(int D, int B, int64_t T, int sms) {
 extern "C" int64_t mg_masked_reduce_workspace_bytes(int n_terms, int B, int64_t T) {
   (void)T;
   if (n_terms < 0 || B < 0) return MG_ERR_INVALID_ARG;
-  return 256 + static_cast<int64_t>(n_terms) * B * kMaxChunks * static_cast<int64_t>(sizeof(double2));
+  return mg_workspace_bytes(n_terms, B);
 }
 
 extern "C" int mg_masked_reduce(const mg_term* terms, int n_terms, const int64_t* seq_len, int B, int64_t T,
@@ -429,8 +427,7 @@ extern "C" int mg_masked_reduce(const mg_term* terms, int n_terms, const int64_t
     if (sl.n_chunks > max_chunks) max_chunks = sl.n_chunks;
   }
   prm.seq_len = seq_len;
-  prm.ticket = static_cast<unsigned int*>(workspace);
-  prm.partials = reinterpret_cast<double2*>(static_cast<unsigned char*>(workspace) + 256);
+  prm.ws = mg_carve_workspace(workspace, n_terms, B);
   prm.T = T;
   prm.n_terms = n_terms;
   prm.B = B;
