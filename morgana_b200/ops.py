@@ -494,3 +494,39 @@ def cast_pad_bf16(x, k_padded=None):
     with _device_of(x):
         check(lib.mg_cast_pad_bf16(_ptr(x), x.stride(0), _ptr(out), k_padded, rows, K, _stream()), 'mg_cast_pad_bf16')
     return out
+
+
+_ACTS = {None: _lib.ACT_NONE, 'none': _lib.ACT_NONE, 'sigmoid': _lib.ACT_SIGMOID}
+
+
+def linear_bf16(x, weight, bias=None, act=None, out_dtype=torch.float32):
+    """K7: ``act(x @ weight.T + bias)`` on the tcgen05 tensor cores.  bf16 operands, fp32 accumulation.
+
+    x : (M, K) bfloat16, row stride a multiple of 8 (fp32 input is converted with :func:`cast_pad_bf16`).
+    weight : (N, K) bfloat16 (``nn.Linear.weight`` layout), bias : (N,) float32 or None.
+    """
+    _require_cuda(x, 'x')
+    _require_cuda(weight, 'weight')
+    if x.dim() != 2 or weight.dim() != 2:
+        raise ValueError('linear_bf16 takes 2-D operands')
+    if x.dtype == torch.float32:
+        x = cast_pad_bf16(x)
+    if weight.dtype == torch.float32:
+        weight = cast_pad_bf16(weight)
+    if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
+        raise TypeError('linear_bf16 takes bfloat16 (or float32, converted) operands')
+    M, N = x.shape[0], weight.shape[0]
+    K = min(x.shape[1], weight.shape[1])   # a padded operand carries zeros beyond the true K
+    for name, t in (('x', x), ('weight', weight)):
+        if t.stride(1) != 1 or t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0:
+            raise ValueError('{}: rows must be contiguous, 16-byte aligned, with a stride that is a multiple of 8'.format(name))
+    if bias is not None:
+        _require_cuda(bias, 'bias')
+        bias = bias.to(torch.float32).contiguous()
+    if out_dtype not in (torch.float32, torch.bfloat16):
+        raise TypeError('out_dtype must be float32 or bfloat16')
+    y = torch.empty((M, N), dtype=out_dtype, device=x.device)
+    with _device_of(x):
+        check(lib.mg_linear_bf16(_ptr(x), x.stride(0), _ptr(weight), weight.stride(0), _ptr(bias), _ptr(y), y.stride(0),
+                                 int(out_dtype == torch.bfloat16), M, N, K, _ACTS[act], _stream()), 'mg_linear_bf16')
+    return y

@@ -436,3 +436,38 @@ def test_fused_objective_matches_drop_in_composition(mg):
         assert float(got.count) == float(want.count)
         assert rel_err(got.sum, float(want.sum)) <= REL
         assert rel_err(got.result(), float(want.result())) <= REL
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# a14: dense layers on tcgen05 (bf16 operands, fp32 accumulate).  Tolerances: (1) against the fp64 product of the
+# bf16-ROUNDED operands only accumulation order and the sigmoid approximation differ: 2e-3 absolute on O(1) activations;
+# (2) against the full-precision layer the bf16 operand rounding dominates: <= 2% of the output range.
+# ----------------------------------------------------------------------------------------------------------------------
+def _bf16_round(a):
+    return torch.from_numpy(a).to(torch.bfloat16).to(torch.float32).numpy()
+
+
+@pytest.mark.parametrize('M,K,N', [(70, 600, 64), (33, 609, 48), (45, 256, 187), (19, 32, 1), (1000, 600, 512),
+                                   (257, 512, 256), (128, 128, 32), (5, 8, 16), (4097, 640, 199)])
+@pytest.mark.parametrize('act', [None, 'sigmoid'])
+def test_linear_tcgen05_vs_oracle(mg, M, K, N, act):
+    rng = np.random.default_rng(M + K + N)
+    x = rng.random((M, K), dtype=np.float32)
+    w = (rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)
+    b = (0.1 * rng.standard_normal(N)).astype(np.float32)
+    y = mg.ops.linear_bf16(dev(x), dev(w), dev(b), act=act).cpu().numpy()
+    assert y.shape == (M, N) and y.dtype == np.float32
+    exact_on_rounded = O.linear(_bf16_round(x), _bf16_round(w), b, act)
+    np.testing.assert_allclose(y, exact_on_rounded, rtol=2e-3, atol=2e-3)
+    full = O.linear(x, w, b, act)
+    assert np.abs(y - full).max() <= 2e-2 * max(1.0, np.abs(full).max())
+    y16 = mg.ops.linear_bf16(dev(x), dev(w), dev(b), act=act, out_dtype=torch.bfloat16).float().cpu().numpy()
+    np.testing.assert_allclose(y16, exact_on_rounded, rtol=1e-2, atol=1e-2)
+
+
+def test_linear_golden(mg, golden):
+    g = golden('linear')
+    for case in ['readme_l1', 'rnn_in', 'out187', 'out1']:
+        x, w, b = g['lin_%s_x' % case], g['lin_%s_w' % case], g['lin_%s_b' % case]
+        y = mg.ops.linear_bf16(dev(x), dev(w), dev(b), act='sigmoid').cpu().numpy()
+        assert np.abs(y - g['lin_%s_sig' % case]).max() <= 1e-2      # bf16 operands vs the reference's fp32 sgemm
