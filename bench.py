@@ -206,7 +206,7 @@ def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
     import morgana_b200 as mg
-    from morgana_b200 import ops, workloads
+    from morgana_b200 import dp, ops, workloads
     from morgana_b200.fused import AcousticObjective
 
     if not torch.cuda.is_available():
@@ -256,10 +256,7 @@ def run_ours(args, rank, world, local_rank):
     def exchange():
         """The path's one collective: SUM of the packed loss / metric-sum records over ranks (NCCL over NVLink)."""
         if world > 1:
-            packed = torch.cat([objective.last_loss_records.view(torch.float64)[:, :3],
-                                objective._records.view(torch.float64)[:, :3]]).clone()
-            dist.all_reduce(packed)
-            return packed
+            return dp.allreduce_records(objective.last_loss_records, objective._records)
         return None
 
     def barrier():
