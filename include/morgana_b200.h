@@ -89,6 +89,17 @@ int mg_upsample_norm_bwd_f32(const float* grad_out, const int32_t* ends, const f
                              int B, int P, int D, int64_t T, mg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * K0  on-device collate -- replaces the zero-padding of FilesDataset.collate_fn (morgana/data.py:159-224, :184-193) and
+ *     the host->device copy of the PADDED batch (data.py:655-663): the host ships only valid rows, packed back to back.
+ *
+ * packed     (sum_b len_b, row_bytes) bytes: utterance 0's rows, then utterance 1's, ...
+ * ends       (B,) int32 inclusive scan of the lengths (mg_dur_scan over the lengths viewed as one (1, B) row).
+ * out        (B, T, row_bytes): rows t < len_b copied, rows t >= len_b zero.  Utterances longer than T are truncated.
+ */
+int mg_pad_collate(const void* packed, const int32_t* ends, void* out, int B, int64_t row_bytes, int64_t T,
+                   mg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * K3  standalone normalise / denormalise -- replaces data.normalise_mvn, denormalise_mvn, normalise_minmax,
  *     denormalise_minmax on torch tensors (morgana/data.py:533-538, 579-590).
  *

@@ -14,6 +14,12 @@ import torch
 from morgana_b200 import ops
 
 
+def pad_collate(packed, lengths, max_len=None):
+    """Zero-pad packed per-utterance rows to ``(B, T, D)`` on the device -- ``collate_fn``'s padding (reference
+    morgana/data.py:184-193) moved after the host->device copy, so only valid rows cross PCIe."""
+    return ops.pad_collate(packed, lengths, max_len=max_len)
+
+
 def _np_scale(mmin, mmax):
     scale = mmax - mmin
     scale[abs(scale) <= 1e-8] = 1.

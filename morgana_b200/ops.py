@@ -176,6 +176,38 @@ def upsample(x, repeats, norm=None, max_len=None, path='auto', return_lengths=Fa
 
 
 # ----------------------------------------------------------------------------------------------------------------------
+# K0: on-device collate (packed rows -> zero-padded batch)
+# ----------------------------------------------------------------------------------------------------------------------
+
+def pad_collate(packed, lengths, max_len=None):
+    """``(sum(lengths), D)`` packed rows -> ``(B, T, D)`` zero-padded batch on the device (any dtype).
+
+    ``lengths``: (B,) integer tensor on the device.  ``max_len``: T, when known on the host (no sync); otherwise the
+    32-byte summary of the length scan is read back.
+    """
+    _require_cuda(packed, 'packed')
+    _require_cuda(lengths, 'lengths')
+    if packed.dim() != 2:
+        raise ValueError('packed must be (total_rows, feat_dim)')
+    packed = packed.contiguous()
+    B = lengths.shape[0]
+    ends, _, summary = dur_scan(lengths.reshape(1, B))
+    if max_len is None:
+        _, n_negative, total, _ = summary.tolist()
+        if n_negative:
+            raise ValueError('lengths may not contain negative values.')
+        if total != packed.shape[0]:
+            raise ValueError('lengths sum to {} rows but packed has {}'.format(total, packed.shape[0]))
+        max_len = int(lengths.max().item()) if B else 0
+    D = packed.shape[1]
+    out = torch.empty((B, int(max_len), D), dtype=packed.dtype, device=packed.device)
+    with _device_of(packed):
+        check(lib.mg_pad_collate(_ptr(packed), _ptr(ends), _ptr(out), B, D * packed.element_size(), int(max_len), _stream()),
+              'mg_pad_collate')
+    return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
 # K3: standalone normalise / denormalise
 # ----------------------------------------------------------------------------------------------------------------------
 

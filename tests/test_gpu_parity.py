@@ -471,3 +471,23 @@ def test_linear_golden(mg, golden):
         x, w, b = g['lin_%s_x' % case], g['lin_%s_w' % case], g['lin_%s_b' % case]
         y = mg.ops.linear_bf16(dev(x), dev(w), dev(b), act='sigmoid').cpu().numpy()
         assert np.abs(y - g['lin_%s_sig' % case]).max() <= 1e-2      # bf16 operands vs the reference's fp32 sgemm
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K0: on-device collate
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('D,dtype', [(187, np.float32), (600, np.float32), (1, np.int64), (3, np.uint8), (8, np.float16)])
+def test_pad_collate_matches_host_padding(mg, D, dtype):
+    rng = np.random.default_rng(D)
+    lengths = rng.integers(0, 40, 9)
+    lengths[3] = 0
+    rows = [(rng.random((n, D)) * 100).astype(dtype) for n in lengths]
+    packed = np.concatenate(rows, axis=0)
+    T = int(lengths.max())
+    want = np.zeros((len(rows), T, D), dtype)                # what collate_fn builds on the host (data.py:184-193)
+    for b, r in enumerate(rows):
+        want[b, :len(r)] = r
+    got = mg.data.pad_collate(dev(packed), dev(lengths))
+    assert np.array_equal(got.cpu().numpy(), want)
+    got = mg.data.pad_collate(dev(packed), dev(lengths), max_len=T + 3)
+    assert np.array_equal(got[:, :T].cpu().numpy(), want) and not got[:, T:].any()
