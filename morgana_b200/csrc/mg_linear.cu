@@ -3,20 +3,23 @@
 // Replaces nn.Linear (+ nn.Sigmoid) of the example models (reference README.rst:65-73; models/RNN_SPSS.py:33,38,41;
 // models/f0_test_model.py:29,41,44), which run as cuBLAS sgemm + separate bias / sigmoid kernels today.
 //
-// One CTA per 128 x BLOCK_N output tile, six warps with fixed roles:
+// Persistent kernel, one CTA per SM walking 128 x BLOCK_N output tiles, six warps with fixed roles:
 //   warp 0  TMA producer   one lane issues cp.async.bulk.tensor (SASS UTMALDG) for the A (128 x 64) and B (BLOCK_N x 64)
-//                          bf16 tiles of each K block into a 3-stage ring, 128-byte swizzle, completion on mbarriers;
+//                          bf16 tiles of each K block into a 4-stage ring, 128-byte swizzle, completion on mbarriers;
 //                          rows / K columns outside the tensors are zero-filled by the TMA unit, so K = 600 needs no padding
 //   warp 1  MMA issuer     one lane issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BLOCK_N, K = 16) per K block
-//                          (SASS UTCHMMA); tcgen05.commit releases the smem stage and, at the end, publishes the accumulator
-//   warps 2-5 epilogue     tcgen05.ld 32 lanes x 32 columns at a time (SASS LDTM), + bias, optional sigmoid, stores
-// The accumulator (128 lanes x BLOCK_N fp32 columns) lives in tensor memory; nothing is kept in registers across K.
-// Two CTAs fit an SM (96 KB of stages each), so one CTA's epilogue overlaps the other's main loop.
+//                          (SASS UTCHMMA); tcgen05.commit releases the smem stage and publishes the accumulator
+//   warps 2-5 epilogue     tcgen05.ld 32 lanes x 32 columns at a time (SASS LDTM), + bias, optional sigmoid, then a
+//                          128-byte-swizzled staging tile in shared memory and one TMA store (SASS UTMASTG) per 128 x 128-byte
+//                          chunk (direct stores when the output row stride is not a 16-byte multiple, e.g. N = 187)
+// Two accumulators (2 x 128 fp32 columns) live in tensor memory, so the epilogue of tile i overlaps the loads and MMAs of
+// tile i + 1; nothing is kept in registers across K.
 //
 // At the model's shapes (M = frames ~ 10^5, N <= 512, K <= 640) the layer is HBM-bound: arithmetic intensity
 // ~ 2*N*K / (2*K + 4*N) FLOP/B < the ~255 FLOP/B ridge, so the roofline that matters is bytes.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "mg_common.cuh"
@@ -49,19 +52,24 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;             // K of one tcgen05.mma for 16-bit operands
 constexpr int kMaxBlockN = 128;
-constexpr int kStages = 3;
-constexpr int kTmemCols = 128;         // power of two >= 32
-constexpr int kGemmThreads = 192;      // 6 warps
+constexpr int kStages = 4;             // smem ring of (A, B) K-blocks
+constexpr int kAccStages = 2;          // accumulators in TMEM: the epilogue of tile i overlaps the MMAs of tile i + 1
+constexpr int kTmemCols = kAccStages * kMaxBlockN;   // 256, a power of two
+constexpr int kGemmThreads = 192;      // 6 warps: TMA producer, MMA issuer, 4 epilogue warps
+constexpr int kEpilogueThreads = 128;
 constexpr uint32_t kATileBytes = kBlockM * kBlockK * 2;       // 16 KB
 constexpr uint32_t kBTileBytes = kMaxBlockN * kBlockK * 2;    // 16 KB (BLOCK_N <= 128)
 constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
-constexpr size_t kGemmSmem = kStages * kStageBytes + 1024;    // + slack to align the ring to 1024 bytes (128B swizzle)
+constexpr uint32_t kOutChunkBytes = kBlockM * 128;            // 128 rows x 128 bytes of output (32 fp32 / 64 bf16 columns)
+constexpr int kOutBuffers = 2;
+constexpr int kMaxBias = 4096 + kMaxBlockN;                  // N <= 4096 (bias staged in shared memory, padded to a tile)
+constexpr size_t kGemmSmem = kStages * kStageBytes + kOutBuffers * kOutChunkBytes + 1024;   // + slack for 1024-byte alignment
 
 struct GemmParams {
   const float* bias;
   void* y;
   int64_t ldy;
-  int M, N, K, block_n, act, y_is_bf16;
+  int M, N, K, block_n, act, y_is_bf16, tma_store, debug;
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -70,7 +78,15 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
                "l"(map), "r"(c0), "r"(c1), "r"(mg_smem_addr(bar))
                : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) { mg_mbar_expect_tx(bar, bytes); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(map), "r"(c0), "r"(c1),
+               "r"(mg_smem_addr(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mg_smem_addr(bar)) : "memory");
+}
+__device__ __forceinline__ void epilogue_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(kEpilogueThreads) : "memory"); }
 
 // K-major operand tile in shared memory, 128-byte swizzle: rows of 128 bytes, 8-row groups 1024 bytes apart.
 __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
@@ -120,27 +136,51 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 2)
+// bias + activation on 32 accumulator columns; `bias32` points at this chunk's 32 biases in shared memory (zero-padded).
+// Sigmoid as ex2 + rcp (two MUFU ops): the layer's operands are bf16, so approximate-division accuracy (~1e-7) is ample.
+__device__ __forceinline__ void finish_columns(const uint32_t (&acc)[32], float (&v)[32], const float* bias32, int act) {
+#pragma unroll
+  for (int j = 0; j < 32; j += 4) {
+    const float4 b4 = *reinterpret_cast<const float4*>(bias32 + j);
+    const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float t = __uint_as_float(acc[j + q]) + b[q];
+      if (act == MG_ACT_SIGMOID) t = __fdividef(1.f, 1.f + __expf(-t));
+      v[j + q] = t;
+    }
+  }
+}
+
+// Persistent kernel: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs that run together
+// share A tiles through L2).
+__global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
-                      const __grid_constant__ GemmParams prm) {
+                      const __grid_constant__ CUtensorMap map_y, const __grid_constant__ GemmParams prm) {
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_accum;
+  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_acc_full[kAccStages], s_acc_empty[kAccStages];
   __shared__ uint32_t s_tmem_base;
+  __shared__ __align__(16) float s_bias[kMaxBias];   // bias, zero-padded to whole tiles (zeros when there is no bias)
 
   // 128-byte swizzle wants the tiles on 1024-byte boundaries.
   unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  unsigned char* out_stage = ring + static_cast<size_t>(kStages) * kStageBytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (prm.N + prm.block_n - 1) / prm.block_n;
-  const int m0 = static_cast<int>(blockIdx.x / n_tiles) * kBlockM, n0 = static_cast<int>(blockIdx.x % n_tiles) * prm.block_n;
+  const int m_tiles = (prm.M + kBlockM - 1) / kBlockM;
+  const int total_tiles = n_tiles * m_tiles;
   const int n_kblocks = (prm.K + kBlockK - 1) / kBlockK;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
+    if (prm.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
     for (int s = 0; s < kStages; ++s) { mg_mbar_init(&s_full[s], 1); mg_mbar_init(&s_empty[s], 1); }
-    mg_mbar_init(&s_accum, 1);
+    for (int a = 0; a < kAccStages; ++a) { mg_mbar_init(&s_acc_full[a], 1); mg_mbar_init(&s_acc_empty[a], 1); }
     mg_mbar_fence_init();
   }
+  for (int i = threadIdx.x; i < kMaxBias; i += kGemmThreads)
+    s_bias[i] = (prm.bias != nullptr && i < prm.N) ? __ldg(prm.bias + i) : 0.f;
   if (warp == 2) {   // one warp owns the TMEM allocation (and frees it at the end)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mg_smem_addr(&s_tmem_base)), "n"(kTmemCols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -154,83 +194,163 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     // ===== TMA producer =====
     if (lane == 0) {
       const uint32_t stage_tx = kATileBytes + static_cast<uint32_t>(prm.block_n) * kBlockK * 2;
-      for (int kb = 0; kb < n_kblocks; ++kb) {
-        const int s = kb % kStages;
-        if (kb >= kStages) mg_mbar_wait(&s_empty[s], static_cast<uint32_t>(((kb / kStages) - 1) & 1));
-        unsigned char* a_tile = ring + static_cast<size_t>(s) * kStageBytes;
-        unsigned char* b_tile = a_tile + kATileBytes;
-        mbar_arrive_expect_tx(&s_full[s], stage_tx);
-        tma_load_2d(a_tile, &map_x, kb * kBlockK, m0, &s_full[s]);
-        tma_load_2d(b_tile, &map_w, kb * kBlockK, n0, &s_full[s]);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * prm.block_n;
+        for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+          const int s = it % kStages;
+          if (it >= kStages) mg_mbar_wait(&s_empty[s], static_cast<uint32_t>(((it / kStages) - 1) & 1));
+          unsigned char* a_tile = ring + static_cast<size_t>(s) * kStageBytes;
+          mg_mbar_expect_tx(&s_full[s], stage_tx);
+          tma_load_2d(a_tile, &map_x, kb * kBlockK, m0, &s_full[s]);
+          tma_load_2d(a_tile + kATileBytes, &map_w, kb * kBlockK, n0, &s_full[s]);
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       const uint32_t idesc = umma_instr_desc(prm.block_n);
-      for (int kb = 0; kb < n_kblocks; ++kb) {
-        const int s = kb % kStages;
-        mg_mbar_wait(&s_full[s], static_cast<uint32_t>((kb / kStages) & 1));
+      int it = 0, t = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+        const int acc = t % kAccStages;
+        if (t >= kAccStages) mg_mbar_wait(&s_acc_empty[acc], static_cast<uint32_t>(((t / kAccStages) - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_addr = mg_smem_addr(ring + static_cast<size_t>(s) * kStageBytes);
-        const uint32_t b_addr = a_addr + kATileBytes;
+        const uint32_t tmem_d = tmem_base + static_cast<uint32_t>(acc * kMaxBlockN);
+        for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
+          const int s = it % kStages;
+          mg_mbar_wait(&s_full[s], static_cast<uint32_t>((it / kStages) & 1));
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_addr = mg_smem_addr(ring + static_cast<size_t>(s) * kStageBytes);
+          const uint32_t b_addr = a_addr + kATileBytes;
 #pragma unroll
-        for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-          // advancing K by 16 elements = 32 bytes inside the 128-byte swizzle row
-          const uint64_t adesc = umma_smem_desc(a_addr + k * kUmmaK * 2);
-          const uint64_t bdesc = umma_smem_desc(b_addr + k * kUmmaK * 2);
-          umma_f16(tmem_base, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < kBlockK / kUmmaK; ++k) {
+            if (prm.debug & 2) break;
+            // advancing K by 16 elements = 32 bytes inside the 128-byte swizzle row
+            umma_f16(tmem_d, umma_smem_desc(a_addr + k * kUmmaK * 2), umma_smem_desc(b_addr + k * kUmmaK * 2), idesc,
+                     (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&s_empty[s]);     // frees the stage when the MMAs that read it are done
         }
-        umma_commit(&s_empty[s]);   // frees the stage when the MMAs that read it are done
+        umma_commit(&s_acc_full[acc]);  // accumulator of this tile complete
       }
-      umma_commit(&s_accum);        // accumulator complete
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lanes 32 * (warp % 4) .. + 31 =====
     const int quarter = warp & 3;
-    const int row = m0 + quarter * 32 + lane;
-    mg_mbar_wait(&s_accum, 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    for (int c0 = 0; c0 < prm.block_n; c0 += 32) {
-      uint32_t acc[32];
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(c0), acc);
-      if (row < prm.M) {
-        float v[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int col = n0 + c0 + j;
-          float t = __uint_as_float(acc[j]);
-          if (col < prm.N) {
-            if (prm.bias != nullptr) t += __ldg(prm.bias + col);
-            if (prm.act == MG_ACT_SIGMOID) t = 1.f / (1.f + __expf(-t));
+    const int tile_row = quarter * 32 + lane;
+    const bool issuer = threadIdx.x == 64;            // first epilogue thread issues the TMA stores
+    const int cols_per_chunk = prm.y_is_bf16 ? 64 : 32;   // 128 bytes of output per row per chunk
+    int t = 0, chunk_count = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * prm.block_n;
+      const int acc = t % kAccStages;
+      mg_mbar_wait(&s_acc_full[acc], static_cast<uint32_t>((t / kAccStages) & 1));
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kMaxBlockN);
+
+      if (prm.debug & 1) {
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        epilogue_barrier();
+        if (issuer) mbar_arrive(&s_acc_empty[acc]);
+      } else if (prm.tma_store) {
+        // registers -> 128-byte-swizzled staging tile in shared memory -> one TMA store per 128 x (32 | 64) chunk;
+        // rows / columns outside the tensor are clipped by the TMA unit.
+        for (int c0 = 0; c0 < prm.block_n; c0 += cols_per_chunk, ++chunk_count) {
+          unsigned char* stage = out_stage + static_cast<size_t>(chunk_count % kOutBuffers) * kOutChunkBytes;
+          if (chunk_count >= kOutBuffers) {   // the store that last read this buffer must have drained
+            if (issuer) mg_bulk_wait_read<kOutBuffers - 1>();
+            epilogue_barrier();
           }
-          v[j] = t;
-        }
-        const int n_valid = min(32, prm.N - (n0 + c0));
-        if (prm.y_is_bf16) {
-          __nv_bfloat16* dst = static_cast<__nv_bfloat16*>(prm.y) + static_cast<int64_t>(row) * prm.ldy + n0 + c0;
-          if (n_valid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+          uint4* dst_row = reinterpret_cast<uint4*>(stage + tile_row * 128);
+          uint32_t a0[32];
+          float v[32];
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), a0);
+          finish_columns(a0, v, s_bias + n0 + c0, prm.act);
+          if (prm.debug & 16) {
+          } else if (!prm.y_is_bf16) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __align__(16) __nv_bfloat16 h[8];
+            for (int j = 0; j < 8; ++j)
+              dst_row[j ^ (tile_row & 7)] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
+                                                       __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
+          } else {
+            uint32_t a1[32];
+            float v1[32];
+            if (c0 + 32 < prm.block_n) {
+              tmem_ld_32x32(taddr + static_cast<uint32_t>(c0 + 32), a1);
+              finish_columns(a1, v1, s_bias + n0 + c0 + 32, prm.act);
+            } else {
 #pragma unroll
-              for (int q = 0; q < 8; ++q) h[q] = __float2bfloat16_rn(v[j + q]);
-              *reinterpret_cast<uint4*>(dst + j) = *reinterpret_cast<const uint4*>(h);
+              for (int j = 0; j < 32; ++j) v1[j] = 0.f;
             }
-          } else {
-            for (int j = 0; j < n_valid; ++j) dst[j] = __float2bfloat16_rn(v[j]);
-          }
-        } else {
-          float* dst = static_cast<float*>(prm.y) + static_cast<int64_t>(row) * prm.ldy + n0 + c0;
-          if (n_valid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+            auto pack = [](float lo, float hi) {
+              const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
+              return *reinterpret_cast<const uint32_t*>(&h);
+            };
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-          } else {
-            for (int j = 0; j < n_valid; ++j) dst[j] = v[j];
+            for (int j = 0; j < 4; ++j) {
+              dst_row[j ^ (tile_row & 7)] = make_uint4(pack(v[8 * j], v[8 * j + 1]), pack(v[8 * j + 2], v[8 * j + 3]),
+                                                       pack(v[8 * j + 4], v[8 * j + 5]), pack(v[8 * j + 6], v[8 * j + 7]));
+              dst_row[(j + 4) ^ (tile_row & 7)] = make_uint4(pack(v1[8 * j], v1[8 * j + 1]), pack(v1[8 * j + 2], v1[8 * j + 3]),
+                                                             pack(v1[8 * j + 4], v1[8 * j + 5]), pack(v1[8 * j + 6], v1[8 * j + 7]));
+            }
+          }
+          if (c0 + cols_per_chunk >= prm.block_n) {   // last TMEM read of this tile: hand the accumulator back
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          }
+          mg_fence_proxy_async_smem();
+          epilogue_barrier();
+          if (issuer) {
+            if (c0 + cols_per_chunk >= prm.block_n) mbar_arrive(&s_acc_empty[acc]);
+            if (!(prm.debug & 8)) tma_store_2d(&map_y, n0 + c0, m0, stage);
+            mg_bulk_commit();
+          }
+        }
+      } else {
+        // Output rows that are not 16-byte multiples (N = 187, 199, 1, ...) cannot go through TMA: transpose each
+        // 128 x 32 chunk through a padded shared-memory tile so that a warp writes 32 consecutive columns of one row.
+        float* tile_f = reinterpret_cast<float*>(out_stage);       // [128][33]
+        const int epi_tid = threadIdx.x - 64;
+        for (int c0 = 0; c0 < prm.block_n; c0 += 32) {
+          uint32_t a0[32];
+          float v[32];
+          tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), a0);
+          finish_columns(a0, v, s_bias + n0 + c0, prm.act);
+          if (c0 + 32 >= prm.block_n) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+          if (prm.N <= 8) {
+            // a handful of output features (the N = 1 head): lane = row, neighbouring lanes write neighbouring rows
+            epilogue_barrier();
+            if (issuer && c0 + 32 >= prm.block_n) mbar_arrive(&s_acc_empty[acc]);
+            const int row = m0 + tile_row;
+            if (row < prm.M) {
+              for (int j = 0; j < prm.N - n0 - c0 && j < 32; ++j) {
+                const int64_t off = static_cast<int64_t>(row) * prm.ldy + n0 + c0 + j;
+                if (prm.y_is_bf16) static_cast<__nv_bfloat16*>(prm.y)[off] = __float2bfloat16_rn(v[j]);
+                else static_cast<float*>(prm.y)[off] = v[j];
+              }
+            }
+            continue;
+          }
+          epilogue_barrier();                                       // the previous chunk has been drained from the tile
+#pragma unroll
+          for (int j = 0; j < 32; ++j) tile_f[tile_row * 33 + j] = v[j];
+          epilogue_barrier();
+          if (issuer && c0 + 32 >= prm.block_n) mbar_arrive(&s_acc_empty[acc]);
+          const int n_valid = min(32, prm.N - (n0 + c0));
+          const int col = epi_tid & 31;
+          if (col < n_valid) {
+            for (int r = epi_tid >> 5; r < kBlockM; r += kEpilogueThreads / 32) {
+              if (m0 + r >= prm.M) break;
+              const float val = tile_f[r * 33 + col];
+              const int64_t off = static_cast<int64_t>(m0 + r) * prm.ldy + n0 + c0 + col;
+              if (prm.y_is_bf16) static_cast<__nv_bfloat16*>(prm.y)[off] = __float2bfloat16_rn(val);
+              else static_cast<float*>(prm.y)[off] = val;
+            }
           }
         }
       }
     }
+    if (issuer && prm.tma_store) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -257,15 +377,17 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-// (rows, K) bf16 row-major with row stride ld -> 2-D map, box = 64 K-elements x box_rows rows, 128-byte swizzle, zero OOB fill.
-int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t K, int64_t ld, int box_rows) {
+// (rows, cols) row-major with row stride ld elements -> 2-D map, box = box_cols x box_rows (box_cols * elem = 128 bytes),
+// 128-byte swizzle, zero fill / clipping outside the tensor.
+int make_map(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_cols, int box_rows,
+             CUtensorMapDataType dtype, int elem_bytes) {
   EncodeTiledFn encode = get_encode_fn();
   if (encode == nullptr) { mg_set_error("mg_linear_bf16: cuTensorMapEncodeTiled is not available from the driver"); return MG_ERR_CUDA; }
-  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
-  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
-  const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBlockK), static_cast<cuuint32_t>(box_rows)};
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * elem_bytes};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
   const cuuint32_t elem_strides[2] = {1, 1};
-  const CUresult rc = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, elem_strides,
+  const CUresult rc = encode(map, dtype, 2, const_cast<void*>(base), dims, strides, box, elem_strides,
                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (rc != CUDA_SUCCESS) { mg_set_error("mg_linear_bf16: cuTensorMapEncodeTiled failed with code %d", static_cast<int>(rc)); return MG_ERR_CUDA; }
@@ -297,6 +419,7 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "mg_linear_bf16: bad shape (M=%d, N=%d, K=%d)", M, N, K);
   MG_REQUIRE(act == MG_ACT_NONE || act == MG_ACT_SIGMOID, "mg_linear_bf16: unknown activation %d", act);
+  MG_REQUIRE(N <= 4096, "mg_linear_bf16: N=%d exceeds 4096 output features", N);
   if (M == 0) return MG_OK;
   MG_REQUIRE(x != nullptr && w != nullptr && y != nullptr, "mg_linear_bf16: NULL buffer");
   MG_REQUIRE(ldx % 8 == 0 && ldw % 8 == 0 && ldx >= K && ldw >= K && ldy >= N,
@@ -306,16 +429,27 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
 
   int block_n = 128;
   if (N <= 16) block_n = 16; else if (N <= 32) block_n = 32; else if (N <= 64) block_n = 64;
-  CUtensorMap map_x, map_w;
-  int rc = make_map(&map_x, x, M, K, ldx, kBlockM);
+  CUtensorMap map_x, map_w, map_y;
+  int rc = make_map(&map_x, x, M, K, ldx, kBlockK, kBlockM, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   if (rc != MG_OK) return rc;
-  rc = make_map(&map_w, w, N, K, ldw, block_n);
+  rc = make_map(&map_w, w, N, K, ldw, kBlockK, block_n, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   if (rc != MG_OK) return rc;
+  // The epilogue stores through TMA when the output rows are 16-byte multiples; otherwise (N = 187, 1, ...) directly.
+  const int y_elem = y_is_bf16 ? 2 : 4;
+  const bool tma_store = (ldy * y_elem) % 16 == 0 && mg_aligned(y, 16);
+  if (tma_store) {
+    rc = make_map(&map_y, y, M, N, ldy, 128 / y_elem, kBlockM,
+                  y_is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, y_elem);
+    if (rc != MG_OK) return rc;
+  } else {
+    map_y = map_x;   // unused
+  }
 
   GemmParams prm;
   memset(&prm, 0, sizeof(prm));
   prm.bias = bias; prm.y = y; prm.ldy = ldy;
-  prm.M = M; prm.N = N; prm.K = K; prm.block_n = block_n; prm.act = act; prm.y_is_bf16 = y_is_bf16;
+  prm.M = M; prm.N = N; prm.K = K; prm.block_n = block_n; prm.act = act; prm.y_is_bf16 = y_is_bf16; prm.tma_store = tma_store ? 1 : 0;
+  { const char* dbg = getenv("MG_GEMM_DEBUG"); prm.debug = dbg ? atoi(dbg) : 0; }
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -323,9 +457,11 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
     attr_set = true;
   }
   // n fastest: the CTAs that share an A tile are neighbours in launch order, so A is re-read from L2, not HBM.
-  const int64_t n_ctas = static_cast<int64_t>((N + block_n - 1) / block_n) * ((M + kBlockM - 1) / kBlockM);
-  MG_REQUIRE(n_ctas < (int64_t(1) << 31), "mg_linear_bf16: too many tiles");
-  linear_tcgen05_kernel<<<static_cast<unsigned>(n_ctas), kGemmThreads, kGemmSmem, stream>>>(map_x, map_w, prm);
+  const int64_t n_tiles_total = static_cast<int64_t>((N + block_n - 1) / block_n) * ((M + kBlockM - 1) / kBlockM);
+  MG_REQUIRE(n_tiles_total < (int64_t(1) << 31), "mg_linear_bf16: too many tiles");
+  const int64_t sms = mg_cached_sm_count();
+  const unsigned n_ctas = static_cast<unsigned>(n_tiles_total < sms ? n_tiles_total : sms);   // persistent: one CTA per SM
+  linear_tcgen05_kernel<<<n_ctas, kGemmThreads, kGemmSmem, stream>>>(map_x, map_w, map_y, prm);
   MG_LAUNCH_OK();
   return MG_OK;
 }
