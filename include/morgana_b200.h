@@ -76,6 +76,12 @@ int mg_upsample_norm_f32(const float* x, int64_t x_stride_b, int64_t x_stride_p,
                          const float* p0, const float* p1, int64_t param_stride_b, int norm_mode,
                          float* out, int B, int P, int D, int64_t T, int path, mg_stream_t stream);
 
+/* The same fused op with a bfloat16 output (additive; not in the reference): the exact fp32 result rounded to nearest-even,
+ * written once at half the bytes -- the activation format of the tensor-core layers (K7).  D % 8 == 0; out (B, T, D) bf16. */
+int mg_upsample_norm_f32_bf16out(const float* x, int64_t x_stride_b, int64_t x_stride_p, const int32_t* ends,
+                                 const float* p0, const float* p1, int64_t param_stride_b, int norm_mode,
+                                 void* out, int B, int P, int D, int64_t T, mg_stream_t stream);
+
 /* Dtype-agnostic expansion (the reference preserves any dtype): rows of row_bytes bytes are copied.
  * Strides in BYTES.  out is (B, T, row_bytes) contiguous. */
 int mg_upsample_bytes(const void* x, int64_t x_stride_b_bytes, int64_t x_stride_p_bytes, const int32_t* ends,

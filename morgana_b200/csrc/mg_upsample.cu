@@ -19,6 +19,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda_bf16.h>
+
 #include "mg_common.cuh"
 
 namespace {
@@ -100,14 +102,16 @@ __device__ __forceinline__ int mg_item_of_frame(const int32_t* e, int P, int64_t
 // BULK path
 // ------------------------------------------------------------------------------------------------------------------
 // Dynamic shared memory: [kUpWarps * kUpSlots rows][zero tile of zero_rows rows][ends row (int32 x P, if it fits)]
-template <int MODE>
+// OUT_BF16: the staged row is rounded to bf16 (round-to-nearest-even of the exact fp32 result) before it is replicated, so
+// the frame-rate tensor that feeds the tensor-core layers is written once at half the bytes (input rows stay fp32).
+template <int MODE, bool OUT_BF16>
 __global__ void __launch_bounds__(kUpThreads)
 upsample_bulk_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t x_sp, const int32_t* __restrict__ ends,
                      const float* __restrict__ p0, const float* __restrict__ p1, int64_t p_sb,
-                     unsigned char* __restrict__ out, int P, int nvec /* row_bytes / 16 */, int64_t T,
+                     unsigned char* __restrict__ out, int P, int nvec /* input row bytes / 16 */, int64_t T,
                      int rows_per_cta, int zero_rows) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const uint32_t row_bytes = static_cast<uint32_t>(nvec) * 16u;
+  const uint32_t row_bytes = static_cast<uint32_t>(nvec) * (OUT_BF16 ? 8u : 16u);   // OUTPUT row
   unsigned char* slots = smem;
   unsigned char* zero_tile = smem + static_cast<size_t>(kUpWarps * kUpSlots) * row_bytes;
   int32_t* smem_ends = reinterpret_cast<int32_t*>(zero_tile + static_cast<size_t>(zero_rows) * row_bytes);
@@ -127,7 +131,7 @@ upsample_bulk_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t 
   const bool has_padding = pad_begin < t1;     // CTA-uniform
   if (has_padding) {
     uint4* z = reinterpret_cast<uint4*>(zero_tile);
-    const int nz = zero_rows * nvec;
+    const int nz = static_cast<int>(zero_rows * (row_bytes / 16));
     for (int i = threadIdx.x; i < nz; i += kUpThreads) z[i] = make_uint4(0, 0, 0, 0);
     mg_fence_proxy_async_smem();
   }
@@ -177,7 +181,16 @@ upsample_bulk_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t 
 #pragma unroll
         for (int j = 0; j < kBatch; ++j) {
           const int i = i0 + 32 * j;
-          if (i < nvec) dst[i] = mg_norm_vec<MODE>(v[j], q0, q1, i);
+          if (i < nvec) {
+            const float4 r = mg_norm_vec<MODE>(v[j], q0, q1, i);
+            if (OUT_BF16) {
+              const __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+              reinterpret_cast<uint2*>(slot)[i] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo),
+                                                             *reinterpret_cast<const uint32_t*>(&hi));
+            } else {
+              dst[i] = r;
+            }
+          }
         }
       }
       mg_fence_proxy_async_smem();
@@ -341,21 +354,22 @@ int mg_rows_per_cta(int64_t T, int B, int64_t row_bytes) {
   return static_cast<int>(rows);
 }
 
-template <int MODE>
+template <int MODE, bool OUT_BF16 = false>
 int launch_bulk(const unsigned char* x, int64_t x_sb, int64_t x_sp, const int32_t* ends, const float* p0, const float* p1,
-                int64_t p_sb, unsigned char* out, int B, int P, int64_t row_bytes, int64_t T, cudaStream_t stream) {
+                int64_t p_sb, unsigned char* out, int B, int P, int64_t in_row_bytes, int64_t T, cudaStream_t stream) {
+  const int64_t row_bytes = OUT_BF16 ? in_row_bytes / 2 : in_row_bytes;   // output row
   const int rows = mg_rows_per_cta(T, B, row_bytes);
   int zero_rows = static_cast<int>((16 * 1024) / row_bytes);
   if (zero_rows < 1) zero_rows = 1;
   if (zero_rows > rows) zero_rows = rows;
   const size_t ends_bytes = (P <= kMaxEndsSmem) ? static_cast<size_t>(P) * 4 : 0;
   const size_t smem = static_cast<size_t>(kUpWarps * kUpSlots + zero_rows) * row_bytes + ends_bytes;
-  auto kernel = upsample_bulk_kernel<MODE>;
+  auto kernel = upsample_bulk_kernel<MODE, OUT_BF16>;
   if (smem > 48 * 1024) {
     MG_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
   dim3 grid(static_cast<unsigned>((T + rows - 1) / rows), static_cast<unsigned>(B));
-  kernel<<<grid, kUpThreads, smem, stream>>>(x, x_sb, x_sp, ends, p0, p1, p_sb, out, P, static_cast<int>(row_bytes / 16),
+  kernel<<<grid, kUpThreads, smem, stream>>>(x, x_sb, x_sp, ends, p0, p1, p_sb, out, P, static_cast<int>(in_row_bytes / 16),
                                               T, rows, zero_rows);
   MG_LAUNCH_OK();
   return MG_OK;
@@ -421,6 +435,31 @@ extern "C" int mg_upsample_norm_f32(const float* x, int64_t x_stride_b, int64_t 
     case MG_NORM_NONE: return launch_direct<float, MG_NORM_NONE>(xb, x_sb, x_sp, ends, p0, p1, param_stride_b, ob, B, P, row_bytes, T, stream);
     case MG_NORM_MVN: return launch_direct<float, MG_NORM_MVN>(xb, x_sb, x_sp, ends, p0, p1, param_stride_b, ob, B, P, row_bytes, T, stream);
     default: return launch_direct<float, MG_NORM_MINMAX>(xb, x_sb, x_sp, ends, p0, p1, param_stride_b, ob, B, P, row_bytes, T, stream);
+  }
+}
+
+extern "C" int mg_upsample_norm_f32_bf16out(const float* x, int64_t x_stride_b, int64_t x_stride_p, const int32_t* ends,
+                                            const float* p0, const float* p1, int64_t param_stride_b, int norm_mode,
+                                            void* out, int B, int P, int D, int64_t T, mg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MG_REQUIRE(B >= 0 && P >= 0 && D >= 0 && T >= 0, "mg_upsample_norm_f32_bf16out: negative shape");
+  MG_REQUIRE(norm_mode >= MG_NORM_NONE && norm_mode <= MG_NORM_MINMAX, "mg_upsample_norm_f32_bf16out: bad norm_mode %d", norm_mode);
+  MG_REQUIRE(B <= 65535, "mg_upsample_norm_f32_bf16out: B=%d exceeds 65535 utterances per call", B);
+  MG_REQUIRE(D % 8 == 0, "mg_upsample_norm_f32_bf16out: D=%d must be a multiple of 8 (16-byte bf16 rows)", D);
+  if (B == 0 || T == 0 || D == 0) return MG_OK;
+  MG_REQUIRE(out != nullptr && (P == 0 || (x != nullptr && ends != nullptr)), "mg_upsample_norm_f32_bf16out: NULL buffer");
+  MG_REQUIRE(norm_mode == MG_NORM_NONE || (p0 != nullptr && p1 != nullptr), "mg_upsample_norm_f32_bf16out: NULL parameters");
+  if (norm_mode == MG_NORM_NONE) { p0 = p1 = nullptr; param_stride_b = 0; }
+  const auto* xb = reinterpret_cast<const unsigned char*>(x);
+  auto* ob = static_cast<unsigned char*>(out);
+  const int64_t row_bytes = static_cast<int64_t>(D) * 4, x_sb = x_stride_b * 4, x_sp = x_stride_p * 4;
+  const bool params_ok = norm_mode == MG_NORM_NONE || (mg_aligned(p0, 16) && mg_aligned(p1, 16) && (param_stride_b % 4) == 0);
+  MG_REQUIRE(bulk_eligible(x, x_sb, x_sp, out, row_bytes, P) && params_ok,
+             "mg_upsample_norm_f32_bf16out: operands must be 16-byte aligned");
+  switch (norm_mode) {
+    case MG_NORM_NONE: return launch_bulk<MG_NORM_NONE, true>(xb, x_sb, x_sp, ends, p0, p1, param_stride_b, ob, B, P, row_bytes, T, stream);
+    case MG_NORM_MVN: return launch_bulk<MG_NORM_MVN, true>(xb, x_sb, x_sp, ends, p0, p1, param_stride_b, ob, B, P, row_bytes, T, stream);
+    default: return launch_bulk<MG_NORM_MINMAX, true>(xb, x_sb, x_sp, ends, p0, p1, param_stride_b, ob, B, P, row_bytes, T, stream);
   }
 }
 

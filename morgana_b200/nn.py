@@ -1,0 +1,60 @@
+"""Dense layers of the example models on the tcgen05 tensor cores (reference README.rst:65-73, models/RNN_SPSS.py:33-41).
+
+:class:`Linear` is a drop-in for ``torch.nn.Linear`` followed (optionally) by ``torch.nn.Sigmoid``: fp32 master weights
+(what the optimiser and the EMA kernel update), a bf16 shadow of the weight refreshed whenever the parameter changes, and
+a forward pass that is one ``mg_linear_bf16`` launch with the bias and the sigmoid fused into the epilogue.
+
+Forward tolerance (stated in tests/test_gpu_parity.py): bf16 operands, fp32 accumulation -> <= 2 % of the output range
+against the fp32 layer, 2e-3 against the exact product of the bf16-rounded operands.
+The backward pass is two plain library GEMMs (dgrad, wgrad) through ``torch.matmul`` in bf16 -- cuBLAS, as the north
+star allows for plain GEMMs; the hand-written kernel is the fused forward.
+"""
+import torch
+
+from morgana_b200 import ops
+
+
+class _LinearFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x2d, weight, bias, weight_bf16, act, out_dtype):
+        x_bf16 = ops.cast_pad_bf16(x2d) if x2d.dtype == torch.float32 else x2d
+        y = ops.linear_bf16(x_bf16, weight_bf16, bias, act=act, out_dtype=out_dtype)
+        ctx.save_for_backward(x_bf16, weight_bf16, y if act == 'sigmoid' else None)
+        ctx.act, ctx.k, ctx.has_bias, ctx.x_dtype = act, weight.shape[1], bias is not None, x2d.dtype
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        x_bf16, weight_bf16, y = ctx.saved_tensors
+        g = grad_y.to(torch.float32)
+        if ctx.act == 'sigmoid':
+            yf = y.to(torch.float32)
+            g = g * yf * (1. - yf)
+        g16 = g.to(torch.bfloat16)
+        k = ctx.k
+        grad_x = torch.matmul(g16, weight_bf16[:, :k]).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
+        grad_w = torch.matmul(g16.t(), x_bf16[:, :k]).to(torch.float32) if ctx.needs_input_grad[1] else None
+        grad_b = g.sum(dim=0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        return grad_x, grad_w, grad_b, None, None, None
+
+
+class Linear(torch.nn.Linear):
+    r"""``act(x W^T + b)`` with ``act`` in ``{None, 'sigmoid'}``; input ``(..., in_features)`` fp32 or bf16."""
+    def __init__(self, in_features, out_features, bias=True, act=None, out_dtype=torch.float32, device=None):
+        super(Linear, self).__init__(in_features, out_features, bias=bias, device=device)
+        self.act, self.out_dtype = act, out_dtype
+        self._shadow, self._shadow_version = None, None
+
+    def weight_bf16(self):
+        """bf16 copy of the weight (rows padded to a multiple of 8), rebuilt when the parameter has been updated."""
+        version = (self.weight._version, self.weight.data_ptr())
+        if self._shadow is None or self._shadow_version != version:
+            self._shadow = ops.cast_pad_bf16(self.weight.detach())
+            self._shadow_version = version
+        return self._shadow
+
+    def forward(self, x):
+        lead = x.shape[:-1]
+        x2d = x.reshape(-1, x.shape[-1])
+        y = _LinearFn.apply(x2d, self.weight, self.bias, self.weight_bf16(), self.act, self.out_dtype)
+        return y.reshape(*lead, self.out_features)

@@ -104,7 +104,7 @@ def _norm_args(norm, feat_dim, batch_size, device):
     return mode, p0, p1, 0
 
 
-def _upsample_forward(x, repeats, norm, max_len, path):
+def _upsample_forward(x, repeats, norm, max_len, path, out_dtype=None):
     _require_cuda(x, 'sequence_feature')
     if x.dim() != 3:
         raise IndexError('sequence_feature must have shape (batch_size, max_seq_len, feat_dim)')  # utils.py:196
@@ -130,6 +130,14 @@ def _upsample_forward(x, repeats, norm, max_len, path):
     mode, p0, p1, p_sb = _norm_args(norm, D, B, x.device)
     if x.stride(2) != 1 and D > 1:
         x = x.contiguous()
+    if out_dtype is not None and out_dtype != x.dtype:
+        if x.dtype != torch.float32 or out_dtype != torch.bfloat16:
+            raise TypeError('out_dtype: only float32 features -> bfloat16 frames is provided')
+        out = torch.empty((B, T, D), dtype=torch.bfloat16, device=x.device)
+        with _device_of(x):
+            check(lib.mg_upsample_norm_f32_bf16out(_ptr(x), x.stride(0), x.stride(1), _ptr(ends), _ptr(p0), _ptr(p1), p_sb, mode,
+                                                   _ptr(out), B, P, D, T, _stream()), 'mg_upsample_norm_f32_bf16out')
+        return out, ends, n_frames, (mode, p0, p1, p_sb)
     out = torch.empty((B, T, D), dtype=x.dtype, device=x.device)
     with _device_of(x):
         if x.dtype == torch.float32:
@@ -166,12 +174,12 @@ class _UpsampleFn(torch.autograd.Function):
         return grad_x, None, None, None, None
 
 
-def upsample(x, repeats, norm=None, max_len=None, path='auto', return_lengths=False):
+def upsample(x, repeats, norm=None, max_len=None, path='auto', return_lengths=False, out_dtype=None):
     """``out[b, t] = norm(x[b, item(b, t)])`` zero-padded to the longest utterance; optionally also ``n_frames``."""
-    if isinstance(x, torch.Tensor) and x.requires_grad and torch.is_grad_enabled():
+    if out_dtype is None and isinstance(x, torch.Tensor) and x.requires_grad and torch.is_grad_enabled():
         out, n_frames = _UpsampleFn.apply(x, repeats, norm, max_len, path)
     else:
-        out, _, n_frames, _ = _upsample_forward(x, repeats, norm, max_len, path)
+        out, _, n_frames, _ = _upsample_forward(x, repeats, norm, max_len, path, out_dtype)
     return (out, n_frames) if return_lengths else out
 
 

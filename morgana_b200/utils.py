@@ -10,7 +10,7 @@ from morgana_b200 import ops
 
 
 def upsample_to_repetitions(sequence_feature, repeats, normaliser=None, deltas=False, max_len=None,
-                            return_lengths=False, path='auto'):
+                            return_lengths=False, path='auto', out_dtype=None):
     r"""Copies sequence items according to ``repeats`` (per-utterance ``np.repeat``), zero-padded to the longest result.
 
     The first two arguments are the reference's (morgana/utils.py:175).  The keyword arguments are additive:
@@ -20,6 +20,8 @@ def upsample_to_repetitions(sequence_feature, repeats, normaliser=None, deltas=F
         ``upsample_to_repetitions(normaliser.normalise(sequence_feature), repeats)`` (padding stays 0).
     max_len : int, known upper bound of the output length; skips the 32-byte device->host read (no sync at all).
     return_lengths : also return ``n_frames`` (``sum(repeats, dim=1)``, int64, on the device).
+    out_dtype : ``torch.bfloat16`` writes the frames as bf16 (the exact fp32 result rounded to nearest-even) -- half the
+        bytes, and the activation format of :class:`morgana_b200.nn.Linear`.  No gradient flows through this variant.
 
     Returns ``(batch_size, max_repeated_len, feat_dim)``, same dtype, contiguous.  Raises ``TypeError`` for non-integer
     ``repeats`` and ``ValueError`` for negative ones, like the reference.
@@ -27,7 +29,8 @@ def upsample_to_repetitions(sequence_feature, repeats, normaliser=None, deltas=F
     norm = None
     if normaliser is not None:
         norm = normaliser if isinstance(normaliser, tuple) else normaliser.fused_params(deltas=deltas)
-    return ops.upsample(sequence_feature, repeats, norm=norm, max_len=max_len, path=path, return_lengths=return_lengths)
+    return ops.upsample(sequence_feature, repeats, norm=norm, max_len=max_len, path=path, return_lengths=return_lengths,
+                        out_dtype=out_dtype)
 
 
 def sequence_mask(seq_len, max_len=None, dtype=torch.ByteTensor, device=None):

@@ -491,3 +491,50 @@ def test_pad_collate_matches_host_padding(mg, D, dtype):
     assert np.array_equal(got.cpu().numpy(), want)
     got = mg.data.pad_collate(dev(packed), dev(lengths), max_len=T + 3)
     assert np.array_equal(got[:, :T].cpu().numpy(), want) and not got[:, T:].any()
+
+
+def test_nn_linear_module_forward_backward(mg):
+    """README MLP stack (600 -> 512 -> 128 -> 32 -> 1) through morgana_b200.nn.Linear against fp32 torch.nn layers."""
+    from morgana_b200 import nn as mnn
+    torch.manual_seed(0)
+    dims = [600, 512, 128, 32, 1]
+    ref = torch.nn.Sequential(*[m for i in range(4) for m in
+                                ([torch.nn.Linear(dims[i], dims[i + 1])] + ([torch.nn.Sigmoid()] if i < 3 else []))]).cuda()
+    ours = [mnn.Linear(dims[i], dims[i + 1], act='sigmoid' if i < 3 else None, device='cuda') for i in range(4)]
+    ref_linears = [m for m in ref if isinstance(m, torch.nn.Linear)]
+    for a, b in zip(ours, ref_linears):
+        a.load_state_dict(b.state_dict())
+    x = torch.rand(3, 50, 600, device='cuda')
+    xo = x.clone().requires_grad_()
+    h = xo
+    for layer in ours:
+        h = layer(h)
+    want = ref(x)
+    assert h.shape == want.shape == (3, 50, 1)
+    assert (h - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+    h.sum().backward()
+    want.sum().backward()
+    for a, b in zip(ours, ref_linears):
+        scale = b.weight.grad.abs().max().item()
+        assert (a.weight.grad - b.weight.grad).abs().max().item() <= 5e-2 * scale + 1e-4
+    # the bf16 shadow follows parameter updates
+    before = ours[0].weight_bf16().clone()
+    with torch.no_grad():
+        ours[0].weight.add_(1.0)
+    assert not torch.equal(before, ours[0].weight_bf16())
+
+
+@pytest.mark.parametrize('kind', [None, 'minmax', 'mvn'])
+def test_fused_upsample_bf16_output_is_rounded_exact_result(mg, kind):
+    rng = np.random.default_rng(17)
+    B, P, D = 6, 25, 600
+    x = rng.random((B, P, D), dtype=np.float32)
+    dur = rng.integers(0, 9, (B, P))
+    p0 = rng.standard_normal(D).astype(np.float32)
+    p1 = (p0 + np.abs(rng.standard_normal(D)) + 0.1).astype(np.float32)
+    norm = None if kind is None else (kind, dev(p0), dev(p1))
+    exact = O.upsample_to_repetitions(x, dur) if kind is None else O.normalise_upsample(x, dur, kind, p0, p1)
+    want = torch.from_numpy(exact).to(torch.bfloat16)                       # round-to-nearest-even of the exact result
+    got = mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=norm, out_dtype=torch.bfloat16)
+    assert got.dtype == torch.bfloat16 and tuple(got.shape) == exact.shape
+    assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
