@@ -14,25 +14,31 @@ import torch.nn.functional as F
 
 
 def upsample_chain(features, durations):
-    """morgana/utils.py:193-228: append a zero item, build a (B, T) index table on the host, gather."""
+    """morgana/utils.py:193-228: append a zero item, build a (B, T) index table on the host, gather.
+
+    Works on CPU tensors (the timed CPU baseline) and, like the reference, on CUDA tensors (the "stock ATen on the same
+    GPU" bar): the index table is always built on the host and uploaded (utils.py:218-222).
+    """
+    device = features.device
     n_utts, n_items, dim = features.shape
     totals = durations.sum(dim=1)                                    # :198
     longest = int(totals.max())                                      # :199 (a sync on a GPU)
-    per_item = durations.reshape(n_utts, -1)                         # :202
-    zero_item = torch.zeros(n_utts, 1, dim, dtype=features.dtype)    # :206
+    per_item = durations.reshape(n_utts, -1).cpu()                   # :202, :218 (device -> host)
+    totals_host = totals.cpu()
+    zero_item = torch.zeros(n_utts, 1, dim, dtype=features.dtype).to(device)   # :206
     extended = torch.cat([features, zero_item], dim=1)               # :207 full copy of the input
-    utt_index = torch.arange(n_utts)[:, None].repeat(1, longest)     # :210-211
+    utt_index = torch.arange(n_utts)[:, None].repeat(1, longest)     # :210-211 (stays on the CPU, Q8)
     item_index = np.full((n_utts, longest), -1, dtype=np.int64)      # :214 (-1 -> the zero item)
     positions = np.arange(n_items)
     for u in range(n_utts):                                          # :218-220 Python loop over the batch
-        item_index[u, :int(totals[u])] = np.repeat(positions, per_item[u].numpy())
-    item_index = torch.tensor(item_index)                            # :222
+        item_index[u, :int(totals_host[u])] = np.repeat(positions, per_item[u].numpy())
+    item_index = torch.tensor(item_index).to(device)                 # :222 (host -> device)
     return extended[utt_index, item_index]                           # :226 advanced-index gather
 
 
 def lengths_mask(lengths, longest, dtype):
     """morgana/utils.py:134-144."""
-    steps = torch.arange(longest).type(lengths.dtype)
+    steps = torch.arange(longest).type(lengths.dtype).to(lengths.device)
     return (steps[None, :] < lengths[:, None])[:, :, None].type(dtype)
 
 
