@@ -284,18 +284,25 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
         const float* sy = sp + stage_elems;
         float* g = GRAD ? g_body + off + tid : nullptr;
         float l_part = 0.f, m_part = 0.f;   // <= 8 rows summed in fp32 in row order, then one fp64 add
-        if (elems == stage_elems) {          // full stage (CTA-uniform): ~10 instructions per element
+        if (elems == stage_elems && lp.loss_sq && (lp.metric_sq || !lp.use_metric)) {
+          // Full stage, squared error into both slots (the mcep / lf0 / bap columns): the hot loop.  32-bit shared
+          // addresses, one product for loss and metric, gradient = d * (2 * w_row) (same single rounding as (2d) * w).
+          uint32_t pa = mg_smem_addr(sp), ya = mg_smem_addr(sy);
+          const uint32_t step = static_cast<uint32_t>(D) * 4u;
+          const float w2 = __fmul_rn(2.f, lp.w_row);
 #pragma unroll
           for (int u = 0; u < kStageRows; ++u) {
-            const float d = __fsub_rn(*sp, *sy);
-            const float sq = __fmul_rn(d, d), ab = fabsf(d);
-            l_part = __fadd_rn(l_part, lp.loss_sq ? sq : ab);
-            m_part = __fadd_rn(m_part, lp.metric_sq ? sq : ab);
-            if (GRAD) { __stcs(g, __fmul_rn(simple_slope(lp.loss_sq, d), lp.w_row)); g += D; }
-            sp += D;
-            sy += D;
+            float pv, yv;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(pv) : "r"(pa));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(yv) : "r"(ya));
+            const float d = __fsub_rn(pv, yv);
+            l_part = __fadd_rn(l_part, __fmul_rn(d, d));
+            if (GRAD) { __stcs(g, __fmul_rn(d, w2)); g += D; }
+            pa += step;
+            ya += step;
           }
-        } else {
+          m_part = l_part;
+        } else {   // partial last stage, or a column with an absolute-error program
           for (int i = tid; i < elems; i += D) {
             const float d = __fsub_rn(*sp, *sy);
             const float sq = __fmul_rn(d, d), ab = fabsf(d);
