@@ -46,9 +46,14 @@ class Linear(torch.nn.Linear):
         self._shadow, self._shadow_version = None, None
 
     def weight_bf16(self):
-        """bf16 copy of the weight (rows padded to a multiple of 8), rebuilt when the parameter has been updated."""
+        """bf16 copy of the weight (rows padded to a multiple of 8).
+
+        Rebuilt on every call in training mode -- fused optimisers update parameters without bumping the autograd version
+        counter, so staleness cannot be detected reliably, and the cast is one tiny kernel -- and cached in eval mode until
+        the parameter's version or storage changes.
+        """
         version = (self.weight._version, self.weight.data_ptr())
-        if self._shadow is None or self._shadow_version != version:
+        if self.training or self._shadow is None or self._shadow_version != version:
             self._shadow = ops.cast_pad_bf16(self.weight.detach())
             self._shadow_version = version
         return self._shadow

@@ -538,3 +538,19 @@ def test_fused_upsample_bf16_output_is_rounded_exact_result(mg, kind):
     got = mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=norm, out_dtype=torch.bfloat16)
     assert got.dtype == torch.bfloat16 and tuple(got.shape) == exact.shape
     assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
+
+
+def test_nn_linear_follows_fused_optimizer_updates(mg):
+    """Fused Adam updates parameters without bumping the autograd version counter: the bf16 shadow must still follow."""
+    from morgana_b200 import nn as mnn
+    torch.manual_seed(1)
+    layer = mnn.Linear(64, 16, device='cuda')
+    opt = torch.optim.Adam(layer.parameters(), lr=0.1, fused=True)
+    x = torch.rand(9, 64, device='cuda')
+    y0 = layer(x).detach().clone()
+    layer(x).sum().backward()
+    opt.step()
+    y1 = layer(x).detach()
+    want = torch.nn.functional.linear(x, layer.weight.detach(), layer.bias.detach())
+    assert (y1 - y0).abs().max().item() > 0.05
+    assert (y1 - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
