@@ -33,6 +33,7 @@ constexpr int kObjUnroll = 8;       // rows in flight per thread (column-per-thr
 constexpr int kStageRows = 8;       // rows per shared-memory stage (8*D floats: a multiple of 16 bytes for every D)
 constexpr int kMaxStages = 8;       // ring depth of the bulk-load pipeline
 constexpr int kMaxSpecial = 4;       // special columns served from the shared-memory side buffer
+constexpr int kSpecialInfo = 1024;   // ballot positions (32 words x 32 lanes)
 constexpr int kMaxCapture = 8;       // columns copied to the side buffer (specials, their mask columns, root groups)
 constexpr int kLanes = 2;           // column programs per thread: the streamed column + one edge element (head / tail)
 constexpr int64_t kObjTargetElems = 24576;   // elements of one operand per CTA (~96 KB)
@@ -163,6 +164,7 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
   __shared__ unsigned s_special[32];          // per 32 columns: which need general_one()
   __shared__ int s_cap_col[kMaxCapture];      // columns copied to the side buffer during the stream
   __shared__ int s_sp_col[kMaxSpecial];       // special columns served from the side buffer
+  __shared__ short s_sp_mask[kSpecialInfo], s_sp_width[kSpecialInfo];   // per special column, by ballot position
   __shared__ int s_n_cap, s_n_sp, s_n_special;
   __shared__ bool s_is_last;
 
@@ -179,11 +181,60 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
   const int rows_cap = prm.rows_per_cta;
   float* side = reinterpret_cast<float*>(smem_raw + prm.side_offset);   // [cap][rows_cap][2]
 
-  // ---- which columns are special, and which columns must be captured for them (themselves + their mask columns) ------
+  double scale = 1.;
+  if (GRAD && prm.grad_scale_dev != nullptr) scale = static_cast<double>(__ldg(prm.grad_scale_dev));
+  const double inv_rows = scale / (static_cast<double>(n_b) * prm.B);   // shared factor of the gradient in this utterance
+
+  const float* p_chunk = prm.pred + b * prm.p_sb + r0 * p_st;
+  const float* y_chunk = prm.target + b * prm.t_sb + r0 * t_st;
+  float* g_chunk = GRAD ? prm.grad + b * prm.g_sb + r0 * g_st : nullptr;
+
+  // ---- geometry of the staged stream, and its first loads: issued before anything else so that the column-program
+  // bookkeeping below runs under their latency -------------------------------------------------------------------------
+  const uintptr_t mis = reinterpret_cast<uintptr_t>(p_chunk) & 15;
+  const bool staged = n_rows > 0 && prm.n_stages > 0 && p_st == D && t_st == D && (!GRAD || g_st == D) &&
+                      (reinterpret_cast<uintptr_t>(y_chunk) & 15) == mis && !(prm.debug & 4);   // CTA-uniform
+  const int64_t total = n_rows * D;                                   // floats in this CTA's span
+  const int64_t head = min(total, static_cast<int64_t>(((16 - mis) & 15) >> 2));
+  const int64_t body = ((total - head) >> 2) << 2;                    // floats that travel through shared memory
+  const int stage_elems = kStageRows * D;
+  const int n_iter = static_cast<int>((body + stage_elems - 1) / stage_elems);
+  const int ring = prm.n_stages;
+  float* s_stage = reinterpret_cast<float*>(smem_raw);
+  const float* p_body = p_chunk + head;
+  const float* y_body = y_chunk + head;
+  auto issue = [&](int it) {   // one elected thread: both operands of stage `it` into ring slot it % ring
+    const int slot = it % ring;
+    const int64_t off = static_cast<int64_t>(it) * stage_elems;
+    const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(stage_elems), body - off)) * 4u;
+    float* dst = s_stage + static_cast<size_t>(slot) * 2 * stage_elems;
+    mg_mbar_expect_tx(&s_bar[slot], 2 * bytes);
+    mg_bulk_load(dst, p_body + off, bytes, &s_bar[slot]);
+    mg_bulk_load(dst + stage_elems, y_body + off, bytes, &s_bar[slot]);
+  };
+  if (tid == 0 && staged) {
+    for (int i = 0; i < ring; ++i) mg_mbar_init(&s_bar[i], 1);
+    mg_mbar_fence_init();
+    for (int it = 0; it < min(ring, n_iter); ++it) issue(it);
+  }
+
+  // ---- which columns are special, and which columns must be captured for them (themselves + their mask columns).
+  // Every thread reads its own column's program once (one parallel round of loads) and leaves what thread 0 needs in
+  // shared memory, so the list is built without a chain of dependent global loads. --------------------------------------
   for (int c0 = warp * 32; c0 < D; c0 += n_warps * 32) {
     const int k = c0 + lane;
-    const unsigned bits = __ballot_sync(MG_FULL_MASK, k < D && !column_is_simple(prm.cols[k < D ? k : 0]));
+    mg_column col;
+    col.loss_kind = col.metric_kind = MG_COL_NONE;
+    col.mask_col = MG_COL_NONE;
+    col.width = 1;
+    if (k < D) col = prm.cols[k];
+    const bool special = k < D && !column_is_simple(col);
+    const unsigned bits = __ballot_sync(MG_FULL_MASK, special);
     if (lane == 0) s_special[c0 >> 5] = (prm.debug & 1) ? 0u : bits;
+    if (special) {   // at most a handful of columns: park (mask column, root-group width) by position in the ballot word
+      const int slot = (c0 >> 5) * 32 + __popc(bits & ((1u << lane) - 1));
+      if (slot < kSpecialInfo) { s_sp_mask[slot] = col.mask_col; s_sp_width[slot] = col.metric_kind == MG_RED_ROOT_SQDIFF ? col.width : 1; }
+    }
   }
   __syncthreads();
   if (tid == 0) {
@@ -196,16 +247,17 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
     };
     for (int w = 0; w < (D + 31) / 32; ++w) {
       unsigned todo = s_special[w];
+      int rank_in_word = 0;
       while (todo) {
         const int k = w * 32 + __ffs(todo) - 1;
         todo &= todo - 1;
+        const int info = w * 32 + rank_in_word++;
         ++n_special;
-        if (n_sp == kMaxSpecial) continue;
-        const mg_column sc = prm.cols[k];
+        if (n_sp == kMaxSpecial || info >= kSpecialInfo) continue;
+        const int mask_col = s_sp_mask[info], width = s_sp_width[info];
         const int saved = n_cap;
-        bool ok = capture(k) >= 0 && (sc.mask_col == MG_COL_NONE || capture(sc.mask_col) >= 0);
-        if (ok && sc.metric_kind == MG_RED_ROOT_SQDIFF)
-          for (int j = 1; j < sc.width && ok; ++j) ok = capture(k + j) >= 0;
+        bool ok = capture(k) >= 0 && (mask_col == MG_COL_NONE || capture(mask_col) >= 0);
+        for (int j = 1; j < width && ok; ++j) ok = capture(k + j) >= 0;
         if (ok) s_sp_col[n_sp++] = k; else n_cap = saved;
       }
     }
@@ -214,26 +266,11 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
     s_n_special = n_special;
   }
 
-  double scale = 1.;
-  if (GRAD && prm.grad_scale_dev != nullptr) scale = static_cast<double>(__ldg(prm.grad_scale_dev));
-  const double inv_rows = scale / (static_cast<double>(n_b) * prm.B);   // shared factor of the gradient in this utterance
-
-  const float* p_chunk = prm.pred + b * prm.p_sb + r0 * p_st;
-  const float* y_chunk = prm.target + b * prm.t_sb + r0 * t_st;
-  float* g_chunk = GRAD ? prm.grad + b * prm.g_sb + r0 * g_st : nullptr;
-
   LaneProgram lanes[kLanes];
   double l_acc[kLanes], m_acc[kLanes];
 #pragma unroll
   for (int k = 0; k < kLanes; ++k) { lanes[k] = idle_lane(); l_acc[k] = 0.; m_acc[k] = 0.; }
 
-  const uintptr_t mis = reinterpret_cast<uintptr_t>(p_chunk) & 15;
-  const bool staged = prm.n_stages > 0 && p_st == D && t_st == D && (!GRAD || g_st == D) &&
-                      (reinterpret_cast<uintptr_t>(y_chunk) & 15) == mis && !(prm.debug & 4);   // CTA-uniform
-  if (tid == 0 && staged && n_rows > 0) {
-    for (int i = 0; i < prm.n_stages; ++i) mg_mbar_init(&s_bar[i], 1);
-    mg_mbar_fence_init();
-  }
   __syncthreads();   // capture list and barriers are ready
   auto capture_index = [&](int col) {
     int idx = -1;
@@ -242,30 +279,7 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
   };
 
   // ---- simple columns: the stream --------------------------------------------------------------------------------------
-  if (n_rows > 0 && staged) {
-    const int64_t total = n_rows * D;                                   // floats in this CTA's span
-    const int64_t head = min(total, static_cast<int64_t>(((16 - mis) & 15) >> 2));
-    const int64_t n_vec = (total - head) >> 2;
-    const int64_t body = n_vec << 2;                                    // floats that travel through shared memory
-    const int stage_elems = kStageRows * D;
-    const int n_iter = static_cast<int>((body + stage_elems - 1) / stage_elems);
-    const int ring = prm.n_stages;
-    float* s_stage = reinterpret_cast<float*>(smem_raw);
-    const float* p_body = p_chunk + head;
-    const float* y_body = y_chunk + head;
-
-    auto issue = [&](int it) {   // one elected thread: both operands of stage `it` into ring slot it % ring
-      const int slot = it % ring;
-      const int64_t off = static_cast<int64_t>(it) * stage_elems;
-      const uint32_t bytes = static_cast<uint32_t>(min(static_cast<int64_t>(stage_elems), body - off)) * 4u;
-      float* dst = s_stage + static_cast<size_t>(slot) * 2 * stage_elems;
-      mg_mbar_expect_tx(&s_bar[slot], 2 * bytes);
-      mg_bulk_load(dst, p_body + off, bytes, &s_bar[slot]);
-      mg_bulk_load(dst + stage_elems, y_body + off, bytes, &s_bar[slot]);
-    };
-    if (tid == 0)
-      for (int it = 0; it < min(ring, n_iter); ++it) issue(it);
-
+  if (staged) {
     // Thread t owns position t of every row of every stage, i.e. column (head + t) % D of the tensor.
     const bool active = tid < D;
     const int my_col = static_cast<int>((head + tid) % D);
