@@ -298,7 +298,7 @@ __device__ __forceinline__ void run_float_term(const mg_term& tm, int b, int64_t
   else run_strided<KIND, false>(a, tm.a_st, bb, tm.b_st, nullptr, 0, n_valid, D, 0.f, sum);
 }
 
-__global__ void __launch_bounds__(kRedThreads)
+__global__ void __launch_bounds__(kRedThreads, 4)
 masked_reduce_kernel(const __grid_constant__ ReduceParams prm) {
   __shared__ double s_red[96];
   __shared__ bool s_is_last;
