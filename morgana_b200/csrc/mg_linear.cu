@@ -5,14 +5,14 @@
 //
 // Persistent kernel, one CTA per SM walking 128 x BLOCK_N output tiles, six warps with fixed roles:
 //   warp 0  TMA producer   one lane issues cp.async.bulk.tensor (SASS UTMALDG) for the A (128 x 64) and B (BLOCK_N x 64)
-//                          bf16 tiles of each K block into a 4-stage ring, 128-byte swizzle, completion on mbarriers;
+//                          bf16 tiles of each K block into a 3-stage ring, 128-byte swizzle, completion on mbarriers;
 //                          rows / K columns outside the tensors are zero-filled by the TMA unit, so K = 600 needs no padding
-//   warp 1  MMA issuer     one lane issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BLOCK_N, K = 16) per K block
+//   warp 1  MMA issuer     one lane issues 4 x tcgen05.mma.cta_group::1.kind::f16 (M = 128, N = BLOCK_N <= 256, K = 16) per K block
 //                          (SASS UTCHMMA); tcgen05.commit releases the smem stage and publishes the accumulator
 //   warps 2-5 epilogue     tcgen05.ld 32 lanes x 32 columns at a time (SASS LDTM), + bias, optional sigmoid, then a
 //                          128-byte-swizzled staging tile in shared memory and one TMA store (SASS UTMASTG) per 128 x 128-byte
 //                          chunk (direct stores when the output row stride is not a 16-byte multiple, e.g. N = 187)
-// Two accumulators (2 x 128 fp32 columns) live in tensor memory, so the epilogue of tile i overlaps the loads and MMAs of
+// Two accumulators (2 x up to 256 fp32 columns: all 512 TMEM columns) live in tensor memory, so the epilogue of tile i overlaps the loads and MMAs of
 // tile i + 1; nothing is kept in registers across K.
 //
 // At the model's shapes (M = frames ~ 10^5, N <= 512, K <= 640) the layer is HBM-bound: arithmetic intensity
@@ -51,25 +51,26 @@ cast_pad_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* __restr
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;            // 64 bf16 = 128 bytes = one swizzle row
 constexpr int kUmmaK = 16;             // K of one tcgen05.mma for 16-bit operands
-constexpr int kMaxBlockN = 128;
-constexpr int kStages = 4;             // smem ring of (A, B) K-blocks
+constexpr int kMaxBlockN = 256;
+constexpr int kMaxStages = 6;          // smem ring of (A, B) K-blocks: 3 stages of 48 KB at BLOCK_N = 256 ... 6 of 24 KB at 64
+constexpr uint32_t kRingBytes = 144 * 1024;
 constexpr int kAccStages = 2;          // accumulators in TMEM: the epilogue of tile i overlaps the MMAs of tile i + 1
-constexpr int kTmemCols = kAccStages * kMaxBlockN;   // 256, a power of two
+constexpr int kTmemCols = kAccStages * kMaxBlockN;   // 512: all of tensor memory (one CTA per SM)
 constexpr int kGemmThreads = 192;      // 6 warps: TMA producer, MMA issuer, 4 epilogue warps
 constexpr int kEpilogueThreads = 128;
 constexpr uint32_t kATileBytes = kBlockM * kBlockK * 2;       // 16 KB
-constexpr uint32_t kBTileBytes = kMaxBlockN * kBlockK * 2;    // 16 KB (BLOCK_N <= 128)
-constexpr uint32_t kStageBytes = kATileBytes + kBTileBytes;
 constexpr uint32_t kOutChunkBytes = kBlockM * 128;            // 128 rows x 128 bytes of output (32 fp32 / 64 bf16 columns)
 constexpr int kOutBuffers = 2;
 constexpr int kMaxBias = 4096 + kMaxBlockN;                  // N <= 4096 (bias staged in shared memory, padded to a tile)
-constexpr size_t kGemmSmem = kStages * kStageBytes + kOutBuffers * kOutChunkBytes + 1024;   // + slack for 1024-byte alignment
+constexpr size_t kGemmSmem = kRingBytes + kOutBuffers * kOutChunkBytes + 1024;   // + slack for 1024-byte alignment
 
 struct GemmParams {
   const float* bias;
   void* y;
   int64_t ldy;
   int M, N, K, block_n, act, y_is_bf16, tma_store, debug;
+  int n_stages;            // ring depth for this BLOCK_N
+  uint32_t stage_bytes;    // A tile + B tile of one K block (a multiple of 1024)
 };
 
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -158,13 +159,15 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ GemmParams prm) {
   extern __shared__ unsigned char smem_dyn[];
-  __shared__ __align__(8) uint64_t s_full[kStages], s_empty[kStages], s_acc_full[kAccStages], s_acc_empty[kAccStages];
+  __shared__ __align__(8) uint64_t s_full[kMaxStages], s_empty[kMaxStages], s_acc_full[kAccStages], s_acc_empty[kAccStages];
   __shared__ uint32_t s_tmem_base;
   __shared__ __align__(16) float s_bias[kMaxBias];   // bias, zero-padded to whole tiles (zeros when there is no bias)
 
   // 128-byte swizzle wants the tiles on 1024-byte boundaries.
   unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
-  unsigned char* out_stage = ring + static_cast<size_t>(kStages) * kStageBytes;
+  unsigned char* out_stage = ring + kRingBytes;
+  const int kStages = prm.n_stages;
+  const uint32_t kStageBytes = prm.stage_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (prm.N + prm.block_n - 1) / prm.block_n;
   const int m_tiles = (prm.M + kBlockM - 1) / kBlockM;
@@ -427,8 +430,11 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
              static_cast<long long>(ldx), static_cast<long long>(ldw), static_cast<long long>(ldy));
   MG_REQUIRE(mg_aligned(x, 16) && mg_aligned(w, 16), "mg_linear_bf16: operands must be 16-byte aligned");
 
-  int block_n = 128;
-  if (N <= 16) block_n = 16; else if (N <= 32) block_n = 32; else if (N <= 64) block_n = 64;
+  // Widest tile that N fills: a 256-wide tile halves how often an A tile is fetched (the layer is bound by operand
+  // delivery, not by MMA time), at the price of idle MMA columns when N is just above 128.
+  int block_n = 256;
+  if (N <= 16) block_n = 16; else if (N <= 32) block_n = 32; else if (N <= 64) block_n = 64; else if (N <= 128) block_n = 128;
+  { const char* e = getenv("MG_GEMM_BLOCK_N"); if (e && atoi(e) > 0 && atoi(e) < block_n) block_n = atoi(e); }
   CUtensorMap map_x, map_w, map_y;
   int rc = make_map(&map_x, x, M, K, ldx, kBlockK, kBlockM, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   if (rc != MG_OK) return rc;
@@ -449,6 +455,10 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
   memset(&prm, 0, sizeof(prm));
   prm.bias = bias; prm.y = y; prm.ldy = ldy;
   prm.M = M; prm.N = N; prm.K = K; prm.block_n = block_n; prm.act = act; prm.y_is_bf16 = y_is_bf16; prm.tma_store = tma_store ? 1 : 0;
+  prm.stage_bytes = kATileBytes + static_cast<uint32_t>(block_n) * kBlockK * 2;
+  if (prm.stage_bytes % 1024) prm.stage_bytes = (prm.stage_bytes / 1024 + 1) * 1024;
+  prm.n_stages = static_cast<int>(kRingBytes / prm.stage_bytes);
+  if (prm.n_stages > kMaxStages) prm.n_stages = kMaxStages;
   { const char* dbg = getenv("MG_GEMM_DEBUG"); prm.debug = dbg ? atoi(dbg) : 0; }
 
   static bool attr_set = false;
