@@ -358,6 +358,12 @@ def run_ours(args, rank, world, local_rank):
 
     pk, pk_src = peaks()
     achieved = k2_avg_bytes / (k2_avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    traffic_path = os.path.join(ROOT, 'profiles', 'k2_traffic.json')
+    if os.path.exists(traffic_path):       # DRAM bytes of one K2 launch from the committed `ncu --set full` capture
+        with open(traffic_path) as f:
+            t = json.load(f)
+        traffic, traffic_src = t['dram_bytes_read'] + t['dram_bytes_write'], t['source']
     line = {
         'metric': METRIC, 'value': frames_done / (elapsed_ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
         'warmup': max(args.warmup, 3), 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -369,7 +375,7 @@ def run_ours(args, rank, world, local_rank):
         'gpu_launches': 3 * args.steps, 'e2e_gpu_launches_per_step': 9,
         'roofline': {'bound': 'hbm', 'kernel': 'upsample_bulk_kernel<MINMAX> (K2, fused normalise + expansion)',
                      'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / pk['hbm_gbs'],
-                     'frac_of_8000_nominal': achieved / 8000.0, 'traffic': None, 'peak_source': pk_src,
+                     'frac_of_8000_nominal': achieved / 8000.0, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk_src,
                      'algorithmic_bytes_per_launch': k2_avg_bytes, 'avg_launch_ms': k2_avg_ms,
                      'share_of_step': k2_avg_ms / (elapsed_ms / args.steps)},
     }
