@@ -264,6 +264,22 @@ int mg_ema_update_f32(float* const* shadow, const float* const* param, const int
 int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const float* bias, void* y, int64_t ldy,
                    int y_is_bf16, int M, int N, int K, int act, mg_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * K8  batched MLPG ("next" row 1 of the scope table) -- replaces viz.synthesis.MLPG (morgana/viz/synthesis.py:79-180)
+ *     with the reference's default windows [1], [-0.5, 0, 0.5], [1, -2, 1] (synthesis.py:122-127): for every utterance and
+ *     static dimension, the pentadiagonal system (sum_k W_k^T diag(1/var_k) W_k) c = sum_k W_k^T (mean_k / var_k) is built
+ *     and solved in fp64 over n + 2 * padding edge-replicated frames; c without the padding is the trajectory.
+ *
+ * means      (B, T, 3 * feat_dim) fp32, layout [static | delta | delta-delta]; strides in elements, inner contiguous.
+ * variances  same layout; per frame (v_sb, v_st as for means), per utterance (v_st = 0) or global (v_sb = v_st = 0).
+ * seq_len    (B,) int64 or NULL (all T frames).  out (B, T, feat_dim) fp32; frames past seq_len are zero.
+ * workspace  mg_mlpg_workspace_bytes(B, T, feat_dim, padding) bytes of device memory (no initialisation needed).
+ */
+int64_t mg_mlpg_workspace_bytes(int B, int64_t T, int feat_dim, int padding);
+int mg_mlpg_f32(const float* means, int64_t m_sb, int64_t m_st, const float* variances, int64_t v_sb, int64_t v_st,
+                const int64_t* seq_len, float* out, int64_t o_sb, int64_t o_st, int B, int64_t T, int feat_dim, int padding,
+                void* workspace, int64_t workspace_bytes, mg_stream_t stream);
+
 /* fp32 -> bf16 row conversion with K padding (feeds K7 from the fp32 frame-rate features; pads K to ld_out with 0). */
 int mg_cast_pad_bf16(const float* x, int64_t ldx, void* out, int64_t ld_out, int64_t rows, int K, mg_stream_t stream);
 

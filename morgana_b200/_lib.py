@@ -80,6 +80,9 @@ PROTOTYPES = {
                                         c_i64, c_void_p]),
     'mg_ema_update_f32': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_i64), c_int,
                                   c_f32, c_void_p]),
+    'mg_mlpg_workspace_bytes': (c_i64, [c_int, c_i64, c_int, c_int]),
+    'mg_mlpg_f32': (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_int, c_i64, c_int,
+                            c_int, c_void_p, c_i64, c_void_p]),
     'mg_linear_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int,
                                c_int, c_void_p]),
     'mg_cast_pad_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_void_p]),

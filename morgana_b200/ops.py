@@ -570,3 +570,52 @@ def linear_bf16(x, weight, bias=None, act=None, out_dtype=torch.float32):
         check(lib.mg_linear_bf16(_ptr(x), x.stride(0), _ptr(weight), weight.stride(0), _ptr(bias), _ptr(y), y.stride(0),
                                  int(out_dtype == torch.bfloat16), M, N, K, _ACTS[act], _stream()), 'mg_linear_bf16')
     return y
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# K8: batched MLPG
+# ----------------------------------------------------------------------------------------------------------------------
+
+_mlpg_workspaces = {}
+
+
+def mlpg(means, variances, padding_size=0, seq_len=None):
+    """Maximum-likelihood parameter generation for (B, T, 3F) [static | delta | delta-delta] means on the device.
+
+    ``variances``: (3F,) global, (B, 3F) per utterance or (B, T, 3F) per frame.  Returns (B, T, F) float32.
+    """
+    _require_cuda(means, 'means')
+    _require_cuda(variances, 'variances')
+    if means.dtype != torch.float32 or variances.dtype != torch.float32:
+        raise TypeError('mlpg takes float32 means and variances')
+    if means.dim() != 3 or means.shape[2] % 3 != 0:
+        raise ValueError('means must be (batch_size, seq_len, 3 * feat_dim)')
+    if means.stride(2) != 1:
+        means = means.contiguous()
+    B, T, D3 = means.shape
+    F = D3 // 3
+    variances = variances.contiguous()
+    if variances.dim() == 1 and variances.shape[0] == D3:
+        v_sb, v_st = 0, 0
+    elif variances.dim() == 2 and tuple(variances.shape) == (B, D3):
+        v_sb, v_st = D3, 0
+    elif variances.dim() == 3 and tuple(variances.shape) == (B, T, D3):
+        v_sb, v_st = T * D3, D3
+    else:
+        raise ValueError('variances of shape {} do not match means {}'.format(tuple(variances.shape), tuple(means.shape)))
+    if seq_len is not None:
+        seq_len = _seq_len_arg(seq_len, B, means.device)
+    out = torch.empty((B, T, F), dtype=torch.float32, device=means.device)
+    if B == 0 or T == 0 or F == 0:
+        return out
+    need = lib.mg_mlpg_workspace_bytes(B, T, F, int(padding_size))
+    key = (means.device.index, _stream())
+    ws = _mlpg_workspaces.get(key)
+    if ws is None or ws.numel() * 8 < need:
+        ws = torch.empty(((need + 7) // 8,), dtype=torch.float64, device=means.device)
+        _mlpg_workspaces[key] = ws
+    with _device_of(means):
+        check(lib.mg_mlpg_f32(_ptr(means), means.stride(0), means.stride(1), _ptr(variances), v_sb, v_st, _ptr(seq_len), _ptr(out),
+                              out.stride(0), out.stride(1), B, T, F, int(padding_size), _ptr(ws), ws.numel() * 8, _stream()),
+              'mg_mlpg_f32')
+    return out

@@ -6,8 +6,8 @@
     morgana_b200.unpatch()      # restore the reference (e.g. for a CPU oracle run)
 
 What is rebound: ``morgana.utils.upsample_to_repetitions``, ``morgana.utils.ExponentialMovingAverage``,
-``morgana.losses.mse`` / ``bce``, ``morgana.data.normalise_*`` / ``denormalise_*`` and the ``accumulate`` / ``result`` /
-``reset_state`` methods of the metric accumulators.  NumPy inputs to the normalisers (DataLoader workers) keep going
+``morgana.losses.mse`` / ``bce``, ``morgana.data.normalise_*`` / ``denormalise_*``, ``morgana.viz.synthesis.MLPG`` and the
+``accumulate`` / ``result`` / ``reset_state`` methods of the metric accumulators.  NumPy inputs to the normalisers (DataLoader workers) keep going
 through NumPy arithmetic; torch tensors must be on a CUDA device.
 """
 from morgana_b200 import data as _data
@@ -36,6 +36,11 @@ def patch(morgana=None):
     _swap(morgana.losses, 'bce', _losses.bce)
     for name in ('normalise_mvn', 'denormalise_mvn', 'normalise_minmax', 'denormalise_minmax'):
         _swap(morgana.data, name, getattr(_data, name))
+    if hasattr(morgana, 'viz') and hasattr(morgana.viz, 'synthesis'):
+        # Model scripts bind the name at import (`from morgana.viz.synthesis import MLPG`, models/RNN_SPSS.py:9), so
+        # patch() must run before they are imported for this rebinding to reach them.
+        from morgana_b200.viz import synthesis as _synthesis
+        _swap(morgana.viz.synthesis, 'MLPG', _synthesis.MLPG)
     for cls in _metrics.ACCUMULATORS:
         ref_cls = getattr(morgana.metrics, cls.__name__)
         for method in _METRIC_METHODS:

@@ -344,3 +344,58 @@ def linear(x, weight, bias=None, act=None):
     elif act is not None:
         raise ValueError(act)
     return y
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# "next" row 1: viz.synthesis.MLPG  (morgana/viz/synthesis.py:79-180)
+# PARITY UNPINNED: the reference solves the system with `bandmat` (unpinned in setup.py:12, absent from this image and
+# from /root/reference), so this restatement is checked against the definition only -- dense window matrices built as
+# synthesis.py:8-36 describes them, numpy's dense fp64 solver -- not against outputs of the reference itself.
+# ----------------------------------------------------------------------------------------------------------------
+
+MLPG_WINDOWS = [(0, 0, np.array([1.0])), (1, 1, np.array([-0.5, 0.0, 0.5])), (1, 1, np.array([1.0, -2.0, 1.0]))]   # :122-127
+
+
+def _window_matrix(left, right, coeffs, n_frames):
+    """frames x frames Toeplitz band matrix whose row t holds `coeffs` at columns t-left .. t+right (synthesis.py:24-27)."""
+    mat = np.zeros((n_frames, n_frames))
+    for j, c in enumerate(coeffs):
+        off = j - left
+        idx = np.arange(max(0, -off), min(n_frames, n_frames - off))
+        mat[idx, idx + off] = c
+    return mat
+
+
+def mlpg(means, variances, padding_size=0, seq_len=None):
+    """Most probable static trajectory given means / variances of [static | delta | delta-delta] features.
+
+    means: (B, T, 3 F); variances: (B, T, 3 F) or (3 F,) global; returns (B, T, F) float64, zeros past seq_len.
+    """
+    means = np.asarray(means, np.float64)
+    batch_size, n_frames, dim3 = means.shape
+    feat_dim = dim3 // 3
+    variances = np.asarray(variances, np.float64)
+    if variances.ndim == 1:
+        variances = np.broadcast_to(variances, means.shape)
+    if seq_len is None:
+        seq_len = [n_frames] * batch_size
+    out = np.zeros((batch_size, n_frames, feat_dim))
+    idx_base = np.arange(3) * feat_dim
+
+    def pad(x, n):   # synthesis.py:114-120: replicate the edge frames as burn-in
+        return np.concatenate([np.repeat(x[:1], n, axis=0), x, np.repeat(x[-1:], n, axis=0)], axis=0)
+
+    for i in range(batch_size):
+        n = int(seq_len[i])
+        if n == 0:
+            continue
+        m_i, v_i = pad(means[i, :n], padding_size), pad(variances[i, :n], padding_size)
+        length = n + 2 * padding_size
+        wins = [_window_matrix(l, u, c, length) for l, u, c in MLPG_WINDOWS]
+        for d in range(feat_dim):
+            mu, var = m_i[:, idx_base + d], v_i[:, idx_base + d]
+            b = sum(w.T @ (mu[:, k] / var[:, k]) for k, w in enumerate(wins))            # synthesis.py:44
+            prec = sum(w.T @ np.diag(1. / var[:, k]) @ w for k, w in enumerate(wins))    # synthesis.py:47
+            traj = np.linalg.solve(prec, b)                                               # synthesis.py:168
+            out[i, :n, d] = traj[padding_size:length - padding_size]
+    return out

@@ -554,3 +554,40 @@ def test_nn_linear_follows_fused_optimizer_updates(mg):
     want = torch.nn.functional.linear(x, layer.weight.detach(), layer.bias.detach())
     assert (y1 - y0).abs().max().item() > 0.05
     assert (y1 - want).abs().max().item() <= 2e-2 * max(1.0, want.abs().max().item())
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# "next" row 1: batched MLPG.  Parity is against the oracle's restatement of the definition (dense window matrices, dense
+# fp64 solve); the reference's own solver (bandmat) is absent here, so this row is "parity unpinned" (DESIGN.md).
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('B,T,F,pad', [(3, 40, 5, 0), (4, 57, 3, 10), (2, 120, 60, 100), (5, 33, 1, 3)])
+@pytest.mark.parametrize('var_kind', ['global', 'frame'])
+def test_mlpg_vs_oracle(mg, B, T, F, pad, var_kind):
+    from morgana_b200.viz.synthesis import MLPG
+    rng = np.random.default_rng(B * 100 + T + F + pad)
+    means = rng.standard_normal((B, T, 3 * F)).astype(np.float32)
+    seq_len = rng.integers(1, T + 1, B)
+    seq_len[0] = T
+    if var_kind == 'global':
+        var = (rng.random(3 * F) + 0.3).astype(np.float32)
+    else:
+        var = (rng.random((B, T, 3 * F)) + 0.3).astype(np.float32)
+    want = O.mlpg(means, var, padding_size=pad, seq_len=seq_len)
+    got = MLPG(dev(means), dev(var), padding_size=pad, seq_len=dev(seq_len))
+    assert got.dtype == torch.float32 and tuple(got.shape) == (B, T, F)
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-5)       # fp64 solve, fp32 output
+    for b in range(B):
+        assert not got[b, seq_len[b]:].any()                                         # out-of-sequence frames are zero
+    as_np = MLPG(means, var, padding_size=pad, seq_len=seq_len)                       # NumPy in -> NumPy out, as the reference
+    assert isinstance(as_np, np.ndarray) and as_np.dtype == np.float64
+    np.testing.assert_allclose(as_np, want, rtol=1e-5, atol=1e-5)
+
+
+def test_mlpg_static_only_limit(mg):
+    """With enormous delta variances the deltas carry no information and the trajectory is the static mean."""
+    from morgana_b200.viz.synthesis import MLPG
+    rng = np.random.default_rng(3)
+    means = rng.standard_normal((2, 50, 6)).astype(np.float32)
+    var = np.array([1., 1., 1e12, 1e12, 1e12, 1e12], np.float32)
+    got = MLPG(dev(means), dev(var), padding_size=0).cpu().numpy()
+    np.testing.assert_allclose(got, means[..., :2], rtol=1e-4, atol=1e-4)

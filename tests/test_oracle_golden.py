@@ -242,3 +242,34 @@ def test_aten_chain_objective_matches_numpy_oracle():
              O.melcep_acc(t[..., 4:64], p[..., 4:64], n), O.distortion_acc(t[..., 184:185], p[..., 184:185], n)]
     for (s, c), (ws, wc) in zip(increments, wants):
         assert c == wc and float(s) == pytest.approx(ws, rel=REL)
+
+
+def test_mlpg_oracle_against_scipy_banded_solver():
+    """The MLPG restatement (dense definition) agrees with an independent assembly + scipy's banded Cholesky solver.
+
+    The reference's own solver (bandmat) is absent, so this row stays "parity unpinned"; this test only guards the
+    oracle against its own mistakes."""
+    import scipy.linalg as sl
+    rng = np.random.default_rng(4)
+    n, pad, F = 37, 6, 2
+    means = rng.standard_normal((1, n, 3 * F))
+    var = rng.random((1, n, 3 * F)) + 0.4
+    want = O.mlpg(means, var, padding_size=pad)
+    L = n + 2 * pad
+    for d in range(F):
+        mu = np.pad(means[0][:, [d, F + d, 2 * F + d]], ((pad, pad), (0, 0)), mode='edge')
+        tau = 1. / np.pad(var[0][:, [d, F + d, 2 * F + d]], ((pad, pad), (0, 0)), mode='edge')
+        bt = mu * tau
+        ab = np.zeros((3, L))                               # upper band storage for solveh_banded
+        b = np.zeros(L)
+        wins = [{0: 1.0}, {-1: -0.5, 1: 0.5}, {-1: 1.0, 0: -2.0, 1: 1.0}]
+        for k, win in enumerate(wins):
+            for t in range(L):
+                cols = [(t + o, c) for o, c in win.items() if 0 <= t + o < L]
+                for a, ca in cols:
+                    b[a] += ca * bt[t, k]
+                    for bcol, cb in cols:
+                        if bcol >= a:
+                            ab[2 - (bcol - a), bcol] += ca * cb * tau[t, k]
+        traj = sl.solveh_banded(ab, b)
+        np.testing.assert_allclose(want[0, :, d], traj[pad:L - pad], rtol=1e-9, atol=1e-10)
