@@ -132,6 +132,50 @@ def main():
     row('C4', 'EMA update, %d parameters in %d tensors' % (n_par, len(params)), timeit(lambda: ops.ema_update(pairs, 0.001, plan=plan)),
         12 * n_par, None, stock)
 
+    # ---- "next" row 1: MLPG inside predict() (models/RNN_SPSS.py:108-118): mcep stream, 32 utterances, padding 100 ---------
+    import time
+    import numpy as np
+    import scipy.linalg as sl
+    from morgana_b200.viz.synthesis import MLPG
+    l32 = workloads.linguistic_batch(batch_size=32, seed=1234)
+    n32, T32, Fm = l32['n_frames'], int(l32['n_frames'].max()), 60
+    g = torch.Generator().manual_seed(5)
+    means = torch.randn(32, T32, 3 * Fm, generator=g)
+    var = torch.rand(3 * Fm, generator=g) + 0.3
+    means_d, var_d, n32_d = means.to(dev), var.to(dev), n32.to(dev)
+    ms = timeit(lambda: MLPG(means_d, var_d, padding_size=100, seq_len=n32_d), 10)
+
+    def cpu_mlpg():      # the reference's loop (synthesis.py:153-171) with scipy's banded Cholesky in place of bandmat
+        pad, out = 100, np.zeros((32, T32, Fm))
+        mu_all, tau = means.numpy().astype(np.float64), 1. / var.numpy().astype(np.float64)
+        for i in range(32):
+            n = int(n32[i])
+            L = n + 2 * pad
+            mu = np.pad(mu_all[i, :n], ((pad, pad), (0, 0)), mode='edge')
+            for d in range(Fm):
+                t0, t1, t2 = tau[d], tau[Fm + d], tau[2 * Fm + d]
+                b0, b1, b2 = mu[:, d] * t0, mu[:, Fm + d] * t1, mu[:, 2 * Fm + d] * t2
+                b = b0 - 2 * b2
+                b[1:] += 0.5 * b1[:-1] + b2[:-1]
+                b[:-1] += -0.5 * b1[1:] + b2[1:]
+                ab = np.zeros((3, L))
+                ab[2] = t0 + 4 * t2
+                ab[2, 1:] += 0.25 * t1 + t2
+                ab[2, :-1] += 0.25 * t1 + t2
+                ab[1, 1:] = -4 * t2
+                ab[0, 2:] = -0.25 * t1 + t2
+                out[i, :n, d] = sl.solveh_banded(ab, b)[pad:L - pad]
+        return out
+    t0 = time.perf_counter()
+    want = cpu_mlpg()
+    cpu_ms = (time.perf_counter() - t0) * 1e3
+    err = float(np.abs(MLPG(means_d, var_d, padding_size=100, seq_len=n32_d).cpu().numpy() - want).max())
+    print(json.dumps({'config': 'C4 predict()', 'op': 'MLPG, mcep stream: 32 utterances x 60 dims, padding 100 (1920 banded solves)',
+                      'ms': round(ms, 4), 'cpu_scipy_banded_ms': round(cpu_ms, 1), 'speedup_vs_cpu_loop': round(cpu_ms / ms, 1),
+                      'max_abs_difference_vs_cpu': err,
+                      'note': 'CPU leg = the reference loop with scipy.linalg.solveh_banded for bandmat (absent); excludes the '
+                              'reference\'s device<->host copies'}), flush=True)
+
     # ---- config 1 shapes at config-2 scale: README MLP forward on the frame-rate features ------------------------------
     dims = [600, 512, 128, 32, 1]
     torch.manual_seed(0)
