@@ -168,7 +168,16 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     import torch
-    sample, frames = make_cpu_sample(args.batch_size, CPU_SAMPLE_UTTS)
+    # Bounded sample: calibrate on 16 utterances, then size each step so that warm-up + K steps take about two minutes.
+    probe, probe_frames = make_cpu_sample(args.batch_size, 16)
+    cpu_pass(probe)
+    t0 = time.perf_counter()
+    cpu_pass(probe)
+    per_utt = (time.perf_counter() - t0) / 16
+    budget_s = 120.0
+    n_utts = int(budget_s / max(args.steps + args.warmup, 1) / max(per_utt, 1e-6))
+    n_utts = max(4, min(CPU_SAMPLE_UTTS, n_utts, args.batch_size))
+    sample, frames = make_cpu_sample(args.batch_size, n_utts)
     times, threads = time_cpu(sample, args.steps, args.warmup)
     total = sum(times)
     value = frames * len(times) / total
@@ -176,11 +185,11 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args, note='each step = the first %d utterances of the batch on the host CPU' % CPU_SAMPLE_UTTS),
+        'config': workload_config(args, note='each step = the first %d utterances of the batch on the host CPU' % n_utts),
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
                          'sample': '%d of %d utterances (%d valid frames) per step; reference op chain restated in '
                                    'oracle/aten_chain.py (the Python reference cannot travel to the GPU box); %s, torch %s'
-                                   % (CPU_SAMPLE_UTTS, args.batch_size, frames, cpu_model_name(), torch.__version__)},
+                                   % (n_utts, args.batch_size, frames, cpu_model_name(), torch.__version__)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }

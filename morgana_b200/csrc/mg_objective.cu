@@ -588,6 +588,7 @@ extern "C" int mg_masked_objective_f32(const float* pred, int64_t p_sb, int64_t 
   memset(&prm, 0, sizeof(prm));
   // Rows per CTA: ~96 KB per operand, but at least 4 CTAs per SM in the grid and at most kMgMaxChunks chunks.
   int64_t rows = kObjTargetElems / D;
+  { const char* e = getenv("MG_OBJ_ROWS"); if (e && atoi(e) > 0) rows = atoi(e); }
   if (rows < kObjUnroll) rows = kObjUnroll;
   if (rows > T) rows = T;
   const int64_t sms = mg_cached_sm_count();
