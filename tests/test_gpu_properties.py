@@ -1,0 +1,140 @@
+"""Property tests on the GPU path (hypothesis): ragged / empty / odd shapes against the oracle, plus the size-independent
+properties the domain offers (round trips, linearity, additivity of metric state, determinism)."""
+import numpy as np
+import pytest
+import torch
+from hypothesis import HealthCheck, given, settings, strategies as st
+
+from oracle import np_oracle as O
+
+pytestmark = pytest.mark.gpu
+COMMON = dict(deadline=None, max_examples=40, suppress_health_check=[HealthCheck.function_scoped_fixture, HealthCheck.too_slow])
+
+
+@pytest.fixture(scope='module')
+def mg():
+    import morgana_b200
+    return morgana_b200
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+@st.composite
+def ragged_batches(draw):
+    B = draw(st.integers(1, 6))
+    P = draw(st.integers(1, 14))
+    D = draw(st.sampled_from([1, 2, 3, 4, 5, 8, 12, 187, 600, 609]))
+    max_dur = draw(st.sampled_from([1, 3, 9, 40]))
+    seed = draw(st.integers(0, 2 ** 31 - 1))
+    rng = np.random.default_rng(seed)
+    dur = rng.integers(0, max_dur + 1, (B, P))
+    dur[rng.random((B, P)) < draw(st.sampled_from([0.0, 0.3, 0.9]))] = 0
+    x = rng.standard_normal((B, P, D)).astype(np.float32)
+    kind = draw(st.sampled_from([None, 'mvn', 'minmax']))
+    p0 = rng.standard_normal(D).astype(np.float32)
+    p1 = (p0 + np.abs(rng.standard_normal(D)) + 0.05).astype(np.float32) if kind == 'minmax' else \
+        (np.abs(rng.standard_normal(D)) + 0.05).astype(np.float32)
+    if kind == 'minmax' and D > 1:
+        p1[0] = p0[0]
+    return x, dur, kind, p0, p1
+
+
+@settings(**COMMON)
+@given(ragged_batches())
+def test_upsample_any_ragged_batch_bit_exact(mg, batch):
+    x, dur, kind, p0, p1 = batch
+    want = O.upsample_to_repetitions(x, dur) if kind is None else O.normalise_upsample(x, dur, kind, p0, p1)
+    norm = None if kind is None else (kind, dev(p0), dev(p1))
+    got, n_frames = mg.utils.upsample_to_repetitions(dev(x), dev(dur)[:, :, None], normaliser=norm, return_lengths=True)
+    assert tuple(got.shape) == want.shape
+    assert np.array_equal(got.cpu().numpy(), want)
+    assert np.array_equal(n_frames.cpu().numpy(), dur.sum(axis=1))
+    # frame count conservation and zero padding, independent of the oracle
+    assert int((got != 0).any(dim=2).sum()) <= int(dur.sum())
+
+
+@settings(**COMMON)
+@given(st.integers(1, 7), st.integers(1, 90), st.sampled_from([1, 3, 5, 60, 187]), st.integers(0, 2 ** 31 - 1),
+       st.sampled_from(['mse', 'l1', 'bce']))
+def test_losses_any_shape(mg, B, T, D, seed, kind):
+    rng = np.random.default_rng(seed)
+    seq_len = rng.integers(1, T + 1, B)
+    p = (rng.random((B, T, D)) * 0.98 + 0.01).astype(np.float32)
+    y = (rng.random((B, T, D)) < 0.5).astype(np.float32) if kind == 'bce' else rng.standard_normal((B, T, D)).astype(np.float32)
+    pt = dev(p).requires_grad_()
+    value = getattr(mg.losses, kind)(pt, dev(y), dev(seq_len))
+    want = O.masked_loss(p, y, seq_len, kind)
+    assert abs(value.item() - want) <= 1e-6 * abs(want) + 1e-12
+    value.backward()
+    np.testing.assert_allclose(pt.grad.cpu().numpy(), O.masked_loss_grad(p, y, seq_len, kind), rtol=3e-6, atol=1e-12)
+    assert not pt.grad[torch.arange(T, device='cuda')[None, :] >= dev(seq_len)[:, None]].any()   # padding gradient is exactly 0
+
+
+def test_normalise_denormalise_round_trip_full_size(mg):
+    """Config-3 sized tensor: denormalise(normalise(x)) returns x to fp32 rounding (the reference's 2.4e-7)."""
+    g = torch.Generator(device='cuda').manual_seed(0)
+    x = torch.randn(1024, 1200, 187, device='cuda', generator=g)
+    mean, std = torch.randn(187, device='cuda', generator=g), torch.rand(187, device='cuda', generator=g) + 0.1
+    back = mg.data.denormalise_mvn(mg.data.normalise_mvn(x, mean, std), mean, std)
+    assert (back - x).abs().max().item() <= 2e-6 * (x.abs().max().item() + 1)
+    mmin = torch.randn(187, device='cuda', generator=g)
+    mmax = mmin + torch.rand(187, device='cuda', generator=g) + 0.5
+    back = mg.data.denormalise_minmax(mg.data.normalise_minmax(x, mmin, mmax), mmin, mmax)
+    assert (back - x).abs().max().item() <= 2e-6 * (x.abs().max().item() + 1)
+
+
+def test_upsample_full_size_properties(mg):
+    """Config 2 at full size: layout properties that need no oracle (every utterance's rows are its items repeated in
+    order, the tail is zero) plus bit-equality of the bulk and direct paths and run-to-run determinism."""
+    from morgana_b200 import workloads
+    ling = workloads.linguistic_batch(batch_size=256, seed=99)
+    lab, dur = ling['lab'].cuda(), ling['dur'].cuda()
+    out, n_frames = mg.utils.upsample_to_repetitions(lab, dur, return_lengths=True)
+    assert torch.equal(n_frames.cpu(), ling['n_frames'])
+    T = out.shape[1]
+    assert T == int(ling['n_frames'].max())
+    pad_mask = torch.arange(T, device='cuda')[None, :] >= n_frames[:, None]
+    assert not out[pad_mask].any()
+    # checksum of checksums: summing frames per utterance == summing items weighted by their durations
+    frames_sum = out.double().sum(dim=1)
+    items_sum = (lab.double() * dur.double()).sum(dim=1)
+    assert torch.allclose(frames_sum, items_sum, rtol=1e-12, atol=1e-9)
+    direct = mg.utils.upsample_to_repetitions(lab, dur, path='direct')
+    again = mg.utils.upsample_to_repetitions(lab, dur)
+    assert torch.equal(out, direct) and torch.equal(out, again)
+
+
+def test_metric_state_is_additive_over_batches_and_shards(mg):
+    """sum / count are additive: one pass over 64 utterances == two passes over 32 == four shards of 16."""
+    from morgana_b200 import workloads
+    n = workloads.acoustic_lengths(batch_size=64, min_frames=50, max_frames=200, seed=3)
+    ac = workloads.acoustic_batch(n, seed=3)
+    tgt, pred, nd = ac['target'].cuda(), ac['pred'].cuda(), n.cuda()
+    whole = mg.metrics.RMSE()
+    whole.reset_state()
+    whole.accumulate(tgt, pred, seq_len=nd)
+    for parts in (2, 4):
+        split = mg.metrics.RMSE()
+        split.reset_state()
+        step = 64 // parts
+        for i in range(parts):
+            sl = slice(i * step, (i + 1) * step)
+            split.accumulate(tgt[sl], pred[sl], seq_len=nd[sl])
+        assert float(split.count) == float(whole.count)
+        assert abs(float(split.sum) - float(whole.sum)) <= 1e-6 * float(whole.sum)
+
+
+def test_ema_converges_to_the_parameters(mg):
+    """Idempotence in the limit: repeated EMA updates with fixed parameters converge to them; decay 0 copies in one step."""
+    p = [torch.randn(1000, device='cuda'), torch.randn(17, 3, device='cuda')]
+    s = [torch.zeros_like(t) for t in p]
+    mg.ops.ema_update(list(zip(s, p)), 1.0)          # decay 0  ->  shadow == param exactly
+    for a, b in zip(s, p):
+        assert torch.equal(a, b)
+    s = [torch.zeros_like(t) for t in p]
+    for _ in range(200):
+        mg.ops.ema_update(list(zip(s, p)), 0.1)
+    for a, b in zip(s, p):
+        assert (a - b).abs().max().item() <= 1e-6 * b.abs().max().item() + 1e-6
