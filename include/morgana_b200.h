@@ -106,6 +106,23 @@ int mg_pad_collate(const void* packed, const int32_t* ends, void* out, int B, in
                    mg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Sibling segment operations ("next" row 4): the same scan drives three more dtype-agnostic row movers.  Strides in BYTES.
+ *
+ * mg_pack_rows -- utils.batched_masked_select (morgana/utils.py:147-166): rows t < len_b of every utterance, back to back.
+ *     ends: (B,) int32 inclusive scan of the lengths; out: (ends[B-1], row_bytes).  The inverse of mg_pad_collate.
+ * mg_segment_ends -- utils.get_segment_ends (morgana/utils.py:287-330): out[b, s] = x[b, cumsum(lens)[b, s] - 1], zero for
+ *     empty segments.  seg_ends: (B, S) int32 inclusive scan of the segment lengths (mg_dur_scan); out: (B, S, row_bytes).
+ * mg_split_to_segments -- utils.split_to_segments (morgana/utils.py:231-284): out[b, s, j] = x[b, begin_s + j] for
+ *     j < len_s, else zero; out: (B, S, L, row_bytes) with L = the longest segment (summary of the caller's choice).
+ */
+int mg_pack_rows(const void* x, int64_t x_stride_b_bytes, int64_t x_stride_t_bytes, const int32_t* ends, void* out,
+                 int B, int64_t T, int64_t row_bytes, mg_stream_t stream);
+int mg_segment_ends(const void* x, int64_t x_stride_b_bytes, int64_t x_stride_t_bytes, const int32_t* seg_ends, void* out,
+                    int B, int S, int64_t T, int64_t row_bytes, mg_stream_t stream);
+int mg_split_to_segments(const void* x, int64_t x_stride_b_bytes, int64_t x_stride_t_bytes, const int32_t* seg_ends, void* out,
+                         int B, int S, int64_t L, int64_t T, int64_t row_bytes, mg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * K3  standalone normalise / denormalise -- replaces data.normalise_mvn, denormalise_mvn, normalise_minmax,
  *     denormalise_minmax on torch tensors (morgana/data.py:533-538, 579-590).
  *

@@ -619,3 +619,74 @@ def mlpg(means, variances, padding_size=0, seq_len=None):
                               out.stride(0), out.stride(1), B, T, F, int(padding_size), _ptr(ws), ws.numel() * 8, _stream()),
               'mg_mlpg_f32')
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# sibling segment operations ("next" row 4)
+# ----------------------------------------------------------------------------------------------------------------------
+
+def _rows3(x, what):
+    _require_cuda(x, what)
+    if x.dim() != 3:
+        raise ValueError('{} must have shape (batch_size, max_seq_len, feat_dim)'.format(what))
+    if x.shape[2] > 1 and x.stride(2) != 1:
+        x = x.contiguous()
+    es = x.element_size()
+    return x, x.stride(0) * es, x.stride(1) * es, x.shape[2] * es
+
+
+def pack_rows(x, seq_len):
+    """``(B, T, D)`` + lengths -> ``(sum(min(len, T)), D)``: the rows inside every utterance, back to back."""
+    x, sb, st, row_bytes = _rows3(x, 'sequence_feature')
+    B, T, D = x.shape
+    if not isinstance(seq_len, torch.Tensor):
+        seq_len = torch.as_tensor(np_asarray(seq_len), device=x.device)
+    _require_cuda(seq_len, 'seq_len')
+    lengths = seq_len.reshape(B).to(torch.int64).clamp(0, T)
+    ends, _, summary = dur_scan(lengths.reshape(1, B))
+    total = int(summary[2].item())                       # the output size is data dependent: one 8-byte read, as the reference's nonzero()
+    out = torch.empty((total, D), dtype=x.dtype, device=x.device)
+    with _device_of(x):
+        check(lib.mg_pack_rows(_ptr(x), sb, st, _ptr(ends), _ptr(out), B, T, row_bytes, _stream()), 'mg_pack_rows')
+    return out
+
+
+def np_asarray(a):
+    import numpy as np
+    return np.asarray(a)
+
+
+def _segment_scan(segment_lens, batch_size):
+    lens = _prepare_repeats(segment_lens, batch_size)
+    ends, _, summary = dur_scan(lens)
+    return lens, ends, summary
+
+
+def segment_ends(x, segment_lens):
+    """``out[b, s] = x[b, cumsum(lens)[b, s] - 1]``, zero for empty segments."""
+    x, sb, st, row_bytes = _rows3(x, 'sequence_feature')
+    B, T, D = x.shape
+    lens, ends, _ = _segment_scan(segment_lens, B)
+    S = lens.shape[1]
+    out = torch.empty((B, S, D), dtype=x.dtype, device=x.device)
+    with _device_of(x):
+        check(lib.mg_segment_ends(_ptr(x), sb, st, _ptr(ends), _ptr(out), B, S, T, row_bytes, _stream()), 'mg_segment_ends')
+    return out
+
+
+def split_to_segments(x, segment_lens, max_segment_len=None):
+    """``out[b, s, j] = x[b, begin_s + j]`` for ``j < len_s`` else zero; ``(B, S, longest segment, D)``."""
+    x, sb, st, row_bytes = _rows3(x, 'sequence_feature')
+    B, T, D = x.shape
+    lens, ends, summary = _segment_scan(segment_lens, B)
+    S = lens.shape[1]
+    if max_segment_len is None:
+        if int(summary[1].item()):
+            raise ValueError('segment_lens may not contain negative values.')
+        max_segment_len = int(lens.max().item()) if lens.numel() else 0     # the reference syncs here too (utils.py:256)
+    L = int(max_segment_len)
+    out = torch.empty((B, S, L, D), dtype=x.dtype, device=x.device)
+    with _device_of(x):
+        check(lib.mg_split_to_segments(_ptr(x), sb, st, _ptr(ends), _ptr(out), B, S, L, T, row_bytes, _stream()),
+              'mg_split_to_segments')
+    return out

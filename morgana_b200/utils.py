@@ -74,3 +74,22 @@ class ExponentialMovingAverage(object):
         pairs = [(self.shadow[name], param.data) for name, param in other_model.named_parameters()
                  if name in self.shadow]
         ops.ema_update(pairs, 1.0 - self.decay, plan=self._plan)
+
+
+def batched_masked_select(sequence_feature, seq_len):
+    r"""Feature vectors of all batch items that lie inside their sequence, as one ``(sum(seq_len), feat_dim)`` tensor
+    (morgana/utils.py:147-166).  One scan + one row-copy kernel instead of mask / nonzero / advanced indexing."""
+    return ops.pack_rows(sequence_feature, seq_len)
+
+
+def get_segment_ends(sequence_feature, segment_lens):
+    r"""Feature at the last position of each segment, ``(batch_size, max_num_segments, feat_dim)``; zero for empty
+    segments (morgana/utils.py:287-330)."""
+    return ops.segment_ends(sequence_feature, segment_lens)
+
+
+def split_to_segments(sequence_feature, segment_lens, max_segment_len=None):
+    r"""Splits sequences into zero-padded segments, ``(batch_size, max_num_segments, max_segment_len, feat_dim)``
+    (morgana/utils.py:231-284; its double Python loop at :272-276 becomes one gather kernel).
+    ``max_segment_len`` (additive): known longest segment, skips the device->host read."""
+    return ops.split_to_segments(sequence_feature, segment_lens, max_segment_len=max_segment_len)

@@ -399,3 +399,45 @@ def mlpg(means, variances, padding_size=0, seq_len=None):
             traj = np.linalg.solve(prec, b)                                               # synthesis.py:168
             out[i, :n, d] = traj[padding_size:length - padding_size]
     return out
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# "next" row 4: sibling segment operations  (morgana/utils.py:147-166, 231-330); pinned by tests/golden/segments.npz
+# ----------------------------------------------------------------------------------------------------------------
+
+def batched_masked_select(sequence_feature, seq_len):
+    """Rows inside each utterance's length, utterance after utterance (utils.py:147-166)."""
+    sequence_feature = np.asarray(sequence_feature)
+    n = np.minimum(np.asarray(seq_len), sequence_feature.shape[1])
+    return np.concatenate([sequence_feature[b, :max(int(n[b]), 0)] for b in range(sequence_feature.shape[0])], axis=0)
+
+
+def get_segment_ends(sequence_feature, segment_lens):
+    """Feature at the last frame of every segment; zero for empty segments (utils.py:287-330)."""
+    sequence_feature = np.asarray(sequence_feature)
+    batch_size, n_frames, feat_dim = sequence_feature.shape
+    lens = np.asarray(segment_lens).reshape(batch_size, -1)
+    ends = np.cumsum(lens, axis=1)
+    out = np.zeros((batch_size, lens.shape[1], feat_dim), dtype=sequence_feature.dtype)
+    for b in range(batch_size):
+        for s in range(lens.shape[1]):
+            if lens[b, s] > 0 and ends[b, s] - 1 < n_frames:
+                out[b, s] = sequence_feature[b, ends[b, s] - 1]
+    return out
+
+
+def split_to_segments(sequence_feature, segment_lens):
+    """(B, T, D) -> (B, S, longest segment, D), each segment's frames then zeros (utils.py:231-284)."""
+    sequence_feature = np.asarray(sequence_feature)
+    batch_size, n_frames, feat_dim = sequence_feature.shape
+    lens = np.asarray(segment_lens).reshape(batch_size, -1)
+    longest = int(lens.max()) if lens.size else 0
+    out = np.zeros((batch_size, lens.shape[1], longest, feat_dim), dtype=sequence_feature.dtype)
+    for b in range(batch_size):
+        start = 0
+        for s in range(lens.shape[1]):
+            stop = start + int(lens[b, s])
+            take = max(0, min(stop, n_frames) - start)
+            out[b, s, :take] = sequence_feature[b, start:start + take]
+            start = stop
+    return out

@@ -276,8 +276,32 @@ def linear_cases():
     return out
 
 
+def segment_cases():
+    out = {}
+    g = gen(600)
+    B, T, D, S = 4, 23, 5, 6
+    x = torch.randn(B, T, D, generator=g)
+    seq_len = torch.tensor([23, 0, 7, 15])
+    out['seg_x'], out['seg_seq_len'] = x.numpy(), seq_len.numpy()
+    out['seg_select'] = utils.batched_masked_select(x, seq_len).numpy()
+    lens = torch.randint(0, 6, (B, S), generator=g)
+    lens[1] = 0
+    lens[2, 3] = 0
+    out['seg_lens'] = lens.numpy()
+    out['seg_ends'] = utils.get_segment_ends(x, lens[:, :, None]).numpy()
+    out['seg_split'] = utils.split_to_segments(x, lens[:, :, None]).numpy()
+    xi = torch.randint(0, 50, (3, 9, 4), generator=g)
+    li = torch.tensor([[2, 3, 0, 4], [0, 0, 0, 0], [9, 0, 0, 0]])
+    out['seg_int_x'], out['seg_int_lens'] = xi.numpy(), li.numpy()
+    out['seg_int_ends'] = utils.get_segment_ends(xi, li[:, :, None]).numpy()
+    out['seg_int_split'] = utils.split_to_segments(xi, li[:, :, None]).numpy()
+    out['seg_int_select'] = utils.batched_masked_select(xi, torch.tensor([9, 1, 4])).numpy()
+    return out
+
+
 def main():
     groups = {
+        'segments': segment_cases(),
         'upsample': upsample_cases(),
         'sequence_mask': sequence_mask_cases(),
         'normalise': normaliser_cases(),

@@ -591,3 +591,40 @@ def test_mlpg_static_only_limit(mg):
     var = np.array([1., 1., 1e12, 1e12, 1e12, 1e12], np.float32)
     got = MLPG(dev(means), dev(var), padding_size=0).cpu().numpy()
     np.testing.assert_allclose(got, means[..., :2], rtol=1e-4, atol=1e-4)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# "next" row 4: sibling segment operations (bit-exact: pure row movers)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_segment_ops_golden(mg, golden):
+    g = golden('segments')
+    U = mg.utils
+    x, lens = dev(g['seg_x']), dev(g['seg_lens'])
+    assert np.array_equal(U.batched_masked_select(x, dev(g['seg_seq_len'])).cpu().numpy(), g['seg_select'])
+    assert np.array_equal(U.get_segment_ends(x, lens[:, :, None]).cpu().numpy(), g['seg_ends'])
+    assert np.array_equal(U.split_to_segments(x, lens[:, :, None]).cpu().numpy(), g['seg_split'])
+    xi, li = dev(g['seg_int_x']), dev(g['seg_int_lens'])
+    assert np.array_equal(U.get_segment_ends(xi, li).cpu().numpy(), g['seg_int_ends'])
+    assert np.array_equal(U.split_to_segments(xi, li).cpu().numpy(), g['seg_int_split'])
+    assert np.array_equal(U.batched_masked_select(xi, torch.tensor([9, 1, 4], device='cuda')).cpu().numpy(), g['seg_int_select'])
+
+
+@pytest.mark.parametrize('D', [1, 7, 600])
+def test_segment_ops_vs_oracle_and_collate_round_trip(mg, D):
+    rng = np.random.default_rng(D)
+    B, T, S = 9, 61, 8
+    x = rng.standard_normal((B, T, D)).astype(np.float32)
+    seq_len = rng.integers(0, T + 1, B)
+    lens = rng.integers(0, 12, (B, S))
+    lens[rng.random((B, S)) < 0.2] = 0
+    while (lens.sum(axis=1) > T).any():
+        lens[lens.sum(axis=1) > T] //= 2
+    U = mg.utils
+    packed = U.batched_masked_select(dev(x), dev(seq_len))
+    assert np.array_equal(packed.cpu().numpy(), O.batched_masked_select(x, seq_len))
+    # pack is the inverse of the on-device collate
+    padded = mg.data.pad_collate(packed, dev(seq_len), max_len=T).cpu().numpy()
+    mask = np.arange(T)[None, :] < seq_len[:, None]
+    assert np.array_equal(padded[mask], x[mask]) and not padded[~mask].any()
+    assert np.array_equal(U.get_segment_ends(dev(x), dev(lens)).cpu().numpy(), O.get_segment_ends(x, lens))
+    assert np.array_equal(U.split_to_segments(dev(x), dev(lens)).cpu().numpy(), O.split_to_segments(x, lens))

@@ -273,3 +273,15 @@ def test_mlpg_oracle_against_scipy_banded_solver():
                             ab[2 - (bcol - a), bcol] += ca * cb * tau[t, k]
         traj = sl.solveh_banded(ab, b)
         np.testing.assert_allclose(want[0, :, d], traj[pad:L - pad], rtol=1e-9, atol=1e-10)
+
+
+def test_segment_ops_bit_exact(golden):
+    g = golden('segments')
+    x, lens = g['seg_x'], g['seg_lens']
+    assert np.array_equal(O.batched_masked_select(x, g['seg_seq_len']), g['seg_select'])
+    assert np.array_equal(O.get_segment_ends(x, lens[:, :, None]), g['seg_ends'])
+    assert np.array_equal(O.split_to_segments(x, lens[:, :, None]), g['seg_split'])
+    xi, li = g['seg_int_x'], g['seg_int_lens']
+    assert np.array_equal(O.get_segment_ends(xi, li), g['seg_int_ends'])
+    assert np.array_equal(O.split_to_segments(xi, li), g['seg_int_split'])
+    assert np.array_equal(O.batched_masked_select(xi, np.array([9, 1, 4])), g['seg_int_select'])
