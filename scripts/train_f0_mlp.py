@@ -78,6 +78,8 @@ def main():
     ap.add_argument('--ema-decay', type=float, default=0.999)
     ap.add_argument('--seed', type=int, default=1234)
     ap.add_argument('--no-cpu-reference', action='store_true')
+    ap.add_argument('--graph', action='store_true', help='capture the whole training step in one CUDA graph (static shapes: '
+                    'every batch is padded to the longest utterance of the run) and replay it')
     args = ap.parse_args()
     rank, world = int(os.environ.get('RANK', '0')), int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
@@ -96,6 +98,18 @@ def main():
         batches.append({'lab': gb['lab'][lo:hi].to(dev), 'dur': gb['dur'][lo:hi].to(dev), 'n_frames': gb['n_frames'][lo:hi].to(dev),
                         'target': gb['target'][lo:hi, :T].contiguous().to(dev), 'T': T, 'frames': int(gb['n_frames'][lo:hi].sum())})
     mmin, mmax = global_batches[0]['mmin'].to(dev), global_batches[0]['mmax'].to(dev)
+    if args.graph:
+        # static shapes for capture: one (P, T) for the whole run; the kernels take the padded length as `max_len` and
+        # mask by n_frames, so padding changes no result
+        P_max, T_max = max(b['lab'].shape[1] for b in batches), max(b['T'] for b in batches)
+        for b in batches:
+            pad_p = P_max - b['lab'].shape[1]
+            b['lab'] = torch.nn.functional.pad(b['lab'], (0, 0, 0, pad_p))
+            b['dur'] = torch.nn.functional.pad(b['dur'], (0, 0, 0, pad_p))
+            b['target'] = torch.nn.functional.pad(b['target'], (0, 0, 0, T_max - b['T']))
+            b['T'] = T_max
+        static = {k: torch.empty_like(batches[0][k]) for k in ('lab', 'dur', 'n_frames', 'target')}
+        static['T'] = T_max
 
     ref_model = build_reference_model(args.seed)          # same initial weights as the CPU leg
     linears = [m for m in ref_model if isinstance(m, torch.nn.Linear)]
@@ -109,7 +123,7 @@ def main():
         for mine, avg, src in zip(layers, ema_layers, linears):
             mine.load_state_dict(src.state_dict())
             avg.load_state_dict(src.state_dict())
-        optimiser = torch.optim.Adam(layers.parameters(), lr=args.lr, fused=True)
+        optimiser = torch.optim.Adam(layers.parameters(), lr=args.lr, fused=True, capturable=args.graph)
         metric = mg.metrics.RMSE()
         metric.reset_state()
         return optimiser, mg.utils.ExponentialMovingAverage(ema_layers, args.ema_decay), metric
@@ -149,6 +163,36 @@ def main():
         train_step(batches[step % n_batches])               # initial weights with a fresh optimiser / EMA / metric
     opt, ema, rmse = fresh_state()
     losses = []
+    graph, static_loss = None, None
+    if args.graph:
+        # Capture once (after a few eager steps on a side stream, as torch.cuda.graphs asks), replay per step: the ~60
+        # launches of a step (scan, expansion, 4 + 8 GEMMs, reductions, Adam, EMA, metric, all-reduce) become one submit.
+        def load(b):
+            for k in ('lab', 'dur', 'n_frames', 'target'):
+                static[k].copy_(b[k])
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for step in range(3):
+                load(batches[step % n_batches])
+                train_step(static)
+        torch.cuda.current_stream().wait_stream(side)
+        # Back to the initial state IN PLACE: anything allocated or zero-initialised during capture would be re-zeroed by
+        # every replay (Adam's moments and step counter, a metric record), so they are created by the warm-up above and only
+        # reset here.
+        for mine, avg, src in zip(layers, ema_layers, linears):
+            mine.load_state_dict(src.state_dict())
+            avg.load_state_dict(src.state_dict())
+        for state in opt.state.values():
+            for value in state.values():
+                if isinstance(value, torch.Tensor):
+                    value.zero_()
+        rmse.reset_state()
+        rmse.accumulate(static['target'], torch.zeros_like(static['target']), seq_len=torch.zeros_like(static['n_frames']))
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = train_step(static)
+        # the capture pass itself did not execute: state is still the fresh one
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -157,7 +201,12 @@ def main():
     start.record()
     for step in range(args.steps):
         b = batches[step % n_batches]
-        losses.append(train_step(b))
+        if graph is None:
+            losses.append(train_step(b))
+        else:
+            load(b)
+            graph.replay()
+            losses.append(static_loss.clone())
         frames += b['frames']
     stop.record()
     torch.cuda.synchronize()
@@ -174,7 +223,8 @@ def main():
         ms, frames = t.item(), f.item()
     packed = dp.allreduce_records(rmse._record)             # global RMSE from additive (sum, count)
     if rank == 0:
-        line = {'config': 'C1/C5 README F0 MLP training, %d utterances / rank / step' % args.batch_size, 'n_gpus': world,
+        line = {'config': 'C1/C5 README F0 MLP training, %d utterances / rank / step%s' % (args.batch_size, ', CUDA graph' if args.graph else ''),
+                'n_gpus': world,
                 'steps': args.steps, 'ms_per_step': round(ms, 3), 'valid_frames_per_s': round(frames / (ms * args.steps) * 1e3),
                 'loss_first_last': [round(loss_values[0].item(), 5), round(loss_values[-1].item(), 5)],
                 'train_rmse': round(float((packed[0, 0] / (packed[0, 1] + 1e-8)) ** 0.5), 5),
