@@ -241,7 +241,12 @@ def main():
                          'tolerance_note': 'bf16 operands in the four layers, fp32 everywhere else: losses within 1e-3 relative of '
                                            'the fp32 CPU trajectory, step-0 gradients within 1 % of their range'})
         print(json.dumps(line), flush=True)
+    if graph is not None:               # a captured NCCL all-reduce must be released before the process group goes away
+        torch.cuda.synchronize()
+        graph.reset()
+        del graph
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
