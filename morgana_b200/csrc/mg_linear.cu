@@ -68,7 +68,7 @@ struct GemmParams {
   const float* bias;
   void* y;
   int64_t ldy;
-  int M, N, K, block_n, act, y_is_bf16, tma_store, debug;
+  int M, N, K, block_n, act, y_is_bf16, tma_store;
   int n_stages;            // ring depth for this BLOCK_N
   uint32_t stage_bytes;    // A tile + B tile of one K block (a multiple of 1024)
 };
@@ -228,7 +228,6 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           const uint32_t b_addr = a_addr + kATileBytes;
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-            if (prm.debug & 2) break;
             // advancing K by 16 elements = 32 bytes inside the 128-byte swizzle row
             umma_f16(tmem_d, umma_smem_desc(a_addr + k * kUmmaK * 2), umma_smem_desc(b_addr + k * kUmmaK * 2), idesc,
                      (kb | k) != 0 ? 1u : 0u);
@@ -252,11 +251,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + static_cast<uint32_t>(acc * kMaxBlockN);
 
-      if (prm.debug & 1) {
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        epilogue_barrier();
-        if (issuer) mbar_arrive(&s_acc_empty[acc]);
-      } else if (prm.tma_store) {
+      if (prm.tma_store) {
         // registers -> 128-byte-swizzled staging tile in shared memory -> one TMA store per 128 x (32 | 64) chunk;
         // rows / columns outside the tensor are clipped by the TMA unit.
         for (int c0 = 0; c0 < prm.block_n; c0 += cols_per_chunk, ++chunk_count) {
@@ -270,8 +265,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           float v[32];
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), a0);
           finish_columns(a0, v, s_bias + n0 + c0, prm.act);
-          if (prm.debug & 16) {
-          } else if (!prm.y_is_bf16) {
+          if (!prm.y_is_bf16) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               dst_row[j ^ (tile_row & 7)] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
@@ -305,7 +299,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           epilogue_barrier();
           if (issuer) {
             if (c0 + cols_per_chunk >= prm.block_n) mbar_arrive(&s_acc_empty[acc]);
-            if (!(prm.debug & 8)) tma_store_2d(&map_y, n0 + c0, m0, stage);
+            tma_store_2d(&map_y, n0 + c0, m0, stage);
             mg_bulk_commit();
           }
         }
@@ -459,7 +453,6 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
   if (prm.stage_bytes % 1024) prm.stage_bytes = (prm.stage_bytes / 1024 + 1) * 1024;
   prm.n_stages = static_cast<int>(kRingBytes / prm.stage_bytes);
   if (prm.n_stages > kMaxStages) prm.n_stages = kMaxStages;
-  { const char* dbg = getenv("MG_GEMM_DEBUG"); prm.debug = dbg ? atoi(dbg) : 0; }
 
   static bool attr_set = false;
   if (!attr_set) {

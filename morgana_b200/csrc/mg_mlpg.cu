@@ -62,42 +62,38 @@ __global__ void mlpg_kernel(const MlpgParams prm) {
     bt = m / v;
   };
 
-  // ---- pass 1: P (three diagonals) and b for every frame; no loop-carried dependence -----------------------------------
+  // ---- pass 1: P (three diagonals) and b for every frame; no loop-carried dependence.  Frames are taken four at a time:
+  // the (mean, variance) pairs of frames a0-1 .. a0+4 for the three windows are all requested before any arithmetic, so the
+  // loads of a batch overlap instead of paying one memory latency per frame. -----------------------------------------------
   // window coefficients at offsets (-1, 0, +1): w0 = (0, 1, 0), w1 = (-0.5, 0, 0.5), w2 = (1, -2, 1)
-  for (int64_t a = 0; a < L; ++a) {
-    double bt0, tau0;
-    load(a, 0, bt0, tau0);
-    double p0 = tau0, p1 = 0., p2 = 0., b = bt0;
-    double bt, tau;
-    // frame a itself: coefficient c_0
-    load(a, 2, bt, tau);
-    p0 += 4.0 * tau;            // c_0^2 = 4
-    b += -2.0 * bt;
-    if (a + 1 < L) p1 += -2.0 * tau;          // c_0 * c_{+1} * tau[a]   (w2: -2 * 1)
-    // w1 has c_0 = 0: nothing from frame a
-    if (a >= 1) {               // frame a - 1 reaches column a through c_{+1}
-      load(a - 1, 1, bt, tau);
-      p0 += 0.25 * tau;
-      b += 0.5 * bt;
-      load(a - 1, 2, bt, tau);
-      p0 += tau;
-      b += bt;
+  constexpr int kP1 = 4;
+  for (int64_t a0 = 0; a0 < L; a0 += kP1) {
+    double bt[3][kP1 + 2], tau[3][kP1 + 2];     // index j <-> frame a0 - 1 + j
+#pragma unroll
+    for (int j = 0; j < kP1 + 2; ++j) {
+      const int64_t t = a0 - 1 + j;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        if (t >= 0 && t < L && !(k == 0 && (j == 0 || j == kP1 + 1))) load(t, k, bt[k][j], tau[k][j]);
+        else { bt[k][j] = 0.; tau[k][j] = 0.; }     // outside the sequence: the truncated window rows contribute nothing
+      }
     }
-    if (a + 1 < L) {            // frame a + 1 reaches column a through c_{-1}
-      load(a + 1, 1, bt, tau);
-      p0 += 0.25 * tau;
-      b += -0.5 * bt;
-      if (a + 2 < L) p2 += -0.25 * tau;       // c_{-1} * c_{+1} * tau[a+1]   (w1: -0.5 * 0.5)
-      load(a + 1, 2, bt, tau);
-      p0 += tau;
-      b += bt;
-      p1 += -2.0 * tau;                       // c_{-1} * c_0 * tau[a+1]      (w2: 1 * -2)
-      if (a + 2 < L) p2 += tau;               // c_{-1} * c_{+1} * tau[a+1]   (w2: 1 * 1)
+#pragma unroll
+    for (int u = 0; u < kP1; ++u) {
+      const int64_t a = a0 + u;
+      if (a >= L) break;
+      const int j = u + 1;
+      const bool has_next = a + 1 < L, has_next2 = a + 2 < L;
+      // zeros stand in for frames outside [0, L): exactly the terms the truncated Toeplitz matrices drop
+      double p0 = tau[0][j] + 4.0 * tau[2][j] + 0.25 * tau[1][j - 1] + tau[2][j - 1] + 0.25 * tau[1][j + 1] + tau[2][j + 1];
+      double p1 = has_next ? -2.0 * tau[2][j] - 2.0 * tau[2][j + 1] : 0.;
+      double p2 = has_next2 ? -0.25 * tau[1][j + 1] + tau[2][j + 1] : 0.;
+      double bsum = bt[0][j] - 2.0 * bt[2][j] + 0.5 * bt[1][j - 1] + bt[2][j - 1] - 0.5 * bt[1][j + 1] + bt[2][j + 1];
+      W(a, 0) = p0;
+      W(a, 1) = p1;
+      W(a, 2) = p2;
+      W(a, 3) = bsum;
     }
-    W(a, 0) = p0;
-    W(a, 1) = p1;
-    W(a, 2) = p2;
-    W(a, 3) = b;
   }
 
   // ---- pass 2: L D L^T factorisation + forward substitution, operands streamed in batches ------------------------------

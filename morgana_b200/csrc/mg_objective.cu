@@ -11,16 +11,19 @@
 //   184 of 187 columns) are streamed through shared memory by the TMA engine: the span is cut into stages of 8 rows
 //   (8*D floats, a multiple of 16 bytes for any D); one elected thread keeps a ring of stages in flight with
 //   cp.async.bulk global->shared (SASS UBLKCP) completing on mbarriers, so the bytes in flight live in shared memory,
-//   not in registers (~215 KB per SM with 3 CTAs).  Thread t reads positions t, t + D, t + 2D, ... of every stage: always
+//   not in registers (2 stages x 5 co-resident CTAs per SM at D = 187).  Thread t reads positions t, t + D, t + 2D, ... of every stage: always
 //   the same column, so its program is a few per-thread constants, shared-memory reads are conflict-free, and each byte
 //   of pred / target crosses HBM once.  The gradient is written straight from registers, coalesced.
 //   (Fallback when pred / target / grad disagree on 16-byte alignment or rows are strided: thread = column, 8 rows in flight.)
 //
-//   "Special" columns (BCE, exp, equality, per-frame root, voiced weighting; 3 of 187) would make their warp a 16x
-//   straggler, so after the stream the WHOLE CTA shares each of them, one row per thread (the data is L2-hot).
+//   "Special" columns (BCE, exp, equality, per-frame root, voiced weighting; 3 of 187) carry ~100 instructions per
+//   element and would make their warp a 16x straggler.  While a stage sits in shared memory one warp copies the special
+//   columns' operands (and their mask columns) into a small side buffer; after the stream the WHOLE CTA evaluates them,
+//   one row per thread, with a single CTA-wide reduction.
 //
-// Determinism: per-thread fp64 accumulators -> per-slot CTA sum (fixed shuffle tree, warps in order) -> special columns
-// added in column order -> per-CTA slot in the workspace -> last CTA (integer ticket) combines in index order.
+// Determinism: per-thread fp64 accumulators -> per-slot CTA sum (entries in index order, fixed shuffle tree) -> special
+// columns added in column order -> per-CTA slot in the workspace -> the last CTA of each utterance folds its chunks, the last
+// of those combines the utterances (integer tickets only; mg_finish.cuh).
 #include <stdlib.h>
 #include <string.h>
 
@@ -49,7 +52,6 @@ struct ObjectiveParams {
   MgWorkspace ws;
   int64_t p_sb, p_st, t_sb, t_st, g_sb, g_st, T;
   int D, B, n_slots, rows_per_cta;
-  int debug;        // MG_OBJ_DEBUG bitmask (profiling experiments only): 1 skip specials, 2 skip finish, 4 skip stream
   int side_offset;  // byte offset of the side buffer in dynamic shared memory
   int n_stages;     // ring depth of the staged stream (0: staged path not applicable, use the column-per-thread loop)
 };
@@ -193,7 +195,7 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
   // bookkeeping below runs under their latency -------------------------------------------------------------------------
   const uintptr_t mis = reinterpret_cast<uintptr_t>(p_chunk) & 15;
   const bool staged = n_rows > 0 && prm.n_stages > 0 && p_st == D && t_st == D && (!GRAD || g_st == D) &&
-                      (reinterpret_cast<uintptr_t>(y_chunk) & 15) == mis && !(prm.debug & 4);   // CTA-uniform
+                      (reinterpret_cast<uintptr_t>(y_chunk) & 15) == mis;   // CTA-uniform
   const int64_t total = n_rows * D;                                   // floats in this CTA's span
   const int64_t head = min(total, static_cast<int64_t>(((16 - mis) & 15) >> 2));
   const int64_t body = ((total - head) >> 2) << 2;                    // floats that travel through shared memory
@@ -230,7 +232,7 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
     if (k < D) col = prm.cols[k];
     const bool special = k < D && !column_is_simple(col);
     const unsigned bits = __ballot_sync(MG_FULL_MASK, special);
-    if (lane == 0) s_special[c0 >> 5] = (prm.debug & 1) ? 0u : bits;
+    if (lane == 0) s_special[c0 >> 5] = bits;
     if (special) {   // at most a handful of columns: park (mask column, root-group width) by position in the ballot word
       const int slot = (c0 >> 5) * 32 + __popc(bits & ((1u << lane) - 1));
       if (slot < kSpecialInfo) { s_sp_mask[slot] = col.mask_col; s_sp_width[slot] = col.metric_kind == MG_RED_ROOT_SQDIFF ? col.width : 1; }
@@ -563,7 +565,6 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
       prm.ws.partials[(static_cast<int64_t>(tid) * prm.B + b) * kMgMaxChunks + chunk] = make_double2(s_slot_sum[tid], s_slot_cnt[tid]);
   }
 
-  if (prm.debug & 2) return;
   mg_finish(prm.slots, prm.n_slots, prm.seq_len, prm.B, T, prm.ws, b, gridDim.x, s_red, &s_is_last);
 }
 
@@ -636,7 +637,6 @@ extern "C" int mg_masked_objective_f32(const float* pred, int64_t p_sb, int64_t 
   if (ring < 2) ring = (2 * stage_pair_bytes + side_bytes <= 200 * 1024) ? 2 : 0;
   if (force_fallback) ring = 0;
   prm.n_stages = ring;
-  { const char* dbg = getenv("MG_OBJ_DEBUG"); prm.debug = dbg ? atoi(dbg) : 0; }
   size_t ring_bytes = static_cast<size_t>(ring) * stage_pair_bytes;
   const size_t reduce_bytes = static_cast<size_t>(kLanes) * threads * (2 * sizeof(double) + 2);
   if (ring_bytes < reduce_bytes) ring_bytes = reduce_bytes;     // the slot-sum scratch reuses the ring

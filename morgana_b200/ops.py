@@ -640,7 +640,7 @@ def pack_rows(x, seq_len):
     x, sb, st, row_bytes = _rows3(x, 'sequence_feature')
     B, T, D = x.shape
     if not isinstance(seq_len, torch.Tensor):
-        seq_len = torch.as_tensor(np_asarray(seq_len), device=x.device)
+        seq_len = torch.as_tensor(seq_len, device=x.device)
     _require_cuda(seq_len, 'seq_len')
     lengths = seq_len.reshape(B).to(torch.int64).clamp(0, T)
     ends, _, summary = dur_scan(lengths.reshape(1, B))
@@ -649,11 +649,6 @@ def pack_rows(x, seq_len):
     with _device_of(x):
         check(lib.mg_pack_rows(_ptr(x), sb, st, _ptr(ends), _ptr(out), B, T, row_bytes, _stream()), 'mg_pack_rows')
     return out
-
-
-def np_asarray(a):
-    import numpy as np
-    return np.asarray(a)
 
 
 def _segment_scan(segment_lens, batch_size):
