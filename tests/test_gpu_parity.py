@@ -628,3 +628,18 @@ def test_segment_ops_vs_oracle_and_collate_round_trip(mg, D):
     assert np.array_equal(padded[mask], x[mask]) and not padded[~mask].any()
     assert np.array_equal(U.get_segment_ends(dev(x), dev(lens)).cpu().numpy(), O.get_segment_ends(x, lens))
     assert np.array_equal(U.split_to_segments(dev(x), dev(lens)).cpu().numpy(), O.split_to_segments(x, lens))
+
+
+def test_torch_custom_ops_match_the_direct_path(mg, golden):
+    g = golden('upsample')
+    x, dur, want = dev(g['ups_lab600_f32_x']), dev(g['ups_lab600_f32_dur']), g['ups_lab600_f32_out']
+    got = torch.ops.morgana_b200.upsample_norm(x, dur, None, None, 'none', -1)
+    assert np.array_equal(got.cpu().numpy(), want)
+    gl = golden('losses')
+    p, y, n = dev(gl['loss_wide_pred']), dev(gl['loss_wide_tgt']), dev(gl['loss_wide_seq_len'])
+    value = torch.ops.morgana_b200.masked_loss(p, y, n, 'mse')
+    assert rel_err(value.item(), gl['loss_wide_mse_masked']) <= REL
+    s, q = torch.randn(100, device='cuda'), torch.randn(100, device='cuda')
+    want_s = O.ema_update(s.cpu().numpy().copy(), q.cpu().numpy(), 0.99)
+    torch.ops.morgana_b200.ema_update([s], [q], 1.0 - 0.99)
+    assert np.array_equal(s.cpu().numpy(), want_s)

@@ -131,3 +131,15 @@ def test_sequence_mask_matches_golden(mg, golden):
     seq_len = torch.from_numpy(g['mask_seq_len'])
     assert np.array_equal(mg.utils.sequence_mask(seq_len).numpy(), g['mask_default'])
     assert np.array_equal(mg.utils.sequence_mask(seq_len, max_len=7, dtype=torch.float32).numpy(), g['mask_len7_f32'])
+
+
+def test_torch_ops_are_registered_for_cuda_only(mg):
+    """The dispatcher knows the operators and has no CPU kernel for them: CPU tensors cannot fall back to anything."""
+    from morgana_b200 import torch_ops
+    for name in torch_ops.OPERATORS:
+        assert hasattr(torch.ops.morgana_b200, name)
+    x = torch.zeros(2, 3, 4)
+    with pytest.raises(NotImplementedError):
+        torch.ops.morgana_b200.upsample_norm(x, torch.ones(2, 3, dtype=torch.long), None, None, 'none', -1)
+    with pytest.raises(NotImplementedError):
+        torch.ops.morgana_b200.masked_loss(x, x, None, 'mse')
