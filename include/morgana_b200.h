@@ -163,6 +163,7 @@ int mg_normalise_f32(const float* x, const float* p0, const float* p1, int norm_
 #define MG_RED_XOR 6         /* a ^ b on uint8/bool   Error (exact integer sum) */
 #define MG_RED_AND 7         /* a & b on uint8/bool   Accuracy */
 #define MG_RED_EQ 8          /* (a == b) ? 1 : 0      V/UV accuracy as models/RNN_SPSS.py:127 builds it, fused */
+#define MG_RED_SQ 9          /* a * a                 Variance / StandardDeviation (morgana/metrics.py:427-442), with MG_RED_SUM */
 
 /* Fuse the `output_features['vuv'] > 0.5` of models/RNN_SPSS.py:122 into the reduction instead of a separate pass: */
 #define MG_FLAG_M_GT_HALF 1 /* the per-frame weight is (m > 0.5) ? 1 : 0 */
@@ -176,7 +177,7 @@ struct mg_term_result;
 
 typedef struct mg_term {
   const void* a; /* (B, T, D) view: element (b, t, d) at a + b*a_sb + t*a_st + d */
-  const void* b; /* second operand or NULL (MG_RED_SUM) */
+  const void* b; /* second operand or NULL (MG_RED_SUM, MG_RED_SQ) */
   const void* m; /* optional per-frame weight (B, T) -- F0Distortion's is_voiced; NULL = 1 */
   float* grad;   /* optional (B, T, D) gradient w.r.t. a (loss kinds), strides g_sb / g_st */
   const float* grad_scale_dev; /* optional device scalar multiplied into the gradient (upstream grad_output) */

@@ -48,6 +48,8 @@ __device__ __forceinline__ float elem_fwd(float a, float b) {
     return __fsub_rn(__fmul_rn(__fsub_rn(b, 1.f), log_1mp), __fmul_rn(b, log_p));
   } else if constexpr (KIND == MG_RED_SUM) {
     return a;
+  } else if constexpr (KIND == MG_RED_SQ) {
+    return __fmul_rn(a, a);
   } else if constexpr (KIND == MG_RED_SQDIFF_EXP) {
     const float d = __fsub_rn(expf(a), expf(b));   // full-precision expf, as torch.exp (metrics.py:631-632)
     return __fmul_rn(d, d);
@@ -69,7 +71,7 @@ __device__ __forceinline__ float elem_bwd(float a, float b) {
   }
 }
 
-__host__ __device__ constexpr bool kind_has_b(int kind) { return kind != MG_RED_SUM; }
+__host__ __device__ constexpr bool kind_has_b(int kind) { return kind != MG_RED_SUM && kind != MG_RED_SQ; }
 
 // ---- contiguous rows: flat 16-byte stream with an alignment peel -----------------------------------------------------
 template <int KIND, bool GRAD>
@@ -335,6 +337,7 @@ masked_reduce_kernel(const __grid_constant__ ReduceParams prm) {
           case MG_RED_BCE: run_float_term<MG_RED_BCE>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
           case MG_RED_SUM: run_float_term<MG_RED_SUM>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
           case MG_RED_ROOT_SQDIFF: run_float_term<MG_RED_ROOT_SQDIFF>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
+          case MG_RED_SQ: run_float_term<MG_RED_SQ>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
           default: run_float_term<MG_RED_SQDIFF_EXP>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
         }
       }
@@ -395,7 +398,7 @@ extern "C" int mg_masked_reduce(const mg_term* terms, int n_terms, const int64_t
   for (int i = 0; i < n_terms; ++i) {
     const mg_term& tm = terms[i];
     MG_REQUIRE(tm.D >= 1, "mg_masked_reduce: term %d has D=%d", i, tm.D);
-    MG_REQUIRE(tm.kind >= MG_RED_SQDIFF && tm.kind <= MG_RED_EQ, "mg_masked_reduce: term %d has unknown kind %d", i, tm.kind);
+    MG_REQUIRE(tm.kind >= MG_RED_SQDIFF && tm.kind <= MG_RED_SQ, "mg_masked_reduce: term %d has unknown kind %d", i, tm.kind);
     MG_REQUIRE(tm.a != nullptr || T == 0, "mg_masked_reduce: term %d has a NULL operand", i);
     MG_REQUIRE(tm.result != nullptr && mg_aligned(tm.result, 16), "mg_masked_reduce: term %d needs a 16-byte aligned result record", i);
     const bool discrete = tm.ab_dtype == MG_DT_U8 || tm.kind == MG_RED_EQ;
@@ -406,7 +409,7 @@ extern "C" int mg_masked_reduce(const mg_term* terms, int n_terms, const int64_t
     } else {
       MG_REQUIRE(tm.kind != MG_RED_XOR && tm.kind != MG_RED_AND, "mg_masked_reduce: term %d: XOR / AND need uint8 operands", i);
     }
-    MG_REQUIRE(tm.kind == MG_RED_SUM || tm.b != nullptr || T == 0, "mg_masked_reduce: term %d needs a second operand", i);
+    MG_REQUIRE(!kind_has_b(tm.kind) || tm.b != nullptr || T == 0, "mg_masked_reduce: term %d needs a second operand", i);
     if (tm.grad != nullptr) {
       MG_REQUIRE(tm.kind == MG_RED_SQDIFF || tm.kind == MG_RED_ABSDIFF || tm.kind == MG_RED_BCE,
                  "mg_masked_reduce: term %d: kind %d has no gradient", i, tm.kind);

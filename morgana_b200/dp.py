@@ -20,6 +20,29 @@ def shard_range(n_items, rank, world_size):
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def sharded_batches(n_items, batch_size, rank, world_size, drop_last=True):
+    """This rank's batches as ``[(begin, end), ...]`` index ranges into the global utterance list.
+
+    Rank r owns the contiguous shard :func:`shard_range` gives it and walks it in order.  Every rank gets the SAME number
+    of steps (a collective per step must not dead-lock): with ``drop_last`` all batches hold exactly ``batch_size``
+    utterances -- so the mean over a batch composes into the global mean -- and the remainder of each
+    shard is dropped; otherwise the shard is cut into ``ceil(largest shard / batch_size)`` near-equal batches.
+    """
+    if batch_size < 1 or world_size < 1 or not 0 <= rank < world_size:
+        raise ValueError('bad batch_size / rank / world_size')
+    begin, end = shard_range(n_items, rank, world_size)
+    smallest, largest = n_items // world_size, -(-n_items // world_size)
+    if drop_last:
+        steps = smallest // batch_size
+        return [(begin + i * batch_size, begin + (i + 1) * batch_size) for i in range(steps)]
+    steps = -(-largest // batch_size)
+    out = []
+    for i in range(steps):
+        lo, hi = shard_range(end - begin, i, steps)
+        out.append((begin + lo, begin + hi))
+    return out
+
+
 def pack_records(*record_blocks):
     """(n_i, 48) uint8 record blocks -> one (sum_i n_i, 3) float64 tensor of [sum, count, loss] (a copy)."""
     rows = [block.reshape(-1, 48).view(torch.float64)[:, :3] for block in record_blocks]

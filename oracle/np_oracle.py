@@ -301,6 +301,31 @@ def accuracy_acc(target, pred, seq_len=None):
     return _masked_sum_count(np.bitwise_and(np.asarray(target), np.asarray(pred)), seq_len)
 
 
+def variance_acc(tensor, seq_len=None):
+    """Variance.accumulate (metrics.py:427-442): increments of (sum, sum_square, count)."""
+    total, count = _masked_sum_count(tensor, seq_len)
+    total_sq, _ = _masked_sum_count(np.asarray(tensor, np.float64) ** 2, seq_len)
+    return total, total_sq, count
+
+
+def variance_result(total, total_sq, count):
+    """Variance.result (metrics.py:444-446)."""
+    count = count + 1e-8
+    return (total_sq - total ** 2 / count) / count
+
+
+def tensor_history(batches, feat_dim, max_len=None):
+    """TensorHistory (metrics.py:302-321): valid rows of every accumulate call concatenated, last `max_len` kept.
+    `batches` is a list of (tensor, seq_len or None)."""
+    history = np.zeros((0, feat_dim), dtype=np.asarray(batches[0][0]).dtype)
+    for tensor, seq_len in batches:
+        rows = np.asarray(tensor).reshape(-1, feat_dim) if seq_len is None else batched_masked_select(tensor, seq_len)
+        history = np.concatenate([history, rows])
+        if max_len is not None:
+            history = history[-max_len:]
+    return history
+
+
 def mean_result(total, count):
     """Mean.result (metrics.py:396-397)."""
     return total / (count + 1e-8)
@@ -398,6 +423,42 @@ def mlpg(means, variances, padding_size=0, seq_len=None):
             prec = sum(w.T @ np.diag(1. / var[:, k]) @ w for k, w in enumerate(wins))    # synthesis.py:47
             traj = np.linalg.solve(prec, b)                                               # synthesis.py:168
             out[i, :n, d] = traj[padding_size:length - padding_size]
+    return out
+
+
+def mlpg_banded(means, variances, padding_size=0, seq_len=None):
+    """The same trajectories through the reference's loop structure (synthesis.py:153-171: one banded Cholesky solve per
+    utterance and static dimension) with scipy's `solveh_banded` standing in for the absent `bandmat`.  Global variances
+    (3 F,) only.  This is the CPU cost model of MLPG inside predict(); `mlpg` above is the definition it is tested against.
+    """
+    import scipy.linalg as sl
+    means = np.asarray(means, np.float64)
+    batch_size, n_frames, dim3 = means.shape
+    feat_dim = dim3 // 3
+    tau = 1. / np.asarray(variances, np.float64)
+    if seq_len is None:
+        seq_len = [n_frames] * batch_size
+    out = np.zeros((batch_size, n_frames, feat_dim))
+    pad = padding_size
+    for i in range(batch_size):
+        n = int(seq_len[i])
+        if n == 0:
+            continue
+        length = n + 2 * pad
+        mu = np.pad(means[i, :n], ((pad, pad), (0, 0)), mode='edge')
+        for d in range(feat_dim):
+            t0, t1, t2 = tau[d], tau[feat_dim + d], tau[2 * feat_dim + d]
+            b0, b1, b2 = mu[:, d] * t0, mu[:, feat_dim + d] * t1, mu[:, 2 * feat_dim + d] * t2
+            rhs = b0 - 2 * b2                                   # W^T (mu / var) for windows [1], [-.5, 0, .5], [1, -2, 1]
+            rhs[1:] += 0.5 * b1[:-1] + b2[:-1]
+            rhs[:-1] += -0.5 * b1[1:] + b2[1:]
+            ab = np.zeros((3, length))                          # upper band storage of W^T diag(1 / var) W
+            ab[2] = t0 + 4 * t2
+            ab[2, 1:] += 0.25 * t1 + t2
+            ab[2, :-1] += 0.25 * t1 + t2
+            ab[1, 1:] = -4 * t2
+            ab[0, 2:] = -0.25 * t1 + t2
+            out[i, :n, d] = sl.solveh_banded(ab, rhs)[pad:length - pad]
     return out
 
 

@@ -236,6 +236,53 @@ def metric_cases():
     return out
 
 
+def metric_extra_cases():
+    """Variance / StandardDeviation (metrics.py:400-471), TensorHistory (:263-356) and the Handler container (:52-185)."""
+    out = {}
+    g = gen(350)
+    B, T, D = 4, 13, 5
+    batches = []
+    for i in range(2):
+        seq_len = torch.randint(1, T + 1, (B,), generator=g)
+        x = 2. + torch.randn(B, T, D, generator=g)
+        y = x + 0.3 * torch.randn(B, T, D, generator=g)
+        batches.append((seq_len, x, y))
+        out['mx_b%d_seq_len' % i], out['mx_b%d_x' % i], out['mx_b%d_y' % i] = seq_len.numpy(), x.numpy(), y.numpy()
+    for masked in (True, False):
+        tag = 'masked' if masked else 'full'
+        var, std = metrics.Variance(), metrics.StandardDeviation()
+        hist, hist_short = metrics.TensorHistory(D), metrics.TensorHistory(D, max_len=7)
+        for seq_len, x, _ in batches:
+            # Variance zeroes the padding of its input in place (metrics.py:436): give it a clone.
+            var.accumulate(x.clone(), seq_len=seq_len if masked else None)
+            std.accumulate(x.clone(), seq_len=seq_len if masked else None)
+            hist.accumulate(x, seq_len=seq_len if masked else None)
+            hist_short.accumulate(x, seq_len=seq_len if masked else None)
+        out['mx_var_%s_sum' % tag] = var.sum.numpy()
+        out['mx_var_%s_sum_square' % tag] = var.sum_square.numpy()
+        out['mx_var_%s_count' % tag] = np.asarray(float(var.count))
+        out['mx_var_%s_result' % tag] = var.result().numpy()
+        out['mx_std_%s_result' % tag] = std.result().numpy()
+        out['mx_hist_%s' % tag] = hist.result().numpy()
+        out['mx_hist_short_%s' % tag] = hist_short.result().numpy()
+    # Handler: the container models use as `self.metrics` (base_models.py), driven as models/RNN_SPSS.py:124-129 does.
+    handler = metrics.Handler(loss=metrics.Mean())
+    handler.add_metrics('all', err=metrics.RMSE(), mae=metrics.MAE())
+    handler.add_metrics('valid', spread=metrics.Variance())
+    for mode in ('train', 'valid'):
+        handler.reset_state(mode)
+        for seq_len, x, y in batches:
+            kwargs = dict(err=(x, y, seq_len), mae=(x, y, {'seq_len': seq_len}), loss=torch.mean(x))   # 0-dim, as experiment_builder.py:484
+            if mode == 'valid':
+                kwargs['spread'] = (x.clone(), seq_len)
+            handler.accumulate(mode, **kwargs)
+        for name, value in handler.results_as_json_dict(mode).items():
+            out['mx_handler_%s_%s' % (mode, name)] = np.asarray(value)
+    out['mx_handler_train_names'] = np.asarray(sorted(handler['train'].keys()))
+    out['mx_handler_valid_names'] = np.asarray(sorted(handler['valid'].keys()))
+    return out
+
+
 def ema_cases():
     out = {}
     g = gen(400)
@@ -307,6 +354,7 @@ def main():
         'normalise': normaliser_cases(),
         'losses': loss_cases(),
         'metrics': metric_cases(),
+        'metrics_extra': metric_extra_cases(),
         'ema': ema_cases(),
         'linear': linear_cases(),
     }

@@ -307,6 +307,87 @@ def test_metrics_golden(mg, golden, name, masked):
         assert torch.equal(b['voiced'], before)
 
 
+@pytest.mark.parametrize('masked', [True, False])
+def test_variance_and_tensor_history_golden(mg, golden, masked):
+    """Variance / StandardDeviation (metrics.py:400-471) and TensorHistory (:263-356) against the reference's outputs."""
+    g = golden('metrics_extra')
+    tag = 'masked' if masked else 'full'
+    M = mg.metrics
+    var, std = M.Variance(), M.StandardDeviation()
+    hist, hist_short = M.TensorHistory(5), M.TensorHistory(5, max_len=7)
+    for i in range(2):
+        x = dev(g['mx_b%d_x' % i])
+        before = x.clone()
+        seq_len = dev(g['mx_b%d_seq_len' % i]) if masked else None
+        for metric in (var, std, hist, hist_short):
+            metric.accumulate(x, seq_len=seq_len)
+        assert torch.equal(x, before)                      # the reference zeroes the padding in place; we do not
+    assert float(var.count) == float(g['mx_var_%s_count' % tag])
+    assert rel_err(var.sum, g['mx_var_%s_sum' % tag]) <= REL
+    assert rel_err(var.sum_square, g['mx_var_%s_sum_square' % tag]) <= REL
+    # the reference forms sum_square - sum^2 / count in fp32 (cancellation ~5x here); ours forms it in fp64
+    assert rel_err(var.result(), g['mx_var_%s_result' % tag]) <= 1e-5
+    want_std = float(g['mx_std_%s_result' % tag])
+    if np.isnan(want_std):                                 # frames-vs-elements count quirk (Q2), pinned as is
+        assert np.isnan(float(std.result()))
+    else:
+        assert rel_err(std.result(), want_std) <= 1e-5
+    assert np.array_equal(hist.result().cpu().numpy(), g['mx_hist_%s' % tag])            # row packing: bit-exact
+    assert np.array_equal(hist_short.result().cpu().numpy(), g['mx_hist_short_%s' % tag])
+    assert str(hist).startswith('N(')
+
+
+def test_metric_handler_golden(mg, golden):
+    """The container as a model drives it: `metrics.accumulate(mode, name=(tensors..., seq_len))`
+    (models/RNN_SPSS.py:124-129) plus the 0-dim batch loss of experiment_builder.py:484."""
+    g = golden('metrics_extra')
+    M = mg.metrics
+    handler = M.Handler(loss=M.Mean())
+    handler.add_metrics('all', err=M.RMSE(), mae=M.MAE())
+    handler.add_metrics('valid', spread=M.Variance())
+    assert sorted(handler['train']) == list(g['mx_handler_train_names'])
+    assert sorted(handler['valid']) == list(g['mx_handler_valid_names'])
+    with pytest.raises(ValueError, match='No collection found'):
+        handler.accumulate('', loss=torch.zeros((), device='cuda'))
+    for mode in ('train', 'valid'):
+        handler.reset_state(mode)
+        assert handler.results_as_json_dict(mode) == {}                      # everything hidden until accumulated
+        for i in range(2):
+            x, y, seq_len = (dev(g['mx_b%d_%s' % (i, k)]) for k in ('x', 'y', 'seq_len'))
+            kwargs = dict(err=(x, y, seq_len), mae=(x, y, {'seq_len': seq_len}), loss=torch.mean(x))
+            if mode == 'valid':
+                kwargs['spread'] = (x, seq_len)
+            handler.accumulate(mode, **kwargs)
+        results = handler.results_as_json_dict(mode)
+        assert sorted(results) == sorted(handler[mode])
+        for name, value in results.items():
+            tol = 1e-5 if name == 'spread' else REL
+            assert rel_err(value, g['mx_handler_%s_%s' % (mode, name)]) <= tol, (mode, name)
+        assert set(handler.results_as_str_dict(mode)) == set(results)
+    assert ' | ' in str(handler)
+
+
+def test_metrics_accept_any_shape_without_seq_len(mg):
+    """Without seq_len the reference reduces any shape (count += numel), e.g. the 0-dim batch loss."""
+    rng = np.random.default_rng(3)
+    M = mg.metrics
+    loss = M.Mean()
+    values = rng.standard_normal(5).astype(np.float32)
+    for v in values:
+        loss.accumulate(dev(np.asarray(v)))
+    assert float(loss.count) == 5. and rel_err(loss.result(), values.astype(np.float64).mean()) <= REL
+    a, b = rng.standard_normal((7, 11)).astype(np.float32), rng.standard_normal((7, 11)).astype(np.float32)
+    rmse, dist = M.RMSE(), M.Distortion()
+    rmse.reset_state()
+    rmse.accumulate(dev(a), dev(b))
+    assert float(rmse.count) == 77. and rel_err(rmse.sum, ((a.astype(np.float64) - b) ** 2).sum()) <= REL
+    dist.accumulate(dev(a), dev(b))
+    assert float(dist.count) == 7.
+    assert rel_err(dist.sum, np.sqrt(((a.astype(np.float64) - b) ** 2).sum(-1)).sum()) <= REL
+    with pytest.raises(ValueError):
+        rmse.accumulate(dev(a), dev(b), seq_len=dev(np.array([3] * 7)))
+
+
 def test_metrics_full_size_vs_oracle(mg):
     """Config 3 shape (reduced batch): 187-dim targets, static-column metrics of models/RNN_SPSS.py:124-129."""
     rng = np.random.default_rng(7)

@@ -126,6 +126,42 @@ def test_patch_and_unpatch_rebind_reference_names(mg):
     assert not hasattr(fake.metrics.RMSE, 'result')
 
 
+def test_metric_containers_host_logic(mg):
+    """Handler / Print / History bookkeeping (morgana/metrics.py:52-260) needs no device."""
+    M = mg.metrics
+    calls = []
+
+    class Probe(M.StatefulMetric):
+        def accumulate(self, *args, **kwargs):
+            M.StatefulMetric.accumulate(self)
+            calls.append((args, kwargs))
+
+        def result(self, *args):
+            return len(calls)
+
+    handler = M.Handler(a=Probe(), hidden=Probe(hidden=True))
+    handler.add_metrics('valid', v=Probe())
+    handler.add_collection('extra', from_collections=('valid',))
+    assert set(handler['train']) == {'a', 'hidden'} and set(handler['valid']) == {'a', 'hidden', 'v'}
+    assert set(handler['extra']) == {'a', 'hidden', 'v'} and set(handler.metrics) == {'a', 'hidden', 'v'}
+    handler.accumulate('valid', a=(1, 2, {'seq_len': 3}), v=7, hidden=(8,))
+    assert calls == [((1, 2), {'seq_len': 3}), ((7,), {}), ((8,), {})]
+    assert handler.results_as_json_dict('valid') == {'a': 3, 'v': 3}           # the hidden metric is not reported
+    assert handler.results_as_str_dict('valid', prefix='p_') == {'p_a': '3', 'p_v': '3'}
+    handler.reset_state('valid')
+    assert handler.results_as_json_dict('valid') == {}
+    with pytest.raises(ValueError):
+        handler['nope']
+    last, hist = M.Print(), M.History(max_len=2)
+    for v in (1, 2, 3):
+        last.accumulate(v)
+        hist.accumulate([v, -v])                                               # History extends by an iterable
+    assert last.result() == 3 and hist.result() == [3, -3] and str(hist) == '-3' and hist.result_as_json() == '-3'
+    th = M.TensorHistory(3, max_len=4)
+    th.accumulate(torch.arange(18.).reshape(2, 3, 3))                         # no seq_len: a plain reshape, CPU is fine
+    assert th.result().shape == (4, 3) and th.result()[-1].tolist() == [15., 16., 17.]
+
+
 def test_sequence_mask_matches_golden(mg, golden):
     g = golden('sequence_mask')
     seq_len = torch.from_numpy(g['mask_seq_len'])

@@ -156,6 +156,32 @@ def test_metric_accumulators(golden, name, masked):
     assert result == pytest.approx(float(g[key + '_result']), rel=REL)
 
 
+@pytest.mark.parametrize('masked', [True, False])
+def test_variance_and_tensor_history(golden, masked):
+    g = golden('metrics_extra')
+    tag = 'masked' if masked else 'full'
+    total = total_sq = count = 0.
+    batches = []
+    for i in range(2):
+        x, seq_len = g['mx_b%d_x' % i], g['mx_b%d_seq_len' % i] if masked else None
+        s, q, c = O.variance_acc(x, seq_len)
+        total, total_sq, count = total + s, total_sq + q, count + c
+        batches.append((x, seq_len))
+    assert count == float(g['mx_var_%s_count' % tag])
+    assert total == pytest.approx(float(g['mx_var_%s_sum' % tag]), rel=REL)
+    assert total_sq == pytest.approx(float(g['mx_var_%s_sum_square' % tag]), rel=REL)
+    # the reference forms sum_square - sum^2 / count in fp32: the cancellation amplifies its rounding by
+    # sum_square / (variance * count) ~ 5 here, so the oracle's fp64 value is compared at 1e-5
+    assert O.variance_result(total, total_sq, count) == pytest.approx(float(g['mx_var_%s_result' % tag]), rel=1e-5)
+    # with seq_len the count is frames while the sums run over frames x feat_dim (Q2), so for feat_dim > 1 the
+    # reference's "variance" is negative and its standard deviation nan -- pinned as is
+    with np.errstate(invalid='ignore'):
+        std = np.float64(O.variance_result(total, total_sq, count)) ** 0.5
+    assert std == pytest.approx(float(g['mx_std_%s_result' % tag]), rel=1e-5, nan_ok=True)
+    assert np.array_equal(O.tensor_history(batches, 5), g['mx_hist_%s' % tag])
+    assert np.array_equal(O.tensor_history(batches, 5, max_len=7), g['mx_hist_short_%s' % tag])
+
+
 def test_ema_bit_exact(golden):
     g = golden('ema')
     decay = float(g['ema_decay'])
