@@ -179,18 +179,18 @@ class AcousticModel(torch.nn.Module):
 class StockModel(torch.nn.Module):
     def __init__(self, ours, normalisers):
         super().__init__()
-        from oracle import aten_chain
-        self.chain, self.normalisers = aten_chain, normalisers
+        self.normalisers = normalisers
         self.inp, self.mid, self.out = (torch.nn.Linear(m.in_features, m.out_features, device=m.weight.device)
                                         for m in (ours.inp, ours.mid, ours.out))
         self.recurrent = copy.deepcopy(ours.recurrent)
+        for lstm in self.recurrent:
+            lstm.flatten_parameters()                                 # deepcopy un-flattens the cuDNN weight buffer
         for mine, theirs in ((self.inp, ours.inp), (self.mid, ours.mid), (self.out, ours.out)):
             mine.load_state_dict(theirs.state_dict())
         self.sums = {}
 
     def forward(self, features):
-        from oracle import np_oracle
-        C = self.chain
+        from oracle import aten_chain as C, np_oracle             # reference arm only
         n_frames, T = features['n_frames'], features['T']
         x = torch.cat((C.upsample_chain(features['normalised_lab'], features['dur']), features['normalised_counters']), dim=-1)
         h = torch.sigmoid(self.inp(x))
@@ -274,7 +274,10 @@ def main():
     def build():
         torch.manual_seed(args.seed)
         model = AcousticModel(normalisers, num_layers=args.num_layers, pack=not args.no_pack, device=dev)
-        return model, copy.deepcopy(model)
+        ema_model = copy.deepcopy(model)
+        for lstm in ema_model.recurrent:
+            lstm.flatten_parameters()                                 # deepcopy un-flattens the cuDNN weight buffer
+        return model, ema_model
 
     line = {'config': 'C4/C5 LSTM acoustic model (609-512-8xLSTM512-256-187) training step with EMA, %d utterances / rank / step'
                       % args.batch_size, 'n_gpus': world}
@@ -343,6 +346,8 @@ def main():
             stock_steps(stock, stock_ema, batches, 1, args.lr, args.ema_decay)   # warm-up
             stock = StockModel(build()[0], normalisers)
             stock_ema = copy.deepcopy(stock)
+            for lstm in stock_ema.recurrent:
+                lstm.flatten_parameters()
             stock_losses, stock_ms = stock_steps(stock, stock_ema, batches, args.steps, args.lr, args.ema_decay)
             rel = [abs(a.item() - b) / max(abs(b), 1e-6) for a, b in zip(ours_losses, stock_losses)]
             line.update({'stock_ms_per_step': round(stock_ms, 1), 'stock_loss_first_last': [round(stock_losses[0], 5), round(stock_losses[-1], 5)],
@@ -371,8 +376,8 @@ def main():
         epoch_losses = []
         for tr.epoch in range(1, args.epochs + 1):
             epoch_losses.append(tr.train_epoch(loader, opt))
-        valid_loss = tr.valid_epoch(loader[:4], model=tr.ema.model)
         stop.record()
+        valid_loss = tr.valid_epoch(loader[:4], model=tr.ema.model)   # the averaged model, into its own metric handler
         torch.cuda.synchronize()
         stats = torch.tensor([start.elapsed_time(stop), float(sum(b['frames_total'] for b in loader) * args.epochs)],
                              dtype=torch.float64, device=dev)
@@ -383,7 +388,7 @@ def main():
             stats = torch.cat([t, f])
         total_ms, frames = stats.tolist()
         line['dp'] = {'utterances': args.utterances, 'steps_per_epoch': len(loader), 'epochs': args.epochs,
-                      'ms_per_step': round(total_ms / (len(loader) * args.epochs + 4), 2),
+                      'ms_per_step': round(total_ms / (len(loader) * args.epochs), 2),
                       'valid_frames_per_s': round(frames / total_ms * 1e3),
                       'epoch_losses': [round(x, 5) for x in epoch_losses], 'ema_valid_loss': round(valid_loss, 5),
                       'train_metrics': {k: round(float(v), 4) for k, v in model.metrics.results_as_json_dict('train').items()},
