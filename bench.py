@@ -270,11 +270,19 @@ def run_ours(args, rank, world, local_rank):
         loss, grad = objective(batch['pred'], batch['target'], n_frames)
         return out, loss, grad
 
+    pending = []
+
     def exchange():
-        """The path's one collective: SUM of the packed loss / metric-sum records over ranks (NCCL over NVLink)."""
+        """The path's one collective: SUM of the packed loss / metric-sum records over ranks (NCCL over NVLink).  It is
+        issued asynchronously -- the records are copied first, the all-reduce runs on NCCL's stream while the next step's
+        kernels run on ours -- and joined one step later (and before the timed region closes)."""
         if world > 1:
-            return dp.allreduce_records(objective.last_loss_records, objective._records)
-        return None
+            join()
+            pending.append(dp.allreduce_records(objective.last_loss_records, objective._records, async_op=True))
+
+    def join():
+        while pending:
+            pending.pop().result()
 
     def barrier():
         if world > 1:
@@ -299,6 +307,7 @@ def run_ours(args, rank, world, local_rank):
         step(batch, time_k2=k2_events)
         exchange()
         frames_done += batch['frames']
+    join()
     stop.record(stream)
     barrier()
     wall1 = time.time()
@@ -340,9 +349,9 @@ def run_ours(args, rank, world, local_rank):
         out, n_frames = mg.utils.upsample_to_repetitions(lab, up['dur'], normaliser=normaliser, max_len=hb['T'],
                                                          return_lengths=True)
         loss, grad = objective(pred, target, n_frames)
-        packed = exchange()
-        host = torch.cat([objective.last_loss_records, objective._records]).cpu()   # device -> host read of the result
-        return host if packed is None else packed.cpu()
+        if world > 1:     # the step's result is read back right away, so this exchange is joined at once
+            return dp.allreduce_records(objective.last_loss_records, objective._records).cpu()
+        return torch.cat([objective.last_loss_records, objective._records]).cpu()   # device -> host read of the result
 
     def e2e_loop(n_steps):
         """Every step's inputs are uploaded inside the loop; the upload of step i + 1 overlaps the kernels of step i."""

@@ -46,19 +46,40 @@ def sharded_batches(n_items, batch_size, rank, world_size, drop_last=True):
 def pack_records(*record_blocks):
     """(n_i, 48) uint8 record blocks -> one (sum_i n_i, 3) float64 tensor of [sum, count, loss] (a copy)."""
     rows = [block.reshape(-1, 48).view(torch.float64)[:, :3] for block in record_blocks]
-    return torch.cat(rows).clone()
+    return torch.cat(rows)
 
 
-def allreduce_records(*record_blocks, group=None):
+class PendingRecords(object):
+    """An all-reduce of packed records in flight on the collective's own stream; :meth:`result` joins it."""
+    def __init__(self, packed, work, world):
+        self.packed, self.work, self.world = packed, work, world
+
+    def result(self):
+        """Make the current stream wait for the collective (no host sync) and return the (n, 3) float64 totals."""
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+            self.packed[:, 2] /= self.world
+        return self.packed
+
+
+def allreduce_records(*record_blocks, group=None, async_op=False):
     """SUM of the packed records over the ranks; ``loss`` columns come back as the MEAN over ranks (equal batch sizes).
 
     Returns a (n, 3) float64 tensor: global ``sum``, global ``count``, rank-mean ``loss``.  A single small collective
-    per step; deterministic (fixed reduction order inside NCCL / gloo for a fixed world size).
+    per step; deterministic (fixed reduction order inside NCCL / gloo for a fixed world size).  With ``async_op`` the
+    collective runs on its own stream, so the next step's kernels overlap its latency, and a :class:`PendingRecords` is
+    returned instead (the records are copied before the call returns, so the caller may overwrite them).
     """
     packed = pack_records(*record_blocks)
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
-        packed[:, 2] /= dist.get_world_size(group)
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    work = None
+    if world > 1:
+        work = dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group, async_op=async_op)
+        if not async_op:
+            packed[:, 2] /= world
+    if async_op:
+        return PendingRecords(packed, work, world)
     return packed
 
 

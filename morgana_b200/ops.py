@@ -412,6 +412,10 @@ def column_table(columns, device):
 
 def masked_objective(pred, target, seq_len, cols, slots, grad=None, grad_scale_dev=None):
     """K4b: one whole-row pass over (B, T, D) `pred` / `target`; `cols` from :func:`column_table`, `slots` a ctypes array."""
+    _require_cuda(pred, 'pred')
+    _require_cuda(target, 'target')
+    if pred.dtype != torch.float32 or target.dtype != torch.float32 or pred.shape != target.shape:
+        raise TypeError('masked_objective takes two float32 tensors of one shape')
     pred, p_sb, p_st = _view3(pred)
     target, t_sb, t_st = _view3(target)
     B, T, D = pred.shape

@@ -197,6 +197,20 @@ def main():
             pred_lf0 = mg.data.denormalise_mvn(pred_norm, lf0_mean, lf0_std)
             return mg.losses.mse(pred_norm, tgt, n_frames), pred_lf0
 
+    def ours_commuted():
+        """Layer 1 commutes with the expansion (every frame row is a copy of a phone row): run it at PHONE rate, then expand
+        its 512-dim bf16 activations.  Same bits on every valid frame; padding frames hold 0 instead of sigmoid(bias)."""
+        with torch.no_grad():
+            P = lab.shape[1]
+            x = mg.data.normalise_minmax(lab, mmin, mmax).reshape(B * P, 600)
+            h = ops.linear_bf16(x, layers[0].weight_bf16(), layers[0].bias, act='sigmoid', out_dtype=torch.bfloat16)
+            h = mg.utils.upsample_to_repetitions(h.reshape(B, P, 512), dur, max_len=T).reshape(B * T, 512)
+            for layer in layers[1:]:
+                h = ops.linear_bf16(h, layer.weight_bf16(), layer.bias, act=layer.act, out_dtype=layer.out_dtype)
+            pred_norm = h.reshape(B, T, 1)
+            pred_lf0 = mg.data.denormalise_mvn(pred_norm, lf0_mean, lf0_std)
+            return mg.losses.mse(pred_norm, tgt, n_frames), pred_lf0
+
     def stock_chain():
         with torch.no_grad():
             h = ref.upsample_chain(ref.normalise_minmax_chain(lab, mmin, mmax), dur)
@@ -208,6 +222,12 @@ def main():
     stock = timeit(stock_chain, 5, 1)
     row('C1@C2', 'README F0 MLP predict + loss: fused normalise/upsample (bf16) -> 4 tcgen05 layers -> denormalise -> mse', ms,
         None, F, stock, note='%.0f TFLOP/s over the four layers incl. the feature path; stock = fp32 cuBLAS + ATen' % (flops / ms / 1e9))
+    (loss_a, lf0_a), (loss_b, lf0_b) = ours(), ours_commuted()
+    valid = (torch.arange(T, device=dev)[None] < n_frames[:, None])[:, :, None]
+    same = bool(torch.equal(lf0_a[valid], lf0_b[valid])) and loss_a.item() == loss_b.item()
+    ms_c = timeit(ours_commuted, 10)
+    row('C1@C2', 'same, first layer run at phone rate and its bf16 activations expanded (layer 1 commutes with the expansion)', ms_c,
+        None, F, stock, note='bit-identical loss and valid-frame predictions: %s' % same)
 
 
 if __name__ == '__main__':

@@ -35,6 +35,8 @@ def _worker(rank, world, port, out_dir):
     s, c = O.rmse_acc(t[..., 4:64], p[..., 4:64], n)                 # what the kernels would leave in a record
     loss = O.masked_loss(p[..., 4:184], t[..., 4:184], n)
     packed = dp.allreduce_records(torch.stack([_make_record(s, c, loss)]))
+    pending = dp.allreduce_records(torch.stack([_make_record(s, c, loss)]), async_op=True)   # same totals when joined later
+    assert torch.equal(pending.result(), packed) and pending.result() is pending.packed
     # gradient all-reduce: rank-dependent gradients must come back as their mean
     model = torch.nn.Linear(3, 2)
     for i, prm in enumerate(model.parameters()):

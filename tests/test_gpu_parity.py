@@ -621,6 +621,30 @@ def test_fused_upsample_bf16_output_is_rounded_exact_result(mg, kind):
     assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
 
 
+def test_first_layer_commutes_with_the_expansion(mg):
+    """Every frame row is a copy of an item row, so Linear(+Sigmoid) may run at item rate before the expansion: the same
+    bits on every valid frame; padding frames hold 0 instead of sigmoid(bias)."""
+    from morgana_b200 import ops
+    rng = np.random.default_rng(23)
+    B, P, D, N = 5, 17, 600, 512
+    lab = dev(rng.random((B, P, D), dtype=np.float32))
+    dur = dev(rng.integers(0, 12, (B, P)))
+    mmin, mmax = dev(np.zeros(D, np.float32)), dev((rng.random(D) + 0.5).astype(np.float32))
+    w = ops.cast_pad_bf16(dev((rng.standard_normal((N, D)) * 0.05).astype(np.float32)))
+    bias = dev(rng.standard_normal(N).astype(np.float32))
+    frames, n_frames = mg.utils.upsample_to_repetitions(lab, dur, normaliser=('minmax', mmin, mmax), out_dtype=torch.bfloat16,
+                                                        return_lengths=True)
+    T = frames.shape[1]
+    at_frame_rate = ops.linear_bf16(frames.reshape(B * T, D), w, bias, act='sigmoid', out_dtype=torch.bfloat16).reshape(B, T, N)
+    items = mg.data.normalise_minmax(lab, mmin, mmax).reshape(B * P, D)
+    at_item_rate = ops.linear_bf16(items, w, bias, act='sigmoid', out_dtype=torch.bfloat16).reshape(B, P, N)
+    expanded = mg.utils.upsample_to_repetitions(at_item_rate, dur, max_len=T)          # bf16 rows: the byte-copy path
+    valid = torch.arange(T, device='cuda')[None] < n_frames[:, None]
+    assert expanded.dtype == torch.bfloat16 and valid.any() and not valid.all()
+    assert torch.equal(expanded[valid].view(torch.int16), at_frame_rate[valid].view(torch.int16))
+    assert not expanded[~valid].any()
+
+
 def test_nn_linear_follows_fused_optimizer_updates(mg):
     """Fused Adam updates parameters without bumping the autograd version counter: the bf16 shadow must still follow."""
     from morgana_b200 import nn as mnn
