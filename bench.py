@@ -193,7 +193,7 @@ def run_reference(args, rank, world):
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(args, note=None):
@@ -424,13 +424,32 @@ def run_ours(args, rank, world, local_rank):
                                 'sample': '%d of %d utterances (%d valid frames), best of %d passes of the reference op '
                                           'chain (oracle/aten_chain.py) on %s' % (CPU_SAMPLE_UTTS, args.batch_size, frames,
                                                                                  len(times), cpu_model_name())}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_RESULT_FD = None
+
+
+def protect_stdout():
+    """Keep stdout for the ONE JSON line: libraries that print there (NCCL writes its version banner to stdout when
+    NCCL_DEBUG is set in the environment) are pointed at stderr for the rest of the run."""
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + '\n').encode()
+    os.write(_RESULT_FD if _RESULT_FD is not None else 1, data)
+
+
 def main():
     args = parse_args()
+    protect_stdout()
     rank = int(os.environ.get('RANK', '0'))
     world = int(os.environ.get('WORLD_SIZE', '1'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
