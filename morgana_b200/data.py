@@ -137,3 +137,182 @@ class MinMaxNormaliser(_FeatureNormaliser):
     kind, param_names, file_suffix = 'minmax', ('mmin', 'mmax'), 'minmax'
     _normalise = staticmethod(normalise_minmax)
     _denormalise = staticmethod(denormalise_minmax)
+
+
+class _SpeakerDependentNormaliser(_FeatureNormaliser):
+    r"""One parameter set per speaker, selected per batch item by ``speaker_ids`` (morgana/data.py:388-531).
+
+    The reference assembles the ``(batch_size, feat_dim)`` parameters of a batch with one ``torch.cat`` per batch item
+    and parameter (``data.py:482-498``); here every parameter is one ``(n_speakers, feat_dim)`` table on the device and a
+    batch's rows are gathered with a single ``index_select``.  The kernels (K3, and K2 when fused) take the
+    ``(batch_size, feat_dim)`` parameters directly -- row ``b`` applies to every frame of utterance ``b``.
+    """
+    def __init__(self, name, speaker_id_list=None, use_deltas=False, file_pattern=None):
+        _FeatureNormaliser.__init__(self, name, use_deltas=use_deltas,
+                                    file_pattern=file_pattern or '{speaker_id}/{name}_' + self.file_suffix + '.json')
+        self.speaker_id_list = speaker_id_list
+        self.speaker_ids = None
+        self.params, self.params_torch = {}, {}
+        if self.use_deltas:
+            self.delta_params, self.delta_params_torch = {}, {}
+        self._tables = {}          # deltas flag -> (speaker -> row, {param name: (n_speakers, feat_dim) device tensor})
+
+    # -- parameters -------------------------------------------------------------------------------------------------
+    def set_params(self, params, delta_params=None, device='cuda'):
+        """``params``: ``{speaker_id: {param name: (feat_dim,) array}}`` (and the same for the delta features)."""
+        self.speaker_ids = list(params.keys())
+        self.params = {s: {k: np.asarray(v, dtype=np.float32) for k, v in p.items()} for s, p in params.items()}
+        self.params_torch = {s: self._to_torch(p, device) for s, p in self.params.items()}
+        if delta_params is not None:
+            self.use_deltas = True
+            self.delta_params = {s: {k: np.asarray(v, dtype=np.float32) for k, v in p.items()} for s, p in delta_params.items()}
+            self.delta_params_torch = {s: self._to_torch(p, device) for s, p in self.delta_params.items()}
+        self._tables = {}
+        return self
+
+    def load_params(self, data_dir, data_root='.', device='cpu'):
+        """Loads ``{data_root}/{data_dir}/{speaker_id}/{name}_{kind}.json`` for every speaker of the id list (one id per
+        line), morgana/data.py:506-531."""
+        if self.speaker_ids is None:
+            with open(os.path.join(data_root, self.speaker_id_list)) as f:
+                self.speaker_ids = [line.strip() for line in f if line.strip()]
+        params, delta_params = {}, ({} if self.use_deltas else None)
+        for speaker_id in self.speaker_ids:
+            params[speaker_id] = self._from_json(os.path.join(
+                data_root, data_dir, self.file_pattern.format(name=self.name, speaker_id=speaker_id)))
+            if self.use_deltas:
+                delta_params[speaker_id] = self._from_json(os.path.join(
+                    data_root, data_dir, self.file_pattern.format(name=self.name + '_deltas', speaker_id=speaker_id)))
+        return self.set_params(params, delta_params, device=device)
+
+    def _table(self, deltas):
+        if deltas not in self._tables:
+            per_speaker = self.delta_params_torch if deltas else self.params_torch
+            rows = {speaker_id: i for i, speaker_id in enumerate(per_speaker)}
+            stacked = {name: torch.stack([per_speaker[s][name] for s in per_speaker]) for name in self.param_names}
+            self._tables[deltas] = (rows, stacked)
+        return self._tables[deltas]
+
+    def fetch_params(self, speaker_ids, data_type=np.ndarray, deltas=False):
+        """``{param name: (batch_size, feat_dim)}`` for a list of speakers, ``(feat_dim,)`` for a single speaker."""
+        single = not isinstance(speaker_ids, (list, tuple))
+        speaker_ids = [speaker_ids] if single else list(speaker_ids)
+        if data_type == torch.Tensor:
+            rows, stacked = self._table(deltas)
+            index = torch.tensor([rows[s] for s in speaker_ids], device=next(iter(stacked.values())).device)
+            out = {name: table.index_select(0, index) for name, table in stacked.items()}
+        else:
+            per_speaker = self.delta_params if deltas else self.params
+            out = {name: np.stack([per_speaker[s][name] for s in speaker_ids]) for name in self.param_names}
+        if len(speaker_ids) == 1:                 # the reference squeezes a one-speaker batch to (feat_dim,), data.py:500-501
+            out = {name: value[0] for name, value in out.items()}
+        return out
+
+    def fused_params(self, speaker_ids, deltas=False):
+        """``(kind, p0, p1)`` with per-utterance parameters, for ``utils.upsample_to_repetitions(..., normaliser=...)``."""
+        params = self.fetch_params(speaker_ids, torch.Tensor, deltas=deltas)
+        return (self.kind,) + tuple(params[n] for n in self.param_names)
+
+    # -- arithmetic -------------------------------------------------------------------------------------------------
+    def _sd_args(self, feature, speaker_ids, deltas):
+        data_type = torch.Tensor if isinstance(feature, torch.Tensor) else np.ndarray
+        params = self.fetch_params(speaker_ids, data_type, deltas=deltas)
+        return tuple(params[n] for n in self.param_names)
+
+    def normalise(self, feature, speaker_ids, deltas=False):
+        return self._normalise(feature, *self._sd_args(feature, speaker_ids, deltas))
+
+    def denormalise(self, feature, speaker_ids, deltas=False):
+        return self._denormalise(feature, *self._sd_args(feature, speaker_ids, deltas))
+
+
+class SpeakerDependentMeanVarianceNormaliser(_SpeakerDependentNormaliser):
+    """Per-speaker zero mean, unit variance (morgana/data.py:567-576)."""
+    kind, param_names, file_suffix = 'mvn', ('mean', 'std_dev'), 'mvn'
+    _normalise = staticmethod(normalise_mvn)
+    _denormalise = staticmethod(denormalise_mvn)
+
+
+class SpeakerDependentMinMaxNormaliser(_SpeakerDependentNormaliser):
+    """Per-speaker minimum 0, maximum 1 (morgana/data.py:619-628)."""
+    kind, param_names, file_suffix = 'minmax', ('mmin', 'mmax'), 'minmax'
+    _normalise = staticmethod(normalise_minmax)
+    _denormalise = staticmethod(denormalise_minmax)
+
+
+class Normalisers(dict):
+    r"""Dictionary of normalisers with their parameters loaded (morgana/data.py:227-249).  ``device`` is honoured: the
+    reference passes it in ``data_root``'s position and leaves every parameter on the CPU."""
+    def __init__(self, normaliser_sources, normalisation_dir, data_root='.', device='cpu'):
+        dict.__init__(self)
+        self.normalisation_dir = os.path.join(data_root, normalisation_dir)
+        self.device = device
+        for name, normaliser in normaliser_sources.items():
+            self[name] = normaliser
+            normaliser.load_params(self.normalisation_dir, device=self.device)
+
+
+def _map_nested(func, data):
+    """Apply ``func`` to every tensor / array leaf of nested dicts, lists and tuples (morgana/utils.py:37-54)."""
+    if isinstance(data, (np.ndarray, torch.Tensor)):
+        return func(data)
+    if isinstance(data, dict):
+        return {k: _map_nested(func, v) for k, v in data.items()}
+    if isinstance(data, (list, tuple)):
+        return type(data)(_map_nested(func, v) for v in data)
+    return data
+
+
+class ToDeviceWrapper(object):
+    r"""Iterates over a data loader and moves every batch to ``device`` (morgana/data.py:631-663), as a feeder for a GPU
+    that consumes a batch in well under a millisecond: tensors are staged in pinned host memory and copied on a side
+    stream ONE BATCH AHEAD, so the upload of batch i + 1 runs under the kernels of batch i.  The consumer's stream only
+    waits on the copy's event; nothing synchronises with the host.  For a CPU ``device`` batches pass through untouched.
+    """
+    def __init__(self, data_loader, device, prefetch=True):
+        self.data_loader = data_loader
+        self.torch_device = torch.device(device)
+        self.prefetch = prefetch and self.torch_device.type == 'cuda'
+
+    def __getattr__(self, attr):            # attribute access falls through to the wrapped loader (data.py:636-642)
+        return getattr(self.__dict__['data_loader'], attr)
+
+    def __len__(self):
+        return len(self.data_loader)
+
+    def to_device(self, tensor):
+        if not isinstance(tensor, torch.Tensor):
+            return tensor
+        if self.torch_device.type == 'cuda' and not tensor.is_cuda:
+            if not tensor.is_pinned():
+                tensor = tensor.pin_memory()
+            return tensor.to(self.torch_device, non_blocking=True)
+        return tensor.to(self.torch_device)
+
+    def __iter__(self):
+        if not self.prefetch:
+            for features in self.data_loader:
+                yield _map_nested(self.to_device, features)
+            return
+        copy_stream = torch.cuda.Stream(self.torch_device)
+
+        def upload(features):
+            with torch.cuda.stream(copy_stream):
+                moved = _map_nested(self.to_device, features)
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            return moved, done
+
+        def hand_over(moved, done):
+            consumer = torch.cuda.current_stream(self.torch_device)
+            consumer.wait_event(done)
+            _map_nested(lambda t: t.record_stream(consumer) if isinstance(t, torch.Tensor) and t.is_cuda else None, moved)
+            return moved
+        pending = None
+        for features in self.data_loader:
+            ahead = upload(features)
+            if pending is not None:
+                yield hand_over(*pending)
+            pending = ahead
+        if pending is not None:
+            yield hand_over(*pending)

@@ -236,6 +236,40 @@ def metric_cases():
     return out
 
 
+def speaker_dependent_cases():
+    """SpeakerDependent{MeanVariance,MinMax}Normaliser (data.py:388-531, 567-576, 619-628) on a 4-utterance batch of three
+    speakers, a one-speaker batch (parameters squeezed to (feat_dim,), :500-501) and the NumPy path."""
+    out = {}
+    g = gen(450)
+    D, speakers = 7, ['spk_a', 'spk_b', 'spk_c']
+    batch_ids = ['spk_b', 'spk_a', 'spk_b', 'spk_c']
+    x = torch.randn(4, 9, D, generator=g)
+    out['sdn_x'], out['sdn_batch_ids'], out['sdn_speakers'] = x.numpy(), np.asarray(batch_ids), np.asarray(speakers)
+    mvn = data.SpeakerDependentMeanVarianceNormaliser('lf0', 'speakers.scp', use_deltas=True)
+    mm = data.SpeakerDependentMinMaxNormaliser('lab', 'speakers.scp')
+    for i, spk in enumerate(speakers):
+        p = {'mean': torch.randn(D, generator=g).numpy(), 'std_dev': (torch.rand(D, generator=g) + 0.2).numpy()}
+        dp = {'mean': torch.randn(D, generator=g).numpy(), 'std_dev': (torch.rand(D, generator=g) + 0.2).numpy()}
+        q = {'mmin': torch.randn(D, generator=g).numpy(), 'mmax': (torch.randn(D, generator=g) + 3.).numpy()}
+        q['mmax'][i] = q['mmin'][i]                                   # a constant dimension per speaker (scale forced to 1)
+        for name, params in (('mvn', p), ('mvn_deltas', dp), ('minmax', q)):
+            for k, v in params.items():
+                out['sdn_%s_%s_%s' % (name, spk, k)] = v
+        mvn.params[spk], mvn.params_torch[spk] = p, {k: torch.tensor(v) for k, v in p.items()}
+        mvn.delta_params[spk], mvn.delta_params_torch[spk] = dp, {k: torch.tensor(v) for k, v in dp.items()}
+        mm.params[spk], mm.params_torch[spk] = q, {k: torch.tensor(v) for k, v in q.items()}
+    out['sdn_mvn_norm'] = mvn.normalise(x, batch_ids).numpy()
+    out['sdn_mvn_denorm'] = mvn.denormalise(x, batch_ids).numpy()
+    out['sdn_mvn_norm_deltas'] = mvn.normalise(x, batch_ids, deltas=True).numpy()
+    out['sdn_minmax_norm'] = mm.normalise(x, batch_ids).numpy()
+    out['sdn_minmax_denorm'] = mm.denormalise(x, batch_ids).numpy()
+    out['sdn_mvn_norm_single'] = mvn.normalise(x[1], 'spk_c').numpy()            # (T, D) feature, one speaker
+    # the DataLoader-worker path: one utterance, one speaker, NumPy (a NumPy batch of several speakers fails in the
+    # reference: np.squeeze(0) on a (batch_size, feat_dim) array, data.py:500-501)
+    out['sdn_minmax_norm_numpy'] = mm.normalise(x[2].numpy(), 'spk_b')
+    return out
+
+
 def metric_extra_cases():
     """Variance / StandardDeviation (metrics.py:400-471), TensorHistory (:263-356) and the Handler container (:52-185)."""
     out = {}
@@ -355,6 +389,7 @@ def main():
         'losses': loss_cases(),
         'metrics': metric_cases(),
         'metrics_extra': metric_extra_cases(),
+        'normalise_sd': speaker_dependent_cases(),
         'ema': ema_cases(),
         'linear': linear_cases(),
     }

@@ -259,6 +259,46 @@ def test_losses_vs_oracle_random_and_strided(mg, B, T, D, kind):
     assert rel_err(v1.item(), want) <= REL and v1.item() == v2.item()
 
 
+def test_speaker_dependent_normalisers_golden(mg, golden):
+    """SpeakerDependent{MeanVariance,MinMax}Normaliser against the reference's outputs: (B, D) parameters gathered per
+    batch item, bit-exact; also fused into the expansion (per-utterance parameters in K2)."""
+    g = golden('normalise_sd')
+    speakers = [str(s) for s in g['sdn_speakers']]
+    batch_ids = [str(s) for s in g['sdn_batch_ids']]
+    D = mg.data
+    mvn = D.SpeakerDependentMeanVarianceNormaliser('lf0', 'speakers.scp', use_deltas=True).set_params(
+        {s: {k: g['sdn_mvn_%s_%s' % (s, k)] for k in ('mean', 'std_dev')} for s in speakers},
+        {s: {k: g['sdn_mvn_deltas_%s_%s' % (s, k)] for k in ('mean', 'std_dev')} for s in speakers})
+    mm = D.SpeakerDependentMinMaxNormaliser('lab', 'speakers.scp').set_params(
+        {s: {k: g['sdn_minmax_%s_%s' % (s, k)] for k in ('mmin', 'mmax')} for s in speakers})
+    x = dev(g['sdn_x'])
+    for got, key in [(mvn.normalise(x, batch_ids), 'sdn_mvn_norm'), (mvn.denormalise(x, batch_ids), 'sdn_mvn_denorm'),
+                     (mvn.normalise(x, batch_ids, deltas=True), 'sdn_mvn_norm_deltas'),
+                     (mm.normalise(x, batch_ids), 'sdn_minmax_norm'), (mm.denormalise(x, batch_ids), 'sdn_minmax_denorm'),
+                     (mvn.normalise(x[1], 'spk_c'), 'sdn_mvn_norm_single')]:
+        assert np.array_equal(got.cpu().numpy(), g[key]), key
+    # fused: per-utterance parameters inside the expansion == normalise, then expand
+    dur = dev(np.array([[2, 0, 1, 3, 1, 0, 2, 1, 1]] * 4) + np.arange(4)[:, None] % 2)
+    fused = mg.utils.upsample_to_repetitions(x, dur, normaliser=mm.fused_params(batch_ids))
+    want = mg.utils.upsample_to_repetitions(mm.normalise(x, batch_ids), dur)
+    assert torch.equal(fused, want)
+
+
+def test_to_device_wrapper_prefetches_one_batch_ahead(mg):
+    """The feeder (data.py:648-663 counterpart): pinned staging + side-stream copies one batch ahead, same values."""
+    g = torch.Generator().manual_seed(5)
+    batches = [{'lab': torch.randn(3, 50, 600, generator=g), 'dur': torch.randint(0, 9, (3, 50, 1), generator=g),
+                'name': ['u%d' % i], 'n_frames': [torch.tensor([7, 8, 9])]} for i in range(5)]
+    seen = []
+    for features in mg.data.ToDeviceWrapper(batches, 'cuda'):
+        assert features['lab'].is_cuda and features['n_frames'][0].is_cuda and features['name'][0].startswith('u')
+        seen.append(mg.utils.upsample_to_repetitions(features['lab'], features['dur']).sum(dim=(1, 2)).cpu())
+    assert len(seen) == 5
+    for got, b in zip(seen, batches):
+        want = O.upsample_to_repetitions(b['lab'].numpy(), b['dur'].numpy()[:, :, 0]).astype(np.float64).sum(axis=(1, 2))
+        np.testing.assert_allclose(got.numpy(), want, rtol=1e-4)
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # a8 - a12 metrics
 # ----------------------------------------------------------------------------------------------------------------------
@@ -686,6 +726,23 @@ def test_mlpg_vs_oracle(mg, B, T, F, pad, var_kind):
     as_np = MLPG(means, var, padding_size=pad, seq_len=seq_len)                       # NumPy in -> NumPy out, as the reference
     assert isinstance(as_np, np.ndarray) and as_np.dtype == np.float64
     np.testing.assert_allclose(as_np, want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize('pad', [0, 100])
+def test_mlpg_chunked_solve_at_every_split(mg, pad):
+    """The solve cuts a sequence into 1..32 chunks depending on its padded length: lengths on both sides of every change
+    of the chunk count, and long utterances, against the banded fp64 solve of the oracle."""
+    from morgana_b200.viz.synthesis import MLPG
+    rng = np.random.default_rng(99 + pad)
+    lengths = np.array([1, 2, 3, 11, 12, 23, 24, 25, 35, 36, 37, 47, 48, 59, 60, 383, 384, 385, 777, 1500])
+    B, T, F = len(lengths), 1500, 3
+    means = rng.standard_normal((B, T, 3 * F)).astype(np.float32)
+    var = (rng.random(3 * F) * 2 + 0.05).astype(np.float32)
+    want = O.mlpg_banded(means, var, padding_size=pad, seq_len=lengths)
+    got = MLPG(dev(means), dev(var), padding_size=pad, seq_len=dev(lengths)).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-5)
+    for b, n in enumerate(lengths):
+        assert not got[b, n:].any()
 
 
 def test_mlpg_static_only_limit(mg):

@@ -126,6 +126,59 @@ def test_patch_and_unpatch_rebind_reference_names(mg):
     assert not hasattr(fake.metrics.RMSE, 'result')
 
 
+def _sd_normalisers(mg, g, device):
+    speakers = [str(s) for s in g['sdn_speakers']]
+    mvn = mg.data.SpeakerDependentMeanVarianceNormaliser('lf0', 'speakers.scp', use_deltas=True).set_params(
+        {s: {k: g['sdn_mvn_%s_%s' % (s, k)] for k in ('mean', 'std_dev')} for s in speakers},
+        {s: {k: g['sdn_mvn_deltas_%s_%s' % (s, k)] for k in ('mean', 'std_dev')} for s in speakers}, device=device)
+    mm = mg.data.SpeakerDependentMinMaxNormaliser('lab', 'speakers.scp').set_params(
+        {s: {k: g['sdn_minmax_%s_%s' % (s, k)] for k in ('mmin', 'mmax')} for s in speakers}, device=device)
+    return mvn, mm
+
+
+def test_speaker_dependent_normalisers_numpy_path_and_loading(mg, golden, tmp_path):
+    """The DataLoader-worker path (NumPy, one utterance, one speaker; data.py:388-531) and the per-speaker JSON layout."""
+    import json
+    g = golden('normalise_sd')
+    mvn, mm = _sd_normalisers(mg, g, 'cpu')
+    got = mm.normalise(g['sdn_x'][2], 'spk_b')
+    assert isinstance(got, np.ndarray) and np.array_equal(got, g['sdn_minmax_norm_numpy'])
+    params = mvn.fetch_params(['spk_b', 'spk_a'], np.ndarray, deltas=True)
+    assert params['mean'].shape == (2, 7) and np.array_equal(params['mean'][1], g['sdn_mvn_deltas_spk_a_mean'])
+    assert mvn.fetch_params('spk_c')['std_dev'].shape == (7,)                   # one speaker: squeezed (data.py:500-501)
+    # load_params: {data_dir}/{speaker_id}/{name}_mvn.json (+ _deltas), speakers from the id list
+    (tmp_path / 'speakers.scp').write_text('spk_a\nspk_c\n')
+    for spk in ('spk_a', 'spk_c'):
+        d = tmp_path / 'train' / spk
+        d.mkdir(parents=True)
+        for suffix, key in (('lf0_mvn.json', 'sdn_mvn_%s_%s'), ('lf0_deltas_mvn.json', 'sdn_mvn_deltas_%s_%s')):
+            (d / suffix).write_text(json.dumps({k: g[key % (spk, k)].tolist() for k in ('mean', 'std_dev')}))
+    loaded = mg.data.SpeakerDependentMeanVarianceNormaliser('lf0', 'speakers.scp', use_deltas=True)
+    loaded.load_params('train', data_root=str(tmp_path), device='cpu')
+    assert loaded.speaker_ids == ['spk_a', 'spk_c']
+    assert np.array_equal(loaded.delta_params['spk_c']['std_dev'], g['sdn_mvn_deltas_spk_c_std_dev'])
+    assert np.array_equal(loaded.normalise(g['sdn_x'][1], 'spk_c'), g['sdn_mvn_norm_single'])
+
+
+def test_normalisers_container_and_cpu_feeder(mg, tmp_path):
+    """data.Normalisers loads every source's JSON (data.py:227-249); ToDeviceWrapper passes CPU batches through."""
+    import json
+    (tmp_path / 'stats').mkdir()
+    (tmp_path / 'stats' / 'lab_minmax.json').write_text(json.dumps({'mmin': [0., 1.], 'mmax': [2., 1.]}))
+    (tmp_path / 'stats' / 'dur_mvn.json').write_text(json.dumps({'mean': [3.], 'std_dev': [2.]}))
+    norms = mg.data.Normalisers({'lab': mg.data.MinMaxNormaliser('lab'), 'dur': mg.data.MeanVarianceNormaliser('dur')},
+                                'stats', data_root=str(tmp_path), device='cpu')
+    assert set(norms) == {'lab', 'dur'} and norms['dur'].params_torch['mean'].device.type == 'cpu'
+    x = np.array([[1., 5.], [2., 7.]], dtype=np.float32)
+    assert np.array_equal(norms['lab'].normalise(x), np.array([[0.5, 4.], [1., 6.]], dtype=np.float32))
+    batches = [{'x': torch.arange(4.), 'name': ['a'], 'nested': (torch.ones(2), 3)} for _ in range(3)]
+    feeder = mg.data.ToDeviceWrapper(batches, 'cpu')
+    assert len(feeder) == 3
+    out = list(feeder)
+    assert len(out) == 3 and out[0]['name'] == ['a'] and out[0]['nested'][1] == 3
+    assert torch.equal(out[2]['x'], batches[2]['x']) and isinstance(out[1]['nested'], tuple)
+
+
 def test_metric_containers_host_logic(mg):
     """Handler / Print / History bookkeeping (morgana/metrics.py:52-260) needs no device."""
     M = mg.metrics
