@@ -164,6 +164,9 @@ int mg_normalise_f32(const float* x, const float* p0, const float* p1, int norm_
 #define MG_RED_AND 7         /* a & b on uint8/bool   Accuracy */
 #define MG_RED_EQ 8          /* (a == b) ? 1 : 0      V/UV accuracy as models/RNN_SPSS.py:127 builds it, fused */
 #define MG_RED_SQ 9          /* a * a                 Variance / StandardDeviation (morgana/metrics.py:427-442), with MG_RED_SUM */
+#define MG_RED_CE 10         /* logsumexp_d(a) - a[b] cross-entropy loss, losses.ce (morgana/losses.py:59-61): a = (B, T, D) logits,
+                                b = (B, T) int64 class indices (b_sb / b_st in elements); one value per frame, the loss's
+                                feature axis has size 1.  Gradient: (softmax(a) - onehot(b)) * scale / (n_b * B) */
 
 /* Fuse the `output_features['vuv'] > 0.5` of models/RNN_SPSS.py:122 into the reduction instead of a separate pass: */
 #define MG_FLAG_M_GT_HALF 1 /* the per-frame weight is (m > 0.5) ? 1 : 0 */

@@ -15,7 +15,7 @@ MG_OK, MG_ERR_INVALID_ARG, MG_ERR_CUDA, MG_ERR_UNSUPPORTED = 0, -1, -2, -3
 NORM_NONE, NORM_MVN, NORM_MINMAX = 0, 1, 2
 PATH_AUTO, PATH_BULK, PATH_DIRECT = 0, 1, 2
 MAX_TERMS = 12
-(RED_SQDIFF, RED_ABSDIFF, RED_BCE, RED_SUM, RED_ROOT_SQDIFF, RED_SQDIFF_EXP, RED_XOR, RED_AND, RED_EQ, RED_SQ) = range(10)
+(RED_SQDIFF, RED_ABSDIFF, RED_BCE, RED_SUM, RED_ROOT_SQDIFF, RED_SQDIFF_EXP, RED_XOR, RED_AND, RED_EQ, RED_SQ, RED_CE) = range(11)
 DT_F32, DT_U8 = 0, 1
 FLAG_M_GT_HALF, FLAG_A_GT_HALF, FLAG_IN_TOTAL = 1, 2, 4
 ACT_NONE, ACT_SIGMOID = 0, 1

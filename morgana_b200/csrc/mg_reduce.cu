@@ -220,6 +220,32 @@ __device__ __forceinline__ void run_per_frame(const float* __restrict__ a, int64
   }
 }
 
+// ---- cross-entropy over the feature axis (losses.ce, morgana/losses.py:59-61): ATen's log_softmax + nll_loss per frame,
+// x[target] - max - log(sum exp(x - max)) negated; one thread per frame, two passes over its D logits ---------------------
+__device__ __forceinline__ void run_cross_entropy(const float* __restrict__ a, int64_t a_st, const int64_t* __restrict__ target,
+                                                  int64_t t_st, float* __restrict__ g, int64_t g_st, float w, int64_t n_rows,
+                                                  int D, double& sum) {
+  for (int64_t r = threadIdx.x; r < n_rows; r += kRedThreads) {
+    const float* x = a + r * a_st;
+    const int64_t cls = __ldg(target + r * t_st);
+    float mx = -INFINITY;
+    for (int d = 0; d < D; ++d) mx = fmaxf(mx, __ldg(x + d));
+    float total = 0.f;
+    for (int d = 0; d < D; ++d) total = __fadd_rn(total, expf(__fsub_rn(__ldg(x + d), mx)));
+    const float log_total = logf(total);
+    const bool valid_cls = cls >= 0 && cls < D;
+    const float picked = valid_cls ? __ldg(x + cls) : 0.f;
+    if (valid_cls) sum += static_cast<double>(-__fsub_rn(__fsub_rn(picked, mx), log_total));
+    if (g != nullptr) {
+      float* gr = g + r * g_st;
+      for (int d = 0; d < D; ++d) {
+        const float soft = valid_cls ? expf(__fsub_rn(__fsub_rn(__ldg(x + d), mx), log_total)) : 0.f;
+        gr[d] = __fmul_rn(__fsub_rn(soft, d == cls ? 1.f : 0.f), w);
+      }
+    }
+  }
+}
+
 // ---- integer / comparison kinds on uint8 (bool) or float operands -----------------------------------------------------
 __device__ __forceinline__ float load_as_float(const void* p, bool is_u8, int64_t idx) {
   if (is_u8) return static_cast<float>(__ldg(static_cast<const unsigned char*>(p) + idx));
@@ -324,12 +350,18 @@ masked_reduce_kernel(const __grid_constant__ ReduceParams prm) {
     if (tm.grad != nullptr) {
       double scale = static_cast<double>(tm.grad_scale);
       if (tm.grad_scale_dev != nullptr) scale *= static_cast<double>(__ldg(tm.grad_scale_dev));
-      w = static_cast<float>(scale / (static_cast<double>(n_b) * prm.B * tm.D));
+      w = static_cast<float>(scale / (static_cast<double>(n_b) * prm.B * (tm.kind == MG_RED_CE ? 1 : tm.D)));
     }
 
     if (n_valid > 0 || tm.grad != nullptr) {
       if (tm.ab_dtype == MG_DT_U8 || tm.kind == MG_RED_EQ) {
         run_discrete(tm, b * tm.a_sb + r0 * tm.a_st, b * tm.b_sb + r0 * tm.b_st, n_valid, sum);
+      } else if (tm.kind == MG_RED_CE) {
+        float* g = tm.grad != nullptr ? tm.grad + b * tm.g_sb + r0 * tm.g_st : nullptr;
+        run_cross_entropy(static_cast<const float*>(tm.a) + b * tm.a_sb + r0 * tm.a_st, tm.a_st,
+                          static_cast<const int64_t*>(tm.b) + b * tm.b_sb + r0 * tm.b_st, tm.b_st, g, tm.g_st, w, n_valid,
+                          tm.D, sum);
+        if (g != nullptr) zero_grad_rows(g, tm.g_st, tm.D, n_valid, r1 - r0);
       } else {
         switch (tm.kind) {
           case MG_RED_SQDIFF: run_float_term<MG_RED_SQDIFF>(tm, b, r0, n_valid, r1, w, sum, cnt); break;
@@ -398,7 +430,7 @@ extern "C" int mg_masked_reduce(const mg_term* terms, int n_terms, const int64_t
   for (int i = 0; i < n_terms; ++i) {
     const mg_term& tm = terms[i];
     MG_REQUIRE(tm.D >= 1, "mg_masked_reduce: term %d has D=%d", i, tm.D);
-    MG_REQUIRE(tm.kind >= MG_RED_SQDIFF && tm.kind <= MG_RED_SQ, "mg_masked_reduce: term %d has unknown kind %d", i, tm.kind);
+    MG_REQUIRE(tm.kind >= MG_RED_SQDIFF && tm.kind <= MG_RED_CE, "mg_masked_reduce: term %d has unknown kind %d", i, tm.kind);
     MG_REQUIRE(tm.a != nullptr || T == 0, "mg_masked_reduce: term %d has a NULL operand", i);
     MG_REQUIRE(tm.result != nullptr && mg_aligned(tm.result, 16), "mg_masked_reduce: term %d needs a 16-byte aligned result record", i);
     const bool discrete = tm.ab_dtype == MG_DT_U8 || tm.kind == MG_RED_EQ;
@@ -411,18 +443,21 @@ extern "C" int mg_masked_reduce(const mg_term* terms, int n_terms, const int64_t
     }
     MG_REQUIRE(!kind_has_b(tm.kind) || tm.b != nullptr || T == 0, "mg_masked_reduce: term %d needs a second operand", i);
     if (tm.grad != nullptr) {
-      MG_REQUIRE(tm.kind == MG_RED_SQDIFF || tm.kind == MG_RED_ABSDIFF || tm.kind == MG_RED_BCE,
+      MG_REQUIRE(tm.kind == MG_RED_SQDIFF || tm.kind == MG_RED_ABSDIFF || tm.kind == MG_RED_BCE || tm.kind == MG_RED_CE,
                  "mg_masked_reduce: term %d: kind %d has no gradient", i, tm.kind);
       MG_REQUIRE(tm.m == nullptr, "mg_masked_reduce: term %d: weighted terms have no gradient", i);
+    }
+    if (tm.kind == MG_RED_CE) {
+      MG_REQUIRE(tm.m == nullptr && tm.ab_dtype == MG_DT_F32, "mg_masked_reduce: term %d: cross-entropy takes float32 logits and no weight", i);
     }
     prm.terms[i] = tm;
     const int rows = rows_per_cta_for(tm.D, B, T, sms);
     MgFinishSlot& sl = prm.slots[i];
     sl.result = tm.result;
-    sl.D = tm.D;
+    sl.D = tm.kind == MG_RED_CE ? 1 : tm.D;   // the cross-entropy collapses the class axis: its loss has one feature
     sl.rows_per_cta = rows;
     sl.n_chunks = T > 0 ? static_cast<int>((T + rows - 1) / rows) : 1;
-    sl.per_frame = !discrete && (tm.m != nullptr || tm.kind == MG_RED_ROOT_SQDIFF);
+    sl.per_frame = !discrete && (tm.m != nullptr || tm.kind == MG_RED_ROOT_SQDIFF || tm.kind == MG_RED_CE);
     sl.weighted = !discrete && tm.m != nullptr;
     sl.accumulate = tm.accumulate;
     sl.in_total = (tm.flags & MG_FLAG_IN_TOTAL) != 0;

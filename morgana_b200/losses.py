@@ -2,7 +2,8 @@
 
 ``mse(predictions, targets, seq_len=None)`` and ``bce(...)`` keep the reference's signature and semantics --
 ``mean over (batch, feature) of [ sum over valid frames / number of valid frames ]`` -- and return a 0-dim float32 tensor
-that supports ``.backward()``.  ``l1`` is the same wrapper around the absolute error.
+that supports ``.backward()``.  ``l1`` is the same wrapper around the absolute error; ``ce`` takes logits and class
+indices (``morgana/losses.py:59-61``).
 """
 from morgana_b200 import ops
 
@@ -20,3 +21,9 @@ def bce(predictions, targets, seq_len=None):
 def l1(predictions, targets, seq_len=None):
     """Masked mean-absolute error: ``sequence_loss`` applied to ``F.l1_loss(reduction='none')``."""
     return ops.masked_loss(predictions, targets, seq_len, 'l1')
+
+
+def ce(predictions, targets, seq_len=None):
+    """Masked cross-entropy of ``(batch_size, seq_len, n_classes)`` logits against ``(batch_size, seq_len)`` int64 class
+    indices (morgana/losses.py:59-61: ``F.cross_entropy`` over the transposed logits, one value per frame)."""
+    return ops.masked_loss(predictions, targets, seq_len, 'ce')

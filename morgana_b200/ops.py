@@ -344,7 +344,13 @@ def make_term(kind, a, b=None, m=None, result=None, accumulate=False, grad=None,
     term.kind, term.D = kind, D
     term.a, term.a_sb, term.a_st = _ptr(a), a_sb, a_st
     term.ab_dtype = _dtype_code(a)
-    if b is not None:
+    if kind == _lib.RED_CE:
+        _require_cuda(b, 'targets')
+        if b.dtype != torch.int64 or tuple(b.shape) != (B, T):
+            raise TypeError('cross-entropy targets must be int64 class indices of shape (batch_size, seq_len)')
+        term.b, term.b_sb, term.b_st = _ptr(b), b.stride(0), b.stride(1)
+        keep.append(b)
+    elif b is not None:
         _require_cuda(b, 'tensor')
         if tuple(b.shape) != (B, T, D):
             raise RuntimeError('operand shapes differ: {} vs {}'.format(tuple(a.shape), tuple(b.shape)))
@@ -428,7 +434,7 @@ def masked_objective(pred, target, seq_len, cols, slots, grad=None, grad_scale_d
                                       ws.numel(), _stream()), 'mg_masked_objective_f32')
 
 
-_LOSS_KINDS = {'mse': _lib.RED_SQDIFF, 'l1': _lib.RED_ABSDIFF, 'bce': _lib.RED_BCE}
+_LOSS_KINDS = {'mse': _lib.RED_SQDIFF, 'l1': _lib.RED_ABSDIFF, 'bce': _lib.RED_BCE, 'ce': _lib.RED_CE}
 
 
 class _MaskedLossFn(torch.autograd.Function):
@@ -469,9 +475,15 @@ def masked_loss(predictions, targets, seq_len=None, kind='mse'):
     """``mean_{b,d} [ sum_{t < n_b} l(p, y) / n_b ]`` as a 0-dim float32 tensor with autograd."""
     _require_cuda(predictions, 'predictions')
     _require_cuda(targets, 'targets')
-    if predictions.dtype != torch.float32 or targets.dtype != torch.float32:
+    if kind == 'ce':
+        if predictions.dtype != torch.float32 or predictions.dim() != 3 or targets.dtype != torch.int64 or \
+                tuple(targets.shape) != tuple(predictions.shape[:2]):
+            raise RuntimeError('ce takes float32 logits (batch_size, seq_len, n_classes) and int64 targets (batch_size, '
+                               'seq_len), got {} {} and {} {}'.format(predictions.dtype, tuple(predictions.shape),
+                                                                      targets.dtype, tuple(targets.shape)))
+    elif predictions.dtype != torch.float32 or targets.dtype != torch.float32:
         raise TypeError('morgana_b200 losses take float32 tensors, got {} and {}'.format(predictions.dtype, targets.dtype))
-    if predictions.dim() != 3 or predictions.shape != targets.shape:
+    elif predictions.dim() != 3 or predictions.shape != targets.shape:
         raise RuntimeError('predictions and targets must share a (batch_size, seq_len, feat_dim) shape, got {} and {}'
                            .format(tuple(predictions.shape), tuple(targets.shape)))
     if predictions.shape[0] == 0 or predictions.shape[2] == 0:

@@ -79,6 +79,11 @@ def bce_chain(prob, label, lengths=None):
     return _sequence_loss(F.binary_cross_entropy(prob, label, reduction='none'), lengths)
 
 
+def ce_chain(logits, classes, lengths=None):
+    """morgana/losses.py:59-61."""
+    return _sequence_loss(F.cross_entropy(logits.transpose(1, 2), classes, reduction='none').unsqueeze(dim=-1), lengths)
+
+
 def _mean_increment(values, lengths):
     """metrics.Mean.accumulate, morgana/metrics.py:383-394 (with its .item() on the count)."""
     if lengths is None:

@@ -232,6 +232,26 @@ def masked_loss_grad(predictions, targets, seq_len=None, kind='mse', grad_output
     return grad.astype(np.asarray(predictions).dtype)
 
 
+def cross_entropy_loss(logits, targets, seq_len=None):
+    """losses.ce (losses.py:59-61): F.cross_entropy over the class axis gives one value per frame (feature axis of size
+    1), then the masked sequence loss of :func:`masked_loss`.  Returns (loss, gradient w.r.t. the logits)."""
+    x = np.asarray(logits, dtype=np.float64)
+    t = np.asarray(targets)
+    batch_size, max_len, n_classes = x.shape
+    shifted = x - x.max(axis=-1, keepdims=True)
+    log_soft = shifted - np.log(np.exp(shifted).sum(axis=-1, keepdims=True))
+    onehot = np.eye(n_classes)[t]
+    per_frame = -(log_soft * onehot).sum(axis=-1, keepdims=True)                 # (B, T, 1)
+    if seq_len is None:
+        mask, frames = np.ones((batch_size, max_len, 1)), np.full((batch_size, 1, 1), float(max_len))
+    else:
+        mask = sequence_mask(np.asarray(seq_len), max_len, dtype=np.float64)
+        frames = np.asarray(seq_len, dtype=np.float64)[:, None, None]
+    loss = float(((per_frame * mask).sum(axis=1) / frames[:, 0]).mean())
+    grad = (np.exp(log_soft) - onehot) * mask / frames / batch_size
+    return loss, grad.astype(np.asarray(logits).dtype)
+
+
 # ----------------------------------------------------------------------------------------------------------------
 # a8 - a12  streaming-metric accumulators  (morgana/metrics.py:359-694)
 # Each returns the (sum, count) increment that one ``accumulate`` call adds to the metric's state.

@@ -180,6 +180,21 @@ def loss_cases():
             tag = 'loss_%s_bce_%s' % (name, 'masked' if masked else 'full')
             out[tag], out[tag + '_grad'] = value.detach().numpy(), prob.grad.numpy().copy()
 
+    # losses.ce (losses.py:59-61): logits (B, T, C), class indices (B, T)
+    for name, B, T, C in [('ce_small', 4, 9, 5), ('ce_wide', 3, 21, 64)]:
+        seq_len = torch.randint(1, T + 1, (B,), generator=g)
+        seq_len[0] = T
+        logits = (3. * torch.randn(B, T, C, generator=g)).requires_grad_()
+        classes = torch.randint(0, C, (B, T), generator=g)
+        out['loss_%s_logits' % name], out['loss_%s_classes' % name] = logits.detach().numpy(), classes.numpy()
+        out['loss_%s_seq_len' % name] = seq_len.numpy()
+        for masked in (True, False):
+            logits.grad = None
+            value = losses.ce(logits, classes, seq_len if masked else None)
+            value.backward()
+            tag = 'loss_%s_%s' % (name, 'masked' if masked else 'full')
+            out[tag], out[tag + '_grad'] = value.detach().numpy(), logits.grad.numpy().copy()
+
     # Zero-length utterance -> nan.
     pred, tgt = torch.randn(2, 4, 3, generator=g), torch.randn(2, 4, 3, generator=g)
     out['loss_zero_len'] = losses.mse(pred, tgt, torch.tensor([0, 3])).numpy()

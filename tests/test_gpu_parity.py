@@ -299,6 +299,37 @@ def test_to_device_wrapper_prefetches_one_batch_ahead(mg):
         np.testing.assert_allclose(got.numpy(), want, rtol=1e-4)
 
 
+@pytest.mark.parametrize('case', ['ce_small', 'ce_wide'])
+@pytest.mark.parametrize('masked', [True, False])
+def test_cross_entropy_golden(mg, golden, case, masked):
+    """losses.ce (losses.py:59-61) forward and backward against the reference's outputs."""
+    g = golden('losses')
+    logits = dev(g['loss_%s_logits' % case]).requires_grad_()
+    classes = dev(g['loss_%s_classes' % case])
+    seq_len = dev(g['loss_%s_seq_len' % case]) if masked else None
+    tag = 'loss_%s_%s' % (case, 'masked' if masked else 'full')
+    value = mg.losses.ce(logits, classes, seq_len)
+    assert rel_err(value.item(), g[tag]) <= REL
+    (value * 3.).backward()
+    np.testing.assert_allclose(logits.grad.cpu().numpy(), 3. * g[tag + '_grad'], rtol=3e-6, atol=6e-8)   # softmax - onehot cancels near 1
+
+
+def test_cross_entropy_vs_oracle_strided_and_ragged(mg):
+    rng = np.random.default_rng(41)
+    B, T, C = 7, 301, 40
+    wide = (2. * rng.standard_normal((B, T, C + 6))).astype(np.float32)
+    classes = rng.integers(0, C, (B, T))
+    seq_len = rng.integers(1, T + 1, B)
+    logits = dev(wide)[:, :, 3:3 + C].requires_grad_()            # a column slice: strided rows
+    value = mg.losses.ce(logits, dev(classes), dev(seq_len))
+    want, want_grad = O.cross_entropy_loss(wide[:, :, 3:3 + C], classes, seq_len)
+    assert rel_err(value.item(), want) <= REL
+    grad, = torch.autograd.grad(value, logits)
+    np.testing.assert_allclose(grad.cpu().numpy(), want_grad, rtol=3e-6, atol=2e-8)
+    with pytest.raises(RuntimeError):
+        mg.losses.ce(logits, dev(classes).float(), dev(seq_len))
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # a8 - a12 metrics
 # ----------------------------------------------------------------------------------------------------------------------

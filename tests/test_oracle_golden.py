@@ -156,6 +156,22 @@ def test_metric_accumulators(golden, name, masked):
     assert result == pytest.approx(float(g[key + '_result']), rel=REL)
 
 
+@pytest.mark.parametrize('case', ['ce_small', 'ce_wide'])
+@pytest.mark.parametrize('masked', [True, False])
+def test_cross_entropy_loss(golden, case, masked):
+    import torch
+    from oracle import aten_chain as C
+    g = golden('losses')
+    logits, classes = g['loss_%s_logits' % case], g['loss_%s_classes' % case]
+    seq_len = g['loss_%s_seq_len' % case] if masked else None
+    tag = 'loss_%s_%s' % (case, 'masked' if masked else 'full')
+    loss, grad = O.cross_entropy_loss(logits, classes, seq_len)
+    assert loss == pytest.approx(float(g[tag]), rel=REL)
+    np.testing.assert_allclose(grad, g[tag + '_grad'], rtol=3e-6, atol=2e-8)   # softmax - onehot cancels near 1: absolute floor
+    chain = C.ce_chain(torch.from_numpy(logits), torch.from_numpy(classes), None if seq_len is None else torch.from_numpy(seq_len))
+    assert chain.item() == float(g[tag])
+
+
 @pytest.mark.parametrize('masked', [True, False])
 def test_variance_and_tensor_history(golden, masked):
     g = golden('metrics_extra')
