@@ -79,7 +79,7 @@ __global__ void __launch_bounds__(256) mlpg_build_kernel(const MlpgParams prm) {
     const double m = static_cast<double>(__ldg(mean_i + tt * prm.m_st + k * F));
     const double v = static_cast<double>(__ldg(var_i + tt * prm.v_st + k * F));
     tau = 1.0 / v;
-    bt = m / v;
+    bt = m * tau;     // one fp64 division per operand pair (within 1 ulp of m / v)
   };
   // window coefficients at offsets (-1, 0, +1): w0 = (0, 1, 0), w1 = (-0.5, 0, 0.5), w2 = (1, -2, 1)
   double bt0, tau0, bt1[3], tau1[3], bt2[3], tau2[3];
@@ -142,14 +142,21 @@ __global__ void __launch_bounds__(kSolveWarps * 32) mlpg_solve_kernel(const Mlpg
   {
     double d1 = 1., d2 = 1., l1_1 = 0., l2_1 = 0., l2_2 = 0.;       // factor history of rows r-1 / r-2
     double g1 = 0., g2 = 0., a1 = 0., a2 = 0., b1 = 0., b2 = 0., yR0a = 0.;
-    for (int64_t q0 = 0; q0 < m; q0 += kAhead) {
-      double2 pa[kAhead], pb[kAhead];
+    // Software pipeline: the operands of batch k + 1 are requested BEFORE batch k is computed and stored (the stores go
+    // to the same array, so the compiler may not move later loads above them), which hides the memory latency of a batch
+    // under the dependent arithmetic of the previous one.
+    double2 pa[kAhead], pb[kAhead], na[kAhead], nb[kAhead];
+    auto fetch = [&](int64_t q0, double2* fa, double2* fb) {
 #pragma unroll
       for (int u = 0; u < kAhead; ++u) {
         const int64_t r = q0 + u < m ? q0 + u : m - 1;
-        pa[u] = line(start + r)[0];
-        pb[u] = line(start + r)[1];
+        fa[u] = line(start + r)[0];
+        fb[u] = line(start + r)[1];
       }
+    };
+    if (m > 0) fetch(0, pa, pb);
+    for (int64_t q0 = 0; q0 < m; q0 += kAhead) {
+      if (q0 + kAhead < m) fetch(q0 + kAhead, na, nb);
 #pragma unroll
       for (int u = 0; u < kAhead; ++u) {
         const int64_t r = q0 + u;
@@ -181,6 +188,8 @@ __global__ void __launch_bounds__(kSolveWarps * 32) mlpg_solve_kernel(const Mlpg
         l2_2 = l2_1; l2_1 = l2; l1_1 = l1;
         g2 = g1; g1 = yg; a2 = a1; a1 = ya; b2 = b1; b1 = yb;
       }
+#pragma unroll
+      for (int u = 0; u < kAhead; ++u) { pa[u] = na[u]; pb[u] = nb[u]; }
     }
   }
 
@@ -189,15 +198,19 @@ __global__ void __launch_bounds__(kSolveWarps * 32) mlpg_solve_kernel(const Mlpg
   Row5 F0 = {0., 0., 0., 0., 0.}, F1 = F0, E0 = F0, E1 = F0;
   {
     Row5 c1 = {0., 0., 0., 0., 0.}, c2 = c1;
-    for (int64_t q0 = m - 1; q0 >= 0; q0 -= kAhead) {
-      double2 wa[kAhead], wb[kAhead], wc[kAhead];
+    double2 wa[kAhead], wb[kAhead], wc[kAhead], xa[kAhead], xb[kAhead], xc[kAhead];
+    auto fetch = [&](int64_t q0, double2* fa, double2* fb, double2* fc) {
 #pragma unroll
       for (int u = 0; u < kAhead; ++u) {
         const int64_t r = q0 - u >= 0 ? q0 - u : 0;
-        wa[u] = line(start + r)[0];
-        wb[u] = line(start + r)[1];
-        wc[u] = line(start + r)[2];
+        fa[u] = line(start + r)[0];
+        fb[u] = line(start + r)[1];
+        fc[u] = line(start + r)[2];
       }
+    };
+    if (m > 0) fetch(m - 1, wa, wb, wc);
+    for (int64_t q0 = m - 1; q0 >= 0; q0 -= kAhead) {
+      if (q0 - kAhead >= 0) fetch(q0 - kAhead, xa, xb, xc);
 #pragma unroll
       for (int u = 0; u < kAhead; ++u) {
         const int64_t r = q0 - u;
@@ -222,6 +235,8 @@ __global__ void __launch_bounds__(kSolveWarps * 32) mlpg_solve_kernel(const Mlpg
         c2 = c1;
         c1 = c;
       }
+#pragma unroll
+      for (int u = 0; u < kAhead; ++u) { wa[u] = xa[u]; wb[u] = xb[u]; wc[u] = xc[u]; }
     }
   }
 
@@ -294,12 +309,23 @@ __global__ void __launch_bounds__(kSolveWarps * 32) mlpg_solve_kernel(const Mlpg
   // ---- every frame of the chunk: c = g - U_L x_left - U_R x_right (no dependence between frames) -----------------------
   const double xl0 = __shfl_up_sync(MG_FULL_MASK, x0, 1), xl1 = __shfl_up_sync(MG_FULL_MASK, x1, 1);
   const double kl0 = has_left ? xl0 : 0., kl1 = has_left ? xl1 : 0., kr0 = has_right ? x0 : 0., kr1 = has_right ? x1 : 0.;
-  for (int64_t r = 0; r < m; ++r) {
-    const int64_t t = start + r - pad;
-    if (t < 0 || t >= n) continue;
-    const double2 wa = line(start + r)[0], wb = line(start + r)[1], wc = line(start + r)[2];
-    const double c = wa.x - wa.y * kl0 - wb.x * kl1 - wb.y * kr0 - wc.x * kr1;
-    out[t * prm.o_st] = static_cast<float>(c);
+  const int64_t r_lo = max(static_cast<int64_t>(0), pad - start), r_hi = min(m, n + pad - start);   // rows inside [pad, pad + n)
+  for (int64_t q0 = r_lo; q0 < r_hi; q0 += kAhead) {
+    double2 wa[kAhead], wb[kAhead], wc[kAhead];
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      const int64_t r = q0 + u < r_hi ? q0 + u : r_hi - 1;
+      wa[u] = line(start + r)[0];
+      wb[u] = line(start + r)[1];
+      wc[u] = line(start + r)[2];
+    }
+#pragma unroll
+    for (int u = 0; u < kAhead; ++u) {
+      const int64_t r = q0 + u;
+      if (r >= r_hi) break;
+      const double c = wa[u].x - wa[u].y * kl0 - wb[u].x * kl1 - wb[u].y * kr0 - wc[u].x * kr1;
+      out[(start + r - pad) * prm.o_st] = static_cast<float>(c);
+    }
   }
   if (has_right) {
     const int64_t t0 = start + m - pad;

@@ -24,7 +24,13 @@ shapes = [(512, 609), (512,)] + [(2048, 512), (2048, 512), (2048,), (2048,)] * 8
 params = [torch.randn(*s, device=dev) for s in shapes]
 shadow = [torch.randn(*s, device=dev) for s in shapes]
 mean, std = torch.randn(187, device=dev), torch.rand(187, device=dev) + 0.1
+# K8 at the config-4 shape: the mcep stream of 32 utterances (60 static dims), padding 100
+l32 = workloads.linguistic_batch(batch_size=32, seed=1234)
+n32, T32 = l32['n_frames'].to(dev), int(l32['n_frames'].max())
+mlpg_means = torch.randn(32, T32, 180, device=dev)
+mlpg_var = torch.rand(180, device=dev) + 0.3
 for _ in range(2):
+    ops.mlpg(mlpg_means, mlpg_var, padding_size=100, seq_len=n32)
     ops.linear_bf16(x, w1, b1, act='sigmoid', out_dtype=torch.bfloat16)
     ops.linear_bf16(h, w2, b2, act='sigmoid', out_dtype=torch.bfloat16)
     mg.losses.mse(pred, target, n3d)
