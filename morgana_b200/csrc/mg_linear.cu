@@ -84,6 +84,51 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int
                "r"(mg_smem_addr(smem_src))
                : "memory");
 }
+// ---- CTA-pair (cta_group::2) forms: two CTAs of a cluster on one TPC run ONE 256-row MMA; rank 0 (the leader) issues it ----
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;   // clears the CTA-rank bit of a shared-window address: "the leader's copy"
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\nbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// Both CTAs load into their OWN shared memory; the bytes are counted on the LEADER's barrier.
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          mg_smem_addr(smem_dst)),
+      "l"(map), "r"(c0), "r"(c1), "r"(mg_smem_addr(bar) & kPeerBitMask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrives on the barrier at this offset in BOTH CTAs once the leader's MMAs so far are complete.
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   mg_smem_addr(bar)),
+               "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint64_t* bar) {   // arrive on the leader CTA's copy of `bar`
+  asm volatile(
+      "{\n"
+      ".reg .b32 remote;\n"
+      "mapa.shared::cluster.u32 remote, %0, 0;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [remote];\n"
+      "}\n" ::"r"(mg_smem_addr(bar))
+      : "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mg_smem_addr(bar)) : "memory");
 }
@@ -101,13 +146,13 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t smem_addr) {
 }
 
 // kind::f16 instruction descriptor: bf16 x bf16 -> fp32, both operands K-major, M = 128.
-__device__ __forceinline__ uint32_t umma_instr_desc(int n) {
+__device__ __forceinline__ uint32_t umma_instr_desc(int n, int m = kBlockM) {
   uint32_t d = 0;
   d |= 1u << 4;                                   // D format: F32
   d |= 1u << 7;                                   // A format: BF16
   d |= 1u << 10;                                  // B format: BF16
   d |= static_cast<uint32_t>(n >> 3) << 17;       // N / 8
-  d |= static_cast<uint32_t>(kBlockM >> 4) << 24; // M / 16
+  d |= static_cast<uint32_t>(m >> 4) << 24;       // M / 16 (256 for a CTA pair)
   return d;
 }
 
@@ -155,6 +200,12 @@ __device__ __forceinline__ void finish_columns(const uint32_t (&acc)[32], float 
 
 // Persistent kernel: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... (n fastest, so CTAs that run together
 // share A tiles through L2).
+//
+// PAIR: the CTAs of a 2-CTA cluster (one TPC) share one 256 x BLOCK_N tile: each loads its own 128 rows of A and HALF of the
+// B tile, the leader issues tcgen05.mma.cta_group::2 (M = 256) reading both halves, and each CTA's tensor memory receives its
+// own 128 rows.  Per output element only half of B crosses L2 -> shared memory: at N = 512, K = 600 the single-CTA kernel
+// pulls 3.6 GB through L2 for 0.78 GB of HBM traffic and sits at the L2 throughput limit (~6300 B/clk chip-wide).
+template <bool PAIR>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_w,
                       const __grid_constant__ CUtensorMap map_y, const __grid_constant__ GemmParams prm) {
@@ -170,52 +221,70 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   const uint32_t kStageBytes = prm.stage_bytes;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (prm.N + prm.block_n - 1) / prm.block_n;
-  const int m_tiles = (prm.M + kBlockM - 1) / kBlockM;
+  constexpr int kTileM = PAIR ? 2 * kBlockM : kBlockM;          // rows of one (pair-)tile
+  const int m_tiles = (prm.M + kTileM - 1) / kTileM;
   const int total_tiles = n_tiles * m_tiles;
   const int n_kblocks = (prm.K + kBlockK - 1) / kBlockK;
+  const int cta_rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = cta_rank == 0;
+  const int first_tile = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int tile_step = PAIR ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  const int b_rows = PAIR ? prm.block_n / 2 : prm.block_n;      // rows of W this CTA loads per K block
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_w) : "memory");
     if (prm.tma_store) asm volatile("prefetch.tensormap [%0];" ::"l"(&map_y) : "memory");
     for (int s = 0; s < kStages; ++s) { mg_mbar_init(&s_full[s], 1); mg_mbar_init(&s_empty[s], 1); }
-    for (int a = 0; a < kAccStages; ++a) { mg_mbar_init(&s_acc_full[a], 1); mg_mbar_init(&s_acc_empty[a], 1); }
+    for (int a = 0; a < kAccStages; ++a) { mg_mbar_init(&s_acc_full[a], 1); mg_mbar_init(&s_acc_empty[a], PAIR ? 2 : 1); }
     mg_mbar_fence_init();
   }
   for (int i = threadIdx.x; i < kMaxBias; i += kGemmThreads)
     s_bias[i] = (prm.bias != nullptr && i < prm.N) ? __ldg(prm.bias + i) : 0.f;
-  if (warp == 2) {   // one warp owns the TMEM allocation (and frees it at the end)
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mg_smem_addr(&s_tmem_base)), "n"(kTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (warp == 2) {   // one warp owns the TMEM allocation (and frees it at the end); in a pair, the same warp of both CTAs
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mg_smem_addr(&s_tmem_base)), "n"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mg_smem_addr(&s_tmem_base)), "n"(kTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across CTAs
+  else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem_base;
 
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      const uint32_t stage_tx = kATileBytes + static_cast<uint32_t>(prm.block_n) * kBlockK * 2;
+      const uint32_t stage_tx = kATileBytes + static_cast<uint32_t>(b_rows) * kBlockK * 2;   // bytes this CTA loads per stage
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * prm.block_n;
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step) {
+        const int m0 = (tile / n_tiles) * kTileM + cta_rank * kBlockM, n0 = (tile % n_tiles) * prm.block_n + cta_rank * b_rows;
         for (int kb = 0; kb < n_kblocks; ++kb, ++it) {
           const int s = it % kStages;
           if (it >= kStages) mg_mbar_wait(&s_empty[s], static_cast<uint32_t>(((it / kStages) - 1) & 1));
           unsigned char* a_tile = ring + static_cast<size_t>(s) * kStageBytes;
-          mg_mbar_expect_tx(&s_full[s], stage_tx);
-          tma_load_2d(a_tile, &map_x, kb * kBlockK, m0, &s_full[s]);
-          tma_load_2d(a_tile + kATileBytes, &map_w, kb * kBlockK, n0, &s_full[s]);
+          if (PAIR) {
+            if (leader) mg_mbar_expect_tx(&s_full[s], 2 * stage_tx);    // both CTAs' bytes land on the leader's barrier
+            tma_load_2d_pair(a_tile, &map_x, kb * kBlockK, m0, &s_full[s]);
+            tma_load_2d_pair(a_tile + kATileBytes, &map_w, kb * kBlockK, n0, &s_full[s]);
+          } else {
+            mg_mbar_expect_tx(&s_full[s], stage_tx);
+            tma_load_2d(a_tile, &map_x, kb * kBlockK, m0, &s_full[s]);
+            tma_load_2d(a_tile + kATileBytes, &map_w, kb * kBlockK, n0, &s_full[s]);
+          }
         }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = umma_instr_desc(prm.block_n);
+    if (lane == 0 && leader) {
+      const uint32_t idesc = umma_instr_desc(prm.block_n, kTileM);
       int it = 0, t = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
+      for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++t) {
         const int acc = t % kAccStages;
         if (t >= kAccStages) mg_mbar_wait(&s_acc_empty[acc], static_cast<uint32_t>(((t / kAccStages) - 1) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -229,12 +298,14 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 #pragma unroll
           for (int k = 0; k < kBlockK / kUmmaK; ++k) {
             // advancing K by 16 elements = 32 bytes inside the 128-byte swizzle row
-            umma_f16(tmem_d, umma_smem_desc(a_addr + k * kUmmaK * 2), umma_smem_desc(b_addr + k * kUmmaK * 2), idesc,
-                     (kb | k) != 0 ? 1u : 0u);
+            if (PAIR) umma_f16_pair(tmem_d, umma_smem_desc(a_addr + k * kUmmaK * 2), umma_smem_desc(b_addr + k * kUmmaK * 2), idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+            else umma_f16(tmem_d, umma_smem_desc(a_addr + k * kUmmaK * 2), umma_smem_desc(b_addr + k * kUmmaK * 2), idesc,
+                          (kb | k) != 0 ? 1u : 0u);
           }
-          umma_commit(&s_empty[s]);     // frees the stage when the MMAs that read it are done
+          if (PAIR) umma_commit_pair(&s_empty[s]); else umma_commit(&s_empty[s]);   // frees the stage (in both CTAs) when the MMAs that read it are done
         }
-        umma_commit(&s_acc_full[acc]);  // accumulator of this tile complete
+        if (PAIR) umma_commit_pair(&s_acc_full[acc]); else umma_commit(&s_acc_full[acc]);   // accumulator of this tile complete
       }
     }
   } else {
@@ -244,8 +315,11 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     const bool issuer = threadIdx.x == 64;            // first epilogue thread issues the TMA stores
     const int cols_per_chunk = prm.y_is_bf16 ? 64 : 32;   // 128 bytes of output per row per chunk
     int t = 0, chunk_count = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++t) {
-      const int m0 = (tile / n_tiles) * kBlockM, n0 = (tile % n_tiles) * prm.block_n;
+    auto release_accumulator = [&](int acc_stage) {   // this CTA's rows of the accumulator have been read
+      if (PAIR) mbar_arrive_leader(&s_acc_empty[acc_stage]); else mbar_arrive(&s_acc_empty[acc_stage]);
+    };
+    for (int tile = first_tile; tile < total_tiles; tile += tile_step, ++t) {
+      const int m0 = (tile / n_tiles) * kTileM + cta_rank * kBlockM, n0 = (tile % n_tiles) * prm.block_n;
       const int acc = t % kAccStages;
       mg_mbar_wait(&s_acc_full[acc], static_cast<uint32_t>((t / kAccStages) & 1));
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -298,7 +372,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           mg_fence_proxy_async_smem();
           epilogue_barrier();
           if (issuer) {
-            if (c0 + cols_per_chunk >= prm.block_n) mbar_arrive(&s_acc_empty[acc]);
+            if (c0 + cols_per_chunk >= prm.block_n) release_accumulator(acc);
             tma_store_2d(&map_y, n0 + c0, m0, stage);
             mg_bulk_commit();
           }
@@ -317,7 +391,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           if (prm.N <= 8) {
             // a handful of output features (the N = 1 head): lane = row, neighbouring lanes write neighbouring rows
             epilogue_barrier();
-            if (issuer && c0 + 32 >= prm.block_n) mbar_arrive(&s_acc_empty[acc]);
+            if (issuer && c0 + 32 >= prm.block_n) release_accumulator(acc);
             const int row = m0 + tile_row;
             if (row < prm.M) {
               for (int j = 0; j < prm.N - n0 - c0 && j < 32; ++j) {
@@ -332,7 +406,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 #pragma unroll
           for (int j = 0; j < 32; ++j) tile_f[tile_row * 33 + j] = v[j];
           epilogue_barrier();
-          if (issuer && c0 + 32 >= prm.block_n) mbar_arrive(&s_acc_empty[acc]);
+          if (issuer && c0 + 32 >= prm.block_n) release_accumulator(acc);
           const int n_valid = min(32, prm.N - (n0 + c0));
           const int col = epi_tid & 31;
           if (col < n_valid) {
@@ -351,9 +425,11 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (PAIR) cluster_sync_all();   // neither CTA frees tensor memory (or exits) while the peer may still use it
+  else __syncthreads();
   if (warp == 2) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols) : "memory");
   }
 }
 
@@ -429,10 +505,15 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
   int block_n = 256;
   if (N <= 16) block_n = 16; else if (N <= 32) block_n = 32; else if (N <= 64) block_n = 64; else if (N <= 128) block_n = 128;
   { const char* e = getenv("MG_GEMM_BLOCK_N"); if (e && atoi(e) > 0 && atoi(e) < block_n) block_n = atoi(e); }
+  // CTA pairs (256-row tiles, half of the B tile per CTA) when there are enough rows to give every pair several tiles;
+  // MG_GEMM_PAIR=0 / 1 overrides.
+  const int64_t sms = mg_cached_sm_count();
+  bool pair = block_n >= 64 && sms % 2 == 0 && static_cast<int64_t>(M) >= 2 * kBlockM * sms;
+  { const char* e = getenv("MG_GEMM_PAIR"); if (e) pair = atoi(e) != 0 && block_n >= 32 && sms % 2 == 0; }
   CUtensorMap map_x, map_w, map_y;
   int rc = make_map(&map_x, x, M, K, ldx, kBlockK, kBlockM, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   if (rc != MG_OK) return rc;
-  rc = make_map(&map_w, w, N, K, ldw, kBlockK, block_n, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  rc = make_map(&map_w, w, N, K, ldw, kBlockK, pair ? block_n / 2 : block_n, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   if (rc != MG_OK) return rc;
   // The epilogue stores through TMA when the output rows are 16-byte multiples; otherwise (N = 187, 1, ...) directly.
   const int y_elem = y_is_bf16 ? 2 : 4;
@@ -449,22 +530,42 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
   memset(&prm, 0, sizeof(prm));
   prm.bias = bias; prm.y = y; prm.ldy = ldy;
   prm.M = M; prm.N = N; prm.K = K; prm.block_n = block_n; prm.act = act; prm.y_is_bf16 = y_is_bf16; prm.tma_store = tma_store ? 1 : 0;
-  prm.stage_bytes = kATileBytes + static_cast<uint32_t>(block_n) * kBlockK * 2;
+  prm.stage_bytes = kATileBytes + static_cast<uint32_t>(pair ? block_n / 2 : block_n) * kBlockK * 2;
   if (prm.stage_bytes % 1024) prm.stage_bytes = (prm.stage_bytes / 1024 + 1) * 1024;
   prm.n_stages = static_cast<int>(kRingBytes / prm.stage_bytes);
   if (prm.n_stages > kMaxStages) prm.n_stages = kMaxStages;
 
   static bool attr_set = false;
   if (!attr_set) {
-    MG_CUDA_OK(cudaFuncSetAttribute(linear_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem)));
+    MG_CUDA_OK(cudaFuncSetAttribute(linear_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem)));
+    MG_CUDA_OK(cudaFuncSetAttribute(linear_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem)));
     attr_set = true;
   }
   // n fastest: the CTAs that share an A tile are neighbours in launch order, so A is re-read from L2, not HBM.
-  const int64_t n_tiles_total = static_cast<int64_t>((N + block_n - 1) / block_n) * ((M + kBlockM - 1) / kBlockM);
+  const int tile_m = pair ? 2 * kBlockM : kBlockM;
+  const int64_t n_tiles_total = static_cast<int64_t>((N + block_n - 1) / block_n) * ((M + tile_m - 1) / tile_m);
   MG_REQUIRE(n_tiles_total < (int64_t(1) << 31), "mg_linear_bf16: too many tiles");
-  const int64_t sms = mg_cached_sm_count();
-  const unsigned n_ctas = static_cast<unsigned>(n_tiles_total < sms ? n_tiles_total : sms);   // persistent: one CTA per SM
-  linear_tcgen05_kernel<<<n_ctas, kGemmThreads, kGemmSmem, stream>>>(map_x, map_w, map_y, prm);
+  if (pair) {
+    // persistent: one CTA per SM, launched as 2-CTA clusters (a pair shares a TPC)
+    const int64_t n_pairs = n_tiles_total < sms / 2 ? n_tiles_total : sms / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(static_cast<unsigned>(2 * n_pairs));
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = kGemmSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MG_CUDA_OK(cudaLaunchKernelEx(&cfg, linear_tcgen05_kernel<true>, map_x, map_w, map_y, prm));
+  } else {
+    const unsigned n_ctas = static_cast<unsigned>(n_tiles_total < sms ? n_tiles_total : sms);   // persistent: one CTA per SM
+    linear_tcgen05_kernel<false><<<n_ctas, kGemmThreads, kGemmSmem, stream>>>(map_x, map_w, map_y, prm);
+  }
   MG_LAUNCH_OK();
   return MG_OK;
 }
