@@ -505,10 +505,12 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
   int block_n = 256;
   if (N <= 16) block_n = 16; else if (N <= 32) block_n = 32; else if (N <= 64) block_n = 64; else if (N <= 128) block_n = 128;
   { const char* e = getenv("MG_GEMM_BLOCK_N"); if (e && atoi(e) > 0 && atoi(e) < block_n) block_n = atoi(e); }
-  // CTA pairs (256-row tiles, half of the B tile per CTA) when there are enough rows to give every pair several tiles;
-  // MG_GEMM_PAIR=0 / 1 overrides.
+  // CTA pairs (256-row tiles, half of the B tile per CTA) where the B tile dominates the L2 -> shared-memory traffic, i.e.
+  // several 256-wide N tiles (N > 256), and there are enough rows to give every pair several tiles.  Measured on B200 at
+  // M = 349k: 600 -> 512 0.291 -> 0.260 ms with pairs, but 512 -> 128 0.081 -> 0.095 and 256 -> 187 0.251 -> 0.268 (those
+  // layers are HBM-bound, and a pair halves the number of independent tile streams).  MG_GEMM_PAIR=0 / 1 overrides.
   const int64_t sms = mg_cached_sm_count();
-  bool pair = block_n >= 64 && sms % 2 == 0 && static_cast<int64_t>(M) >= 2 * kBlockM * sms;
+  bool pair = N > 256 && sms % 2 == 0 && static_cast<int64_t>(M) >= 2 * kBlockM * sms;
   { const char* e = getenv("MG_GEMM_PAIR"); if (e) pair = atoi(e) != 0 && block_n >= 32 && sms % 2 == 0; }
   CUtensorMap map_x, map_w, map_y;
   int rc = make_map(&map_x, x, M, K, ldx, kBlockK, kBlockM, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);

@@ -645,6 +645,27 @@ def test_pad_collate_matches_host_padding(mg, D, dtype):
     assert np.array_equal(got[:, :T].cpu().numpy(), want) and not got[:, T:].any()
 
 
+@pytest.mark.parametrize('M,K,N,act,out_dtype', [(300, 600, 512, 'sigmoid', torch.bfloat16), (1000, 40, 96, None, torch.float32),
+                                                  (517, 256, 187, None, torch.float32), (256, 64, 64, 'sigmoid', torch.float32)])
+def test_linear_cta_pair_equals_single_cta(mg, monkeypatch, M, K, N, act, out_dtype):
+    """The 2-CTA (cta_group::2, 256-row tile) form of K7 against the single-CTA form: same K order per output element, so
+    the results are identical; ragged M (second CTA of the last pair partly / wholly outside the matrix) included."""
+    from morgana_b200 import ops
+    rng = np.random.default_rng(M + K + N)
+    x = dev(rng.standard_normal((M, K)).astype(np.float32)).to(torch.bfloat16)
+    w = dev((rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)).to(torch.bfloat16)
+    if K % 8:
+        x, w = torch.nn.functional.pad(x, (0, 8 - K % 8)), torch.nn.functional.pad(w, (0, 8 - K % 8))
+    bias = dev(rng.standard_normal(N).astype(np.float32))
+    monkeypatch.setenv('MG_GEMM_PAIR', '0')
+    single = ops.linear_bf16(x, w, bias, act=act, out_dtype=out_dtype)
+    monkeypatch.setenv('MG_GEMM_PAIR', '1')
+    paired = ops.linear_bf16(x, w, bias, act=act, out_dtype=out_dtype)
+    assert torch.equal(single, paired)
+    want = O.linear(x.float().cpu().numpy()[:, :K], w.float().cpu().numpy()[:, :K], bias.cpu().numpy(), act)
+    np.testing.assert_allclose(paired.float().cpu().numpy(), want, rtol=2e-2, atol=2e-2)
+
+
 def test_nn_linear_module_forward_backward(mg):
     """README MLP stack (600 -> 512 -> 128 -> 32 -> 1) through morgana_b200.nn.Linear against fp32 torch.nn layers."""
     from morgana_b200 import nn as mnn
