@@ -646,6 +646,7 @@ def test_pad_collate_matches_host_padding(mg, D, dtype):
 
 
 @pytest.mark.parametrize('M,K,N,act,out_dtype', [(300, 600, 512, 'sigmoid', torch.bfloat16), (1000, 40, 96, None, torch.float32),
+                                                  (700, 136, 400, 'sigmoid', torch.float32), (513, 72, 1000, None, torch.bfloat16),
                                                   (517, 256, 187, None, torch.float32), (256, 64, 64, 'sigmoid', torch.float32)])
 def test_linear_cta_pair_equals_single_cta(mg, monkeypatch, M, K, N, act, out_dtype):
     """The 2-CTA (cta_group::2, 256-row tile) form of K7 against the single-CTA form: same K order per output element, so
@@ -660,8 +661,12 @@ def test_linear_cta_pair_equals_single_cta(mg, monkeypatch, M, K, N, act, out_dt
     monkeypatch.setenv('MG_GEMM_PAIR', '0')
     single = ops.linear_bf16(x, w, bias, act=act, out_dtype=out_dtype)
     monkeypatch.setenv('MG_GEMM_PAIR', '1')
+    monkeypatch.setenv('MG_GEMM_WIDE', '0')
     paired = ops.linear_bf16(x, w, bias, act=act, out_dtype=out_dtype)
     assert torch.equal(single, paired)
+    monkeypatch.setenv('MG_GEMM_WIDE', '1')                  # 256 x 512 pair tiles (taken when N > 256)
+    wide = ops.linear_bf16(x, w, bias, act=act, out_dtype=out_dtype)
+    assert torch.equal(single, wide)
     want = O.linear(x.float().cpu().numpy()[:, :K], w.float().cpu().numpy()[:, :K], bias.cpu().numpy(), act)
     np.testing.assert_allclose(paired.float().cpu().numpy(), want, rtol=2e-2, atol=2e-2)
 
