@@ -276,8 +276,9 @@ int mg_ema_update_f32(float* const* shadow, const float* const* param, const int
  *     y[M, N] = act(x[M, K] @ w[N, K]^T + bias[N]),  bf16 operands, fp32 accumulation in TMEM.
  *
  * x          (M, K) bf16, row stride ldx (elements, multiple of 8); K multiple of 8.
- * w          (N, K) bf16, row stride ldw (multiple of 8).
+ * w          (N, K) bf16, row stride ldw (multiple of 8); N <= 2048 (the bias is staged in shared memory).
  * y          (M, N) fp32 (y_is_bf16 = 0) or bf16 (= 1), row stride ldy.
+ * For N > 256 and M >= 256 * #SMs the kernel runs as 2-CTA clusters (tcgen05.mma.cta_group::2); same results.
  * act        MG_ACT_NONE | MG_ACT_SIGMOID.
  */
 #define MG_ACT_NONE 0
