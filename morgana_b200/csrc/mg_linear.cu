@@ -170,6 +170,7 @@ __device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(mg_smem_addr(bar)) : "memory");
 }
+// Issues the load only: tmem_ld_wait() must follow before the registers are read (several loads may share one wait).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -180,8 +181,8 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
         "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
         "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // bias + activation on 32 accumulator columns; `bias32` points at this chunk's 32 biases in shared memory (zero-padded).
 // Sigmoid as ex2 + rcp (two MUFU ops): the layer's operands are bf16, so approximate-division accuracy (~1e-7) is ample.
@@ -367,9 +368,12 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             group_barrier();
           }
           uint4* dst_row = reinterpret_cast<uint4*>(stage + tile_row * 128);
-          uint32_t a0[32];
+          uint32_t a0[32], a1[32];
           float v[32];
+          const bool second_half = prm.y_is_bf16 && c0 + 32 < prm.block_n;
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), a0);
+          if (second_half) tmem_ld_32x32(taddr + static_cast<uint32_t>(c0 + 32), a1);   // both loads in flight, one wait
+          tmem_ld_wait();
           finish_columns(a0, v, s_bias + n0 + c0, prm.act);
           if (!prm.y_is_bf16) {
 #pragma unroll
@@ -377,10 +381,8 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
               dst_row[j ^ (tile_row & 7)] = make_uint4(__float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]),
                                                        __float_as_uint(v[4 * j + 2]), __float_as_uint(v[4 * j + 3]));
           } else {
-            uint32_t a1[32];
             float v1[32];
-            if (c0 + 32 < prm.block_n) {
-              tmem_ld_32x32(taddr + static_cast<uint32_t>(c0 + 32), a1);
+            if (second_half) {
               finish_columns(a1, v1, s_bias + n0 + c0 + 32, prm.act);
             } else {
 #pragma unroll
@@ -418,6 +420,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           uint32_t a0[32];
           float v[32];
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), a0);
+          tmem_ld_wait();
           finish_columns(a0, v, s_bias + n0 + c0, prm.act);
           if (ci == last_chunk) asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           if (prm.N <= 8) {
