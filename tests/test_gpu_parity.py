@@ -862,3 +862,55 @@ def test_torch_custom_ops_match_the_direct_path(mg, golden):
     want_s = O.ema_update(s.cpu().numpy().copy(), q.cpu().numpy(), 0.99)
     torch.ops.morgana_b200.ema_update([s], [q], 1.0 - 0.99)
     assert np.array_equal(s.cpu().numpy(), want_s)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# "next" row 2: the epoch loops on the device (single process; the two-rank logic is covered by tests/test_dp_gloo.py)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_trainer_epochs_on_device(mg):
+    """DataParallelTrainer with the real pieces: tcgen05 layers, masked mse through K4, device-resident metric records,
+    the multi-tensor EMA, a prefetching feeder; against the same loop written out with stock torch ops in fp32."""
+    from morgana_b200 import nn as mnn, trainer as T
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            torch.manual_seed(5)
+            self.l1 = mnn.Linear(40, 64, act='sigmoid', device='cuda')
+            self.l2 = mnn.Linear(64, 3, device='cuda')
+            self.mode, self.step = '', 0
+            self.metrics = mg.metrics.Handler(loss=mg.metrics.Mean())
+            self.metrics.add_metrics('all', err=mg.metrics.RMSE())
+
+        def forward(self, features):
+            frames = mg.utils.upsample_to_repetitions(features['lab'], features['dur'], max_len=features['T'])
+            pred = self.l2(self.l1(frames))
+            self.metrics.accumulate(self.mode, err=(features['target'], pred.detach(), features['n_frames']))
+            return mg.losses.mse(pred, features['target'], features['n_frames']), {'pred': pred}
+
+    g = torch.Generator().manual_seed(9)
+    batches = []
+    for _ in range(4):
+        dur = torch.randint(1, 6, (6, 11, 1), generator=g)
+        n_frames = dur.sum(dim=(1, 2))
+        lab = torch.rand(6, 11, 40, generator=g)
+        frames = torch.from_numpy(O.upsample_to_repetitions(lab.numpy(), dur.numpy()[:, :, 0]))
+        target = torch.stack([frames[:, :, :5].sum(-1), frames[:, :, 5:9].mean(-1), frames[:, :, 9] * 2.], dim=-1)
+        batches.append({'lab': lab, 'dur': dur, 'n_frames': n_frames, 'target': target, 'T': int(n_frames.max()), 'name': ['x']})
+    model, ema_model = Model(), Model()
+    tr = T.DataParallelTrainer(model, ema_model=ema_model, ema_decay=0.9)
+    before = [p.detach().clone() for p in ema_model.parameters()]
+    opt = torch.optim.Adam(model.parameters(), lr=0.01, fused=True)
+    losses = []
+    for tr.epoch in range(1, 6):
+        losses.append(tr.train_epoch(mg.data.ToDeviceWrapper(batches, 'cuda'), opt))
+    assert model.step == 20 and losses[-1] < 0.6 * losses[0]
+    train = model.metrics.results_as_json_dict('train')
+    assert set(train) == {'loss', 'err'} and train['loss'] == pytest.approx(losses[-1], rel=1e-5)
+    assert train['err'] == pytest.approx(np.sqrt(train['loss']), rel=1e-4)      # rmse over frames x dims == sqrt(mse) here
+    assert all(p.grad.untyped_storage().data_ptr() == tr.bucket.flat.untyped_storage().data_ptr() for p in model.parameters())
+    # the EMA model moved towards the trained weights and validates into its own handler
+    assert all(not torch.equal(a, b.detach()) for a, b in zip(before, ema_model.parameters()))
+    valid_loss = tr.valid_epoch(mg.data.ToDeviceWrapper(batches, 'cuda'), model=tr.ema.model)
+    assert np.isfinite(valid_loss) and ema_model.metrics.results_as_json_dict('valid')['loss'] == pytest.approx(valid_loss, rel=1e-5)
+    assert model.metrics.results_as_json_dict('valid') == {}
