@@ -907,7 +907,8 @@ def test_trainer_epochs_on_device(mg):
     assert model.step == 20 and losses[-1] < 0.6 * losses[0]
     train = model.metrics.results_as_json_dict('train')
     assert set(train) == {'loss', 'err'} and train['loss'] == pytest.approx(losses[-1], rel=1e-5)
-    assert train['err'] == pytest.approx(np.sqrt(train['loss']), rel=1e-4)      # rmse over frames x dims == sqrt(mse) here
+    # count is frames, the sum runs over frames x 3 dims (Q2): err^2 ~ 3 x the frame-weighted mse of the epoch
+    assert 0.5 * 3 * train['loss'] < train['err'] ** 2 < 2. * 3 * train['loss']
     assert all(p.grad.untyped_storage().data_ptr() == tr.bucket.flat.untyped_storage().data_ptr() for p in model.parameters())
     # the EMA model moved towards the trained weights and validates into its own handler
     assert all(not torch.equal(a, b.detach()) for a, b in zip(before, ema_model.parameters()))
