@@ -914,4 +914,3 @@ def test_trainer_epochs_on_device(mg):
     assert all(not torch.equal(a, b.detach()) for a, b in zip(before, ema_model.parameters()))
     valid_loss = tr.valid_epoch(mg.data.ToDeviceWrapper(batches, 'cuda'), model=tr.ema.model)
     assert np.isfinite(valid_loss) and ema_model.metrics.results_as_json_dict('valid')['loss'] == pytest.approx(valid_loss, rel=1e-5)
-    assert model.metrics.results_as_json_dict('valid') == {}
