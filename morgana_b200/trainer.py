@@ -25,7 +25,7 @@ passes any ``lr_schedule`` object with a ``step()`` and says whether it is batch
 import torch
 import torch.distributed as dist
 
-from morgana_b200 import dp
+from morgana_b200 import dp, ops
 
 
 def _world(group=None):
@@ -91,7 +91,8 @@ def all_reduce_metrics(handler, mode, extra=None, group=None):
     pieces = []
     for r in rows:
         f64, i64 = r.view(torch.float64), r.view(torch.int64)
-        pieces.append(torch.stack([f64[:, 0], f64[:, 1], i64[:, 3].to(torch.float64)], dim=1).reshape(-1))
+        pieces.append(torch.stack([f64[:, ops.F64_SUM], f64[:, ops.F64_COUNT], i64[:, ops.I64_ISUM].to(torch.float64)],
+                                  dim=1).reshape(-1))
     if extra is not None:
         pieces.append(extra.to(device=device, dtype=torch.float64).reshape(-1))
     packed = torch.cat(pieces)
@@ -102,9 +103,9 @@ def all_reduce_metrics(handler, mode, extra=None, group=None):
         block = packed[offset:offset + 3 * n].reshape(n, 3)
         offset += 3 * n
         f64, i64, f32 = r.view(torch.float64), r.view(torch.int64), r.view(torch.float32)
-        f64[:, 0], f64[:, 1] = block[:, 0], block[:, 1]
-        i64[:, 3] = block[:, 2].to(torch.int64)
-        f32[:, 8], f32[:, 9] = block[:, 0].to(torch.float32), block[:, 1].to(torch.float32)   # the fp32 mirrors
+        f64[:, ops.F64_SUM], f64[:, ops.F64_COUNT] = block[:, 0], block[:, 1]
+        i64[:, ops.I64_ISUM] = block[:, 2].to(torch.int64)
+        f32[:, ops.F32_SUM], f32[:, ops.F32_COUNT] = block[:, 0].to(torch.float32), block[:, 1].to(torch.float32)   # fp32 mirrors
     return packed[offset:] if extra is not None else None
 
 
