@@ -138,3 +138,49 @@ def test_ema_converges_to_the_parameters(mg):
         mg.ops.ema_update(list(zip(s, p)), 0.1)
     for a, b in zip(s, p):
         assert (a - b).abs().max().item() <= 1e-6 * b.abs().max().item() + 1e-6
+
+
+def test_objective_full_size_properties(mg):
+    """Config 3 at full size (1024 utterances, 300..1200 frames, 187 dims; ~0.9 GB per tensor), through properties that
+    need no oracle: the fused objective equals the four separate losses, the gradient obeys sum(grad * (p - y)) = 2 * mse
+    on the squared-error columns and is exactly zero in the padding, metric state is additive over shards, and two runs
+    are bit-identical (deterministic reductions)."""
+    from morgana_b200 import workloads
+    from morgana_b200.fused import AcousticObjective
+    B, T, D = 1024, 1200, 187
+    n = workloads.acoustic_lengths(batch_size=B, min_frames=300, max_frames=T, seed=1234).cuda()
+    g = torch.Generator(device='cuda').manual_seed(1234)
+    target = torch.randn(B, T, D, generator=g, device='cuda')
+    pred = target + 0.1 * torch.randn(B, T, D, generator=g, device='cuda')
+    target[:, :, 0] = 5. + 0.3 * target[:, :, 0]
+    pred[:, :, 0] = target[:, :, 0] + 0.05 * pred[:, :, 0]
+    target[:, :, 3] = (torch.rand(B, T, generator=g, device='cuda') < 0.6).float()
+    pred[:, :, 3] = torch.sigmoid(torch.randn(B, T, generator=g, device='cuda'))
+
+    objective = AcousticObjective()
+    total, grad = objective(pred, target, n)
+    parts = (mg.losses.mse(pred[..., 0:3], target[..., 0:3], n) + mg.losses.mse(pred[..., 4:184], target[..., 4:184], n) +
+             mg.losses.mse(pred[..., 184:187], target[..., 184:187], n) + mg.losses.bce(pred[..., 3:4], target[..., 3:4], n)) / 4.
+    assert abs(total.item() - parts.item()) <= 1e-6 * abs(parts.item())
+
+    # d/dp of mean_b mean_d sum_t (p - y)^2 / n_b, weighted by (p - y), gives back 2 x that loss (x 1/4 for the total)
+    sq_cols = [c for c in range(D) if c != 3]
+    inner = (grad[..., sq_cols].double() * (pred[..., sq_cols] - target[..., sq_cols]).double()).sum().item()
+    three_mse = 4. * parts.item() - mg.losses.bce(pred[..., 3:4], target[..., 3:4], n).item()
+    assert abs(inner - 2. * three_mse / 4.) <= 2e-6 * abs(three_mse)
+    padding = torch.arange(T, device='cuda')[None, :] >= n[:, None]
+    assert not grad[padding].any()
+
+    whole = dict(objective.metrics)
+    sums = {k: (float(m.sum), float(m.count)) for k, m in whole.items()}
+    sharded = AcousticObjective()
+    for i in range(4):
+        sl = slice(i * 256, (i + 1) * 256)
+        sharded(pred[sl], target[sl], n[sl], want_grad=False)
+    for k, m in sharded.metrics.items():
+        assert float(m.count) == sums[k][1], k
+        assert abs(float(m.sum) - sums[k][0]) <= 1e-6 * abs(sums[k][0]), k
+
+    again = AcousticObjective()
+    total2, grad2 = again(pred, target, n)
+    assert total2.item() == total.item() and torch.equal(grad, grad2)
