@@ -211,7 +211,9 @@ typedef struct mg_term_result {
 } mg_term_result;
 
 /* Bytes of workspace mg_masked_reduce needs for this geometry.  The workspace must be zero-filled ONCE when it is
- * allocated; the kernel leaves it clean for the next launch.  One workspace per concurrently-used stream. */
+ * allocated; the kernel leaves it clean for the next launch -- of ANY geometry the workspace is large enough for (the
+ * ticket area at its start has a fixed size, so changing B or n_terms between launches is safe).  One workspace per
+ * concurrently-used stream. */
 int64_t mg_masked_reduce_workspace_bytes(int n_terms, int B, int64_t T);
 
 int mg_masked_reduce(const mg_term* terms /* host array */, int n_terms, const int64_t* seq_len /* (B,) or NULL */,

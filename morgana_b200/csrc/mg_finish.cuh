@@ -24,6 +24,11 @@ struct MgFinishSlot {
 };
 
 // Workspace carved by the host: [global ticket | per-utterance tickets | per-utterance totals | per-CTA partials].
+// The kernels leave every TICKET at zero, so a workspace is zeroed once and reused; totals and partials are overwritten
+// before they are read and may hold anything.  The ticket area therefore has a FIXED size (the largest supported batch):
+// with a batch-dependent size, the tickets of a larger batch would land on stale totals / partials of a smaller one.
+constexpr int64_t kMgMaxBatch = 65536;
+constexpr int64_t kMgTicketBytes = 256 + kMgMaxBatch * 4;
 struct MgWorkspace {
   unsigned int* ticket;       // 1
   unsigned int* utt_ticket;   // [B]
@@ -32,8 +37,7 @@ struct MgWorkspace {
 };
 
 static inline int64_t mg_workspace_bytes(int n_slots, int B) {
-  const int64_t tickets = 256 + ((static_cast<int64_t>(B) * 4 + 255) / 256) * 256;
-  return tickets + static_cast<int64_t>(n_slots) * B * (1 + kMgMaxChunks) * static_cast<int64_t>(sizeof(double2));
+  return kMgTicketBytes + static_cast<int64_t>(n_slots) * B * (1 + kMgMaxChunks) * static_cast<int64_t>(sizeof(double2));
 }
 
 static inline MgWorkspace mg_carve_workspace(void* workspace, int n_slots, int B) {
@@ -41,7 +45,7 @@ static inline MgWorkspace mg_carve_workspace(void* workspace, int n_slots, int B
   unsigned char* base = static_cast<unsigned char*>(workspace);
   ws.ticket = reinterpret_cast<unsigned int*>(base);
   ws.utt_ticket = reinterpret_cast<unsigned int*>(base + 256);
-  base += 256 + ((static_cast<int64_t>(B) * 4 + 255) / 256) * 256;
+  base += kMgTicketBytes;
   ws.utt_total = reinterpret_cast<double2*>(base);
   ws.partials = ws.utt_total + static_cast<int64_t>(n_slots) * B;
   return ws;

@@ -330,6 +330,30 @@ def test_cross_entropy_vs_oracle_strided_and_ragged(mg):
         mg.losses.ce(logits, dev(classes).float(), dev(seq_len))
 
 
+def test_reductions_reuse_their_workspace_across_batch_sizes(mg):
+    """The per-stream workspace is zeroed once and reused: a small batch followed by a larger one (the last batch of an
+    epoch, then the next epoch; validation after training) must not see the small batch's partial sums as tickets."""
+    from morgana_b200.fused import AcousticObjective
+    rng = np.random.default_rng(77)
+    T = 90
+    results = []
+    for B in (6, 3, 48, 5, 200, 48):
+        n = rng.integers(1, T + 1, B)
+        tgt = rng.standard_normal((B, T, 187)).astype(np.float32)
+        pred = (tgt + 0.1 * rng.standard_normal((B, T, 187))).astype(np.float32)
+        tgt[:, :, 3] = rng.random((B, T)) < 0.6
+        pred[:, :, 3] = 1. / (1. + np.exp(-rng.standard_normal((B, T))))
+        got = mg.losses.mse(dev(pred[..., 4:184]), dev(tgt[..., 4:184]), dev(n)).item()
+        want = O.masked_loss(pred[..., 4:184], tgt[..., 4:184], n)
+        assert rel_err(got, want) <= REL, B
+        total, _ = AcousticObjective()(dev(pred), dev(tgt), dev(n))
+        want_total = (O.masked_loss(pred[..., 0:3], tgt[..., 0:3], n) + want + O.masked_loss(pred[..., 184:187], tgt[..., 184:187], n)
+                      + O.masked_loss(pred[..., 3:4], tgt[..., 3:4], n, 'bce')) / 4.
+        assert rel_err(total.item(), want_total) <= REL, B
+        results.append(total.item())
+    assert all(np.isfinite(results)) and min(results) > 0.
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # a8 - a12 metrics
 # ----------------------------------------------------------------------------------------------------------------------
