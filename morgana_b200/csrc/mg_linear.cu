@@ -577,7 +577,10 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
   prm.n_stages = static_cast<int>(kRingBytes / prm.stage_bytes);
   if (prm.n_stages > kMaxStages) prm.n_stages = kMaxStages;
 
-  static bool attr_set = false;
+  static bool attr_done[64] = {};   // the attribute is per device (several GPUs in one process are allowed)
+  int device = 0;
+  MG_CUDA_OK(cudaGetDevice(&device));
+  bool& attr_set = attr_done[device & 63];
   if (!attr_set) {
     MG_CUDA_OK(cudaFuncSetAttribute(linear_tcgen05_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem)));
     MG_CUDA_OK(cudaFuncSetAttribute(linear_tcgen05_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kGemmSmem)));
