@@ -184,3 +184,95 @@ def test_objective_full_size_properties(mg):
     again = AcousticObjective()
     total2, grad2 = again(pred, target, n)
     assert total2.item() == total.item() and torch.equal(grad, grad2)
+
+
+def test_interleaved_calls_with_changing_shapes(mg):
+    """Every op keeps some state between calls (per-stream workspaces, pointer tables, cached attributes, metric records):
+    a seeded random walk over ops and shapes, each result checked against the oracle, looks for state that leaks from one
+    geometry into the next."""
+    from oracle import np_oracle as O
+    from morgana_b200 import ops
+    from morgana_b200.fused import AcousticObjective
+    from morgana_b200.viz.synthesis import MLPG
+    rng = np.random.default_rng(2026)
+    dev = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()   # noqa: E731
+    rel = lambda got, want: abs(float(got) - float(want)) / max(abs(float(want)), 1e-30)   # noqa: E731
+    rmse, objective = mg.metrics.RMSE(), AcousticObjective()
+    rmse.reset_state()
+    rmse_sum = rmse_count = 0.
+    obj_sum = obj_count = 0.
+    for step in range(60):
+        op = rng.integers(0, 9)
+        B, T = int(rng.integers(1, 70)), int(rng.integers(1, 130))
+        n = rng.integers(1, T + 1, B)
+        if op == 0:      # K1 + K2, fused normalisation
+            P, D = int(rng.integers(1, 40)), int(rng.choice([1, 5, 64, 187, 600]))
+            x, dur = rng.random((B, P, D), dtype=np.float32), rng.integers(0, 7, (B, P))
+            lo, hi = rng.standard_normal(D).astype(np.float32), (rng.standard_normal(D) + 3).astype(np.float32)
+            got = mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=('minmax', dev(lo), dev(hi)))
+            assert np.array_equal(got.cpu().numpy(), O.normalise_upsample(x, dur, 'minmax', lo, hi)), step
+        elif op == 1:    # K4: a loss with its gradient
+            D = int(rng.choice([1, 3, 60, 187]))
+            kind = str(rng.choice(['mse', 'l1']))
+            p = dev(rng.standard_normal((B, T, D)).astype(np.float32)).requires_grad_()
+            y = rng.standard_normal((B, T, D)).astype(np.float32)
+            value = getattr(mg.losses, kind)(p, dev(y), dev(n))
+            grad, = torch.autograd.grad(value, p)
+            assert rel(value.item(), O.masked_loss(p.detach().cpu().numpy(), y, n, kind)) <= 1e-6, step
+            np.testing.assert_allclose(grad.cpu().numpy(), O.masked_loss_grad(p.detach().cpu().numpy(), y, n, kind), rtol=3e-6, atol=1e-12)
+        elif op == 2:    # K5: a metric whose state spans the whole walk
+            D = int(rng.choice([1, 7, 60]))
+            a, b = rng.standard_normal((B, T, D)).astype(np.float32), rng.standard_normal((B, T, D)).astype(np.float32)
+            rmse.accumulate(dev(a), dev(b), seq_len=dev(n))
+            s, c = O.rmse_acc(a, b, n)
+            rmse_sum, rmse_count = rmse_sum + s, rmse_count + c
+            assert float(rmse.count) == rmse_count and rel(rmse.sum, rmse_sum) <= 2e-6, step
+        elif op == 3:    # K4b
+            y = rng.standard_normal((B, T, 187)).astype(np.float32)
+            p = (y + 0.1 * rng.standard_normal((B, T, 187))).astype(np.float32)
+            y[:, :, 3] = rng.random((B, T)) < 0.6
+            p[:, :, 3] = 1. / (1. + np.exp(-rng.standard_normal((B, T))))
+            total, grad = objective(dev(p), dev(y), dev(n))
+            want = (O.masked_loss(p[..., 0:3], y[..., 0:3], n) + O.masked_loss(p[..., 4:184], y[..., 4:184], n) +
+                    O.masked_loss(p[..., 184:187], y[..., 184:187], n) + O.masked_loss(p[..., 3:4], y[..., 3:4], n, 'bce')) / 4.
+            assert rel(total.item(), want) <= 1e-6, step
+            s, c = O.melcep_acc(y[..., 4:64], p[..., 4:64], n)
+            obj_sum, obj_count = obj_sum + s, obj_count + c
+            got = objective.metrics['MCEP_distortion']
+            assert float(got.count) == obj_count and rel(got.sum, obj_sum) <= 2e-6, step
+        elif op == 4:    # K6
+            shapes = [tuple(int(v) for v in rng.integers(1, 40, int(rng.integers(1, 3)))) for _ in range(int(rng.integers(1, 6)))]
+            shadow = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+            param = [rng.standard_normal(s).astype(np.float32) for s in shapes]
+            s_dev, p_dev = [dev(s) for s in shadow], [dev(p) for p in param]
+            ops.ema_update(list(zip(s_dev, p_dev)), 1. - 0.99)
+            for got, s, p in zip(s_dev, shadow, param):
+                assert np.array_equal(got.cpu().numpy(), O.ema_update(s.copy(), p, 0.99)), step
+        elif op == 5:    # K7, all tile shapes
+            M, K, N = int(rng.integers(1, 700)), int(rng.choice([8, 40, 64, 600])), int(rng.choice([1, 3, 32, 187, 300, 512]))
+            x = dev(rng.standard_normal((M, K)).astype(np.float32)).to(torch.bfloat16)
+            w = dev((rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)).to(torch.bfloat16)
+            bias = rng.standard_normal(N).astype(np.float32)
+            act = [None, 'sigmoid'][int(rng.integers(0, 2))]
+            got = ops.linear_bf16(x, w, dev(bias), act=act)
+            want = O.linear(x.float().cpu().numpy(), w.float().cpu().numpy(), bias, act)
+            np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-3, atol=2e-3)
+        elif op == 6:    # K8
+            F, pad = int(rng.choice([1, 2, 5])), int(rng.choice([0, 3, 100]))
+            means = rng.standard_normal((B, T, 3 * F)).astype(np.float32)
+            var = (rng.random(3 * F) + 0.3).astype(np.float32)
+            got = MLPG(dev(means), dev(var), padding_size=pad, seq_len=dev(n))
+            np.testing.assert_allclose(got.cpu().numpy(), O.mlpg_banded(means, var, padding_size=pad, seq_len=n), rtol=1e-5, atol=1e-5)
+        elif op == 7:    # K0 + the row packer: a round trip
+            D = int(rng.choice([1, 9, 187]))
+            x = rng.standard_normal((B, T, D)).astype(np.float32)
+            packed = mg.utils.batched_masked_select(dev(x), dev(n))
+            assert np.array_equal(packed.cpu().numpy(), O.batched_masked_select(x, n)), step
+            padded = mg.data.pad_collate(packed, dev(n), max_len=T)
+            assert np.array_equal(padded.cpu().numpy(), x * (np.arange(T)[None, :] < n[:, None])[:, :, None]), step
+        else:            # K3
+            D = int(rng.choice([1, 9, 187, 600]))
+            x = rng.standard_normal((B, T, D)).astype(np.float32)
+            mean, std = rng.standard_normal(D).astype(np.float32), (rng.random(D) + 0.1).astype(np.float32)
+            assert np.array_equal(mg.data.normalise_mvn(dev(x), dev(mean), dev(std)).cpu().numpy(), O.normalise_mvn(x, mean, std)), step
+            assert np.array_equal(mg.data.denormalise_mvn(dev(x), dev(mean), dev(std)).cpu().numpy(), O.denormalise_mvn(x, mean, std)), step
