@@ -94,7 +94,7 @@ def test_fused_normalise_upsample_golden(mg, golden, kind, path):
 
 
 @pytest.mark.parametrize('B,P,D,max_dur', [(7, 33, 600, 30), (3, 70, 187, 12), (16, 5, 4, 300), (2, 300, 64, 3),
-                                             (5, 20, 609, 9), (1, 1, 8, 1)])
+                                             (5, 20, 609, 9), (1, 1, 8, 1), (2, 9000, 4, 2)])   # last: more items than the smem scan row
 @pytest.mark.parametrize('kind', [None, 'minmax', 'mvn'])
 def test_fused_vs_oracle_random(mg, B, P, D, max_dur, kind):
     rng = np.random.default_rng(B * 1000 + P + D)
@@ -116,6 +116,14 @@ def test_fused_vs_oracle_random(mg, B, P, D, max_dur, kind):
         norm = (kind, dev(p0), dev(p1))
     got = mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=norm)
     assert np.array_equal(got.cpu().numpy(), want)
+    for path in ('bulk', 'direct'):
+        assert torch.equal(mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=norm, path=path), got), path
+    if kind is None:   # the segment-sum backward against the oracle
+        xg = dev(x).requires_grad_()
+        out = mg.utils.upsample_to_repetitions(xg, dev(dur))
+        upstream = rng.standard_normal(out.shape).astype(np.float32)
+        out.backward(dev(upstream))
+        np.testing.assert_allclose(xg.grad.cpu().numpy(), O.upsample_backward(upstream, dur), rtol=1e-5, atol=1e-5)
 
 
 def test_fused_speaker_dependent_params(mg):
