@@ -116,7 +116,7 @@ def test_fused_vs_oracle_random(mg, B, P, D, max_dur, kind):
         norm = (kind, dev(p0), dev(p1))
     got = mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=norm)
     assert np.array_equal(got.cpu().numpy(), want)
-    for path in ('bulk', 'direct'):
+    for path in (('bulk', 'direct') if D % 4 == 0 else ('direct',)):   # the bulk engine moves 16-byte multiples
         assert torch.equal(mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=norm, path=path), got), path
     if kind is None:   # the segment-sum backward against the oracle
         xg = dev(x).requires_grad_()
