@@ -97,7 +97,7 @@ class AcousticObjective(object):
                 sl.weighted = int(i == 4)
                 if i >= 4:
                     sl.result = self._records[i - 4].data_ptr()
-        loss_records = ops.new_result_records(4, pred.device)
+        loss_records = ops.new_output_records(4, pred.device)
         for i in range(4):
             self._slots[i].result = loss_records[i].data_ptr()
         grad = torch.empty((B, T, D), dtype=torch.float32, device=pred.device) if want_grad else None

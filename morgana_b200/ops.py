@@ -316,6 +316,12 @@ def new_result_records(n, device):
     return torch.zeros((n, RESULT_BYTES), dtype=torch.uint8, device=device)
 
 
+def new_output_records(n, device):
+    """``n`` uninitialised records for results that are WRITTEN, not accumulated into (a loss value): the finisher stores
+    every field, so no fill kernel is needed."""
+    return torch.empty((n, RESULT_BYTES), dtype=torch.uint8, device=device)
+
+
 def _view3(t):
     """(B, T, D) view with unit inner stride -> (tensor, stride_b, stride_t)."""
     if t.dim() != 3:
@@ -441,7 +447,7 @@ class _MaskedLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, predictions, targets, seq_len, kind):
         B, T, D = predictions.shape
-        record = new_result_records(1, predictions.device)
+        record = new_output_records(1, predictions.device)
         with _device_of(predictions):
             term = make_term(kind, predictions, targets, result=record[0])
             masked_reduce([term], seq_len, B, T, predictions.device)
@@ -458,7 +464,7 @@ class _MaskedLossFn(torch.autograd.Function):
         B, T, D = predictions.shape
         grad = torch.empty((B, T, D), dtype=torch.float32, device=predictions.device)
         scale = grad_output.detach().to(torch.float32).contiguous()
-        record = new_result_records(1, predictions.device)
+        record = new_output_records(1, predictions.device)
         with _device_of(predictions):
             term = make_term(ctx.kind, predictions, targets, result=record[0], grad=grad, grad_scale=1.0,
                              grad_scale_dev=scale)
