@@ -395,7 +395,54 @@ def segment_cases():
     return out
 
 
+def signature_cases():
+    """Call signatures of every reference callable that `morgana_b200` mirrors, as {dotted name: [[parameter, default], ...]}
+    (default "<required>" when there is none): the drop-in boundary of SURVEY.md section 8b, pinned as data."""
+    import inspect
+    from morgana.viz import synthesis
+    names = {
+        'utils': ['upsample_to_repetitions', 'sequence_mask', 'batched_masked_select', 'get_segment_ends', 'split_to_segments'],
+        'losses': ['mse', 'bce', 'ce'],
+        'data': ['normalise_mvn', 'denormalise_mvn', 'normalise_minmax', 'denormalise_minmax'],
+        'viz.synthesis': ['MLPG'],
+    }
+    classes = {
+        'utils': {'ExponentialMovingAverage': ['__init__', 'update_params']},
+        'data': {'MeanVarianceNormaliser': ['__init__', 'normalise', 'denormalise', 'fetch_params', 'load_params'],
+                 'MinMaxNormaliser': ['__init__', 'normalise', 'denormalise', 'fetch_params', 'load_params'],
+                 'SpeakerDependentMeanVarianceNormaliser': ['__init__', 'normalise', 'denormalise', 'fetch_params', 'load_params'],
+                 'SpeakerDependentMinMaxNormaliser': ['__init__', 'normalise', 'denormalise', 'fetch_params', 'load_params'],
+                 'Normalisers': ['__init__'], 'ToDeviceWrapper': ['__init__', 'to_device']},
+        'metrics': {cls: ['__init__', 'reset_state', 'accumulate', 'result'] for cls in
+                    ['Handler', 'Print', 'History', 'TensorHistory', 'Mean', 'Variance', 'StandardDeviation', 'RMSE', 'MAE',
+                     'Accuracy', 'Error', 'F0Distortion', 'LF0Distortion', 'Distortion', 'MelCepDistortion']},
+    }
+    classes['metrics']['Handler'] += ['add_metrics', 'add_collection', 'results_as_json_dict', 'results_as_str_dict']
+    modules = {'utils': utils, 'losses': losses, 'data': data, 'metrics': metrics, 'viz.synthesis': synthesis}
+
+    def describe(fn):
+        out = []
+        for p in inspect.signature(fn, follow_wrapped=False).parameters.values():
+            kind = {p.VAR_POSITIONAL: '*', p.VAR_KEYWORD: '**'}.get(p.kind, '')
+            default = '<required>' if p.default is p.empty else repr(p.default)
+            out.append([kind + p.name, default])
+        return out
+    table = {}
+    for mod, fns in names.items():
+        for fn in fns:
+            table['%s.%s' % (mod, fn)] = describe(getattr(modules[mod], fn))
+    for mod, cls_map in classes.items():
+        for cls, methods in cls_map.items():
+            for method in methods:
+                table['%s.%s.%s' % (mod, cls, method)] = describe(getattr(getattr(modules[mod], cls), method))
+    return table
+
+
 def main():
+    import json
+    with open(os.path.join(HERE, 'signatures.json'), 'w') as f:
+        json.dump(signature_cases(), f, indent=1, sort_keys=True)
+    print('signatures.json written')
     groups = {
         'segments': segment_cases(),
         'upsample': upsample_cases(),
