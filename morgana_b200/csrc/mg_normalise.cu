@@ -41,31 +41,47 @@ normalise_kernel(const float* __restrict__ x, const float* __restrict__ p0, cons
   int64_t elem = first_elem + tid * VEC;
   int64_t row = elem / D;
   int col = static_cast<int>(elem - row * D);
-  for (int64_t u = tid; u < n_units; u += n_threads) {
-    float v[VEC];
-    if constexpr (VEC == 4) {
-      const float4 t = __ldcs(reinterpret_cast<const float4*>(x + first_elem) + u);
-      v[0] = t.x; v[1] = t.y; v[2] = t.z; v[3] = t.w;
-    } else {
-      v[0] = __ldcs(x + first_elem + u);
-    }
-    int64_t r = row;
-    int c = col;
+  // Two units per iteration, both loads issued before any arithmetic: with one 16-byte load in flight per thread the
+  // kernel held ~65 KB per SM in flight and ran at 0.79 of the copy peak.
+  constexpr int kUnits = 2;
+  for (int64_t u0 = tid; u0 < n_units; u0 += kUnits * n_threads) {
+    float v[kUnits][VEC];
+    bool live[kUnits];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) {
-      const int64_t prow = rows_per_param > 0 ? r / rows_per_param : 0;
-      const float a = __ldg(p0 + prow * D + c), s = __ldg(p1 + prow * D + c);
-      v[k] = apply1<MODE, INVERSE>(v[k], a, s);
-      if (++c == D) { c = 0; ++r; }
+    for (int j = 0; j < kUnits; ++j) {
+      const int64_t u = u0 + j * n_threads;
+      live[j] = u < n_units;
+      if (!live[j]) continue;
+      if constexpr (VEC == 4) {
+        const float4 t = __ldcs(reinterpret_cast<const float4*>(x + first_elem) + u);
+        v[j][0] = t.x; v[j][1] = t.y; v[j][2] = t.z; v[j][3] = t.w;
+      } else {
+        v[j][0] = __ldcs(x + first_elem + u);
+      }
     }
-    if constexpr (VEC == 4) {
-      __stcs(reinterpret_cast<float4*>(out + first_elem) + u, make_float4(v[0], v[1], v[2], v[3]));
-    } else {
-      __stcs(out + first_elem + u, v[0]);
+#pragma unroll
+    for (int j = 0; j < kUnits; ++j) {
+      if (live[j]) {
+        int64_t r = row;
+        int c = col;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          const int64_t prow = rows_per_param > 0 ? r / rows_per_param : 0;
+          const float a = __ldg(p0 + prow * D + c), s = __ldg(p1 + prow * D + c);
+          v[j][k] = apply1<MODE, INVERSE>(v[j][k], a, s);
+          if (++c == D) { c = 0; ++r; }
+        }
+        const int64_t u = u0 + j * n_threads;
+        if constexpr (VEC == 4) {
+          __stcs(reinterpret_cast<float4*>(out + first_elem) + u, make_float4(v[j][0], v[j][1], v[j][2], v[j][3]));
+        } else {
+          __stcs(out + first_elem + u, v[j][0]);
+        }
+      }
+      row += step_rows;      // (row, col) of the next unit of this thread
+      col += step_cols;
+      if (col >= D) { col -= D; ++row; }
     }
-    row += step_rows;
-    col += step_cols;
-    if (col >= D) { col -= D; ++row; }
   }
 }
 
