@@ -208,7 +208,7 @@ def test_interleaved_calls_with_changing_shapes(mg, seed):
     rmse_sum = rmse_count = 0.
     obj_sum = obj_count = 0.
     for step in range(60):
-        op = rng.integers(0, 9)
+        op = rng.integers(0, 14)
         B, T = int(rng.integers(1, 70)), int(rng.integers(1, 130))
         n = rng.integers(1, T + 1, B)
         if op == 0:      # K1 + K2, fused normalisation
@@ -254,7 +254,9 @@ def test_interleaved_calls_with_changing_shapes(mg, seed):
             ops.ema_update(list(zip(s_dev, p_dev)), 1. - 0.99)
             for got, s, p in zip(s_dev, shadow, param):
                 assert np.array_equal(got.cpu().numpy(), O.ema_update(s.copy(), p, 0.99)), step
-        elif op == 5:    # K7, all tile shapes
+        elif op == 5:    # K7, all tile shapes, single-CTA and CTA-pair forms
+            os.environ['MG_GEMM_PAIR'] = str(int(rng.integers(0, 2)))
+            os.environ['MG_GEMM_WIDE'] = str(int(rng.integers(0, 2)))
             M, K, N = int(rng.integers(1, 700)), int(rng.choice([8, 40, 64, 600])), int(rng.choice([1, 3, 32, 187, 300, 512]))
             x = dev(rng.standard_normal((M, K)).astype(np.float32)).to(torch.bfloat16)
             w = dev((rng.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32)).to(torch.bfloat16)
@@ -263,6 +265,7 @@ def test_interleaved_calls_with_changing_shapes(mg, seed):
             got = ops.linear_bf16(x, w, dev(bias), act=act)
             want = O.linear(x.float().cpu().numpy(), w.float().cpu().numpy(), bias, act)
             np.testing.assert_allclose(got.cpu().numpy(), want, rtol=2e-3, atol=2e-3)
+            del os.environ['MG_GEMM_PAIR'], os.environ['MG_GEMM_WIDE']
         elif op == 6:    # K8
             F, pad = int(rng.choice([1, 2, 5])), int(rng.choice([0, 3, 100]))
             means = rng.standard_normal((B, T, 3 * F)).astype(np.float32)
@@ -276,6 +279,65 @@ def test_interleaved_calls_with_changing_shapes(mg, seed):
             assert np.array_equal(packed.cpu().numpy(), O.batched_masked_select(x, n)), step
             padded = mg.data.pad_collate(packed, dev(n), max_len=T)
             assert np.array_equal(padded.cpu().numpy(), x * (np.arange(T)[None, :] < n[:, None])[:, :, None]), step
+        elif op == 8:    # weighted / exp metric, Variance, integer metric
+            lf0_t = (5 + 0.3 * rng.standard_normal((B, T, 1))).astype(np.float32)
+            lf0_p = (lf0_t + 0.05 * rng.standard_normal((B, T, 1))).astype(np.float32)
+            voiced = rng.random((B, T, 1)) < 0.6
+            m = mg.metrics.LF0Distortion()
+            m.reset_state()
+            m.accumulate(dev(lf0_t), dev(lf0_p), dev(voiced), seq_len=dev(n))
+            s_, c_ = O.lf0_acc(lf0_t, lf0_p, voiced, n)
+            assert float(m.count) == c_ and (c_ == 0 or rel(m.sum, s_) <= 2e-6), step
+            var = mg.metrics.Variance()
+            var.accumulate(dev(lf0_t), seq_len=dev(n))
+            s_, q_, c_ = O.variance_acc(lf0_t, n)
+            assert float(var.count) == c_ and rel(var.sum, s_) <= 2e-6 and rel(var.sum_square, q_) <= 2e-6, step
+            err = mg.metrics.Error()
+            bits = rng.random((B, T, 1)) < 0.5
+            err.accumulate(dev(voiced), dev(bits), seq_len=dev(n))
+            s_, c_ = O.error_acc(voiced, bits, n)
+            assert int(err.sum) == int(s_) and float(err.count) == c_, step
+        elif op == 9:    # cross-entropy and bce with their gradients
+            C = int(rng.choice([2, 5, 40]))
+            logits = dev((2 * rng.standard_normal((B, T, C))).astype(np.float32)).requires_grad_()
+            classes = rng.integers(0, C, (B, T))
+            value = mg.losses.ce(logits, dev(classes), dev(n))
+            want, want_grad = O.cross_entropy_loss(logits.detach().cpu().numpy(), classes, n)
+            grad, = torch.autograd.grad(value, logits)
+            assert rel(value.item(), want) <= 2e-6, step
+            np.testing.assert_allclose(grad.cpu().numpy(), want_grad, rtol=3e-6, atol=3e-8)
+            prob = (1. / (1. + np.exp(-rng.standard_normal((B, T, 1))))).astype(np.float32)
+            label = (rng.random((B, T, 1)) < 0.5).astype(np.float32)
+            assert rel(mg.losses.bce(dev(prob), dev(label), dev(n)).item(), O.masked_loss(prob, label, n, 'bce')) <= 2e-6, step
+        elif op == 10:   # expansion: other dtypes (byte path), bf16 output, and the backward
+            P, D = int(rng.integers(1, 30)), int(rng.choice([1, 8, 64, 600]))
+            dur = rng.integers(0, 6, (B, P))
+            xi = rng.integers(-1000, 1000, (B, P, D))
+            assert np.array_equal(mg.utils.upsample_to_repetitions(dev(xi), dev(dur)).cpu().numpy(), O.upsample_to_repetitions(xi, dur)), step
+            xf = rng.random((B, P, D), dtype=np.float32)
+            xg = dev(xf).requires_grad_()
+            out = mg.utils.upsample_to_repetitions(xg, dev(dur))
+            up = rng.standard_normal(tuple(out.shape)).astype(np.float32)
+            out.backward(dev(up))
+            np.testing.assert_allclose(xg.grad.cpu().numpy(), O.upsample_backward(up, dur), rtol=1e-5, atol=1e-5)
+            if D % 8 == 0:
+                got16 = mg.utils.upsample_to_repetitions(dev(xf), dev(dur), out_dtype=torch.bfloat16)
+                want16 = torch.from_numpy(O.upsample_to_repetitions(xf, dur)).to(torch.bfloat16)
+                assert torch.equal(got16.cpu().view(torch.int16), want16.view(torch.int16)), step
+        elif op == 11:   # segment ops
+            S, D = int(rng.integers(1, 9)), int(rng.choice([1, 7, 64]))
+            x = rng.standard_normal((B, T, D)).astype(np.float32)
+            lens = rng.integers(0, max(1, T // S) + 1, (B, S))
+            assert np.array_equal(mg.utils.get_segment_ends(dev(x), dev(lens)[:, :, None]).cpu().numpy(), O.get_segment_ends(x, lens)), step
+            assert np.array_equal(mg.utils.split_to_segments(dev(x), dev(lens)[:, :, None]).cpu().numpy(), O.split_to_segments(x, lens)), step
+        elif op == 12:   # per-utterance (speaker-dependent) parameters, standalone and fused
+            P, D = int(rng.integers(1, 20)), int(rng.choice([4, 187, 600]))
+            x, dur = rng.random((B, P, D), dtype=np.float32), rng.integers(0, 5, (B, P))
+            lo, hi = rng.standard_normal((B, D)).astype(np.float32), (rng.standard_normal((B, D)) + 3).astype(np.float32)
+            normed = mg.data.normalise_minmax(dev(x), dev(lo), dev(hi))
+            assert np.array_equal(normed.cpu().numpy(), O.normalise_minmax(x, lo, hi)), step
+            fused = mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=('minmax', dev(lo), dev(hi)))
+            assert torch.equal(fused, mg.utils.upsample_to_repetitions(normed, dev(dur))), step
         else:            # K3
             D = int(rng.choice([1, 9, 187, 600]))
             x = rng.standard_normal((B, T, D)).astype(np.float32)
