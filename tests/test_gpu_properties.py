@@ -344,3 +344,67 @@ def test_interleaved_calls_with_changing_shapes(mg, seed):
             mean, std = rng.standard_normal(D).astype(np.float32), (rng.random(D) + 0.1).astype(np.float32)
             assert np.array_equal(mg.data.normalise_mvn(dev(x), dev(mean), dev(std)).cpu().numpy(), O.normalise_mvn(x, mean, std)), step
             assert np.array_equal(mg.data.denormalise_mvn(dev(x), dev(mean), dev(std)).cpu().numpy(), O.denormalise_mvn(x, mean, std)), step
+
+
+def test_path_replays_from_a_cuda_graph_on_a_side_stream(mg):
+    """The kernels take the caller's stream, never synchronise and never allocate: the whole path (scan, expansion with a
+    length hint, fused objective with its gradient, a streaming metric, the EMA update) captures into one CUDA graph on a
+    side stream and replays on new inputs with the results of the eager calls."""
+    from morgana_b200 import ops, workloads
+    from morgana_b200.fused import AcousticObjective
+    batches = []
+    for seed in (11, 12, 13):
+        ling = workloads.linguistic_batch(batch_size=12, min_phones=8, max_phones=16, max_dur=9, seed=seed)
+        batches.append((ling, workloads.acoustic_batch(ling['n_frames'], max_len=150, seed=seed)))
+    P = max(b[0]['lab'].shape[1] for b in batches)
+    pad_items = lambda t: torch.nn.functional.pad(t, (0, 0, 0, P - t.shape[1]))   # noqa: E731
+    static = {'lab': torch.empty(12, P, 600, device='cuda'), 'dur': torch.empty(12, P, 1, dtype=torch.int64, device='cuda'),
+              'pred': torch.empty(12, 150, 187, device='cuda'), 'target': torch.empty(12, 150, 187, device='cuda')}
+    mmin, mmax = batches[0][0]['mmin'].cuda(), batches[0][0]['mmax'].cuda()
+    shadow, param = torch.zeros(5000, device='cuda'), torch.ones(5000, device='cuda')
+
+    def load(ling, ac):
+        static['lab'].copy_(pad_items(ling['lab']))
+        static['dur'].copy_(pad_items(ling['dur']))
+        static['pred'].copy_(ac['pred'])
+        static['target'].copy_(ac['target'])
+
+    def run(objective, rmse):
+        frames, n_frames = mg.utils.upsample_to_repetitions(static['lab'], static['dur'], normaliser=('minmax', mmin, mmax),
+                                                            max_len=150, return_lengths=True)
+        total, grad = objective(static['pred'], static['target'], n_frames)
+        rmse.accumulate(static['target'], static['pred'], seq_len=n_frames)
+        ops.ema_update([(shadow, param)], 0.5)
+        return frames, total, grad
+
+    # eager reference on the default stream
+    eager_obj, eager_rmse = AcousticObjective(), mg.metrics.RMSE()
+    eager_rmse.reset_state()
+    eager = []
+    for ling, ac in batches:
+        load(ling, ac)
+        frames, total, grad = run(eager_obj, eager_rmse)
+        eager.append((frames.clone(), total.clone(), grad.clone()))
+    eager_shadow, eager_sum = shadow.clone(), float(eager_rmse.sum)
+    shadow.zero_()
+
+    side = torch.cuda.Stream()
+    obj, rmse = AcousticObjective(), mg.metrics.RMSE()
+    rmse.reset_state()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        load(*batches[0])
+        run(obj, rmse)                       # warm-up on the side stream: workspaces and records exist before capture
+        shadow.zero_()
+        rmse.reset_state()
+        rmse.accumulate(static['target'], static['pred'], seq_len=torch.zeros(12, dtype=torch.int64, device='cuda'))   # bind the record
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=side):
+        g_frames, g_total, g_grad = run(obj, rmse)
+    for (ling, ac), (frames, total, grad) in zip(batches, eager):
+        load(ling, ac)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(g_frames, frames) and g_total.item() == total.item() and torch.equal(g_grad, grad)
+    assert torch.equal(shadow, eager_shadow) and float(rmse.sum) == eager_sum
