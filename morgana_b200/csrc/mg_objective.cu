@@ -39,7 +39,7 @@ constexpr int kMaxSpecial = 4;       // special columns served from the shared-m
 constexpr int kSpecialInfo = 1024;   // ballot positions (32 words x 32 lanes)
 constexpr int kMaxCapture = 8;       // columns copied to the side buffer (specials, their mask columns, root groups)
 constexpr int kLanes = 2;           // column programs per thread: the streamed column + one edge element (head / tail)
-constexpr int64_t kObjTargetElems = 24576;   // elements of one operand per CTA (~96 KB)
+constexpr int64_t kObjTargetElems = 37400;   // elements of one operand per CTA (~146 KB): 200 rows at D = 187 (measured optimum)
 
 struct ObjectiveParams {
   MgFinishSlot slots[MG_MAX_TERMS];
@@ -627,9 +627,11 @@ extern "C" int mg_masked_objective_f32(const float* pred, int64_t p_sb, int64_t 
   // the per-CTA serial phases (special columns, slot sums, ticket) want more co-resident CTAs, not a deeper ring.
   const size_t side_bytes = static_cast<size_t>(kMaxCapture) * rows * 2 * sizeof(float);
   const size_t stage_pair_bytes = static_cast<size_t>(2) * kStageRows * D * sizeof(float);
+  // Default: a 2-stage ring + the side buffer (measured on B200 at D = 187: rows per CTA 131 / 160 / 200 / 262 / 400 ->
+  // 0.153 / 0.152 / 0.148 / 0.154 / 0.168 ms with 2 stages; a third stage at the same rows is slower).
   static int budget_kb = -1;
-  if (budget_kb < 0) { const char* e = getenv("MG_OBJ_SMEM_KB"); budget_kb = e ? atoi(e) : 34; }
-  const size_t budget = static_cast<size_t>(budget_kb) * 1024;
+  if (budget_kb < 0) { const char* e = getenv("MG_OBJ_SMEM_KB"); budget_kb = e ? atoi(e) : 0; }
+  const size_t budget = budget_kb > 0 ? static_cast<size_t>(budget_kb) * 1024 : 2 * stage_pair_bytes + side_bytes + 64;
   int ring = side_bytes < budget ? static_cast<int>((budget - side_bytes) / stage_pair_bytes) : 0;
   if (ring > kMaxStages) ring = kMaxStages;
   static int force_fallback = -1;
@@ -645,7 +647,7 @@ extern "C" int mg_masked_objective_f32(const float* pred, int64_t p_sb, int64_t 
   const size_t smem = ring_bytes + side_bytes;
   MG_REQUIRE(smem <= 200 * 1024, "mg_masked_objective_f32: D=%d needs %zu bytes of shared memory", D, smem);
   dim3 grid(static_cast<unsigned>(n_chunks), static_cast<unsigned>(B));
-  if (smem > 48 * 1024) {
+  if (smem > 32 * 1024) {   // static + dynamic shared memory above 48 KB needs the opt-in (the kernel has ~5 KB static)
     MG_CUDA_OK(cudaFuncSetAttribute(masked_objective_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MG_CUDA_OK(cudaFuncSetAttribute(masked_objective_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MG_CUDA_OK(cudaFuncSetAttribute(masked_objective_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
