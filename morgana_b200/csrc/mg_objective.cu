@@ -39,7 +39,9 @@ constexpr int kMaxSpecial = 4;       // special columns served from the shared-m
 constexpr int kSpecialInfo = 1024;   // ballot positions (32 words x 32 lanes)
 constexpr int kMaxCapture = 8;       // columns copied to the side buffer (specials, their mask columns, root groups)
 constexpr int kLanes = 2;           // column programs per thread: the streamed column + one edge element (head / tail)
-constexpr int64_t kObjTargetElems = 37400;   // elements of one operand per CTA (~146 KB): 200 rows at D = 187 (measured optimum)
+constexpr int64_t kObjTargetElems = 24576;   // elements of one operand per CTA (~96 KB): 131 rows at D = 187.  200-row chunks
+                                             // are 3 % faster in isolation (0.148 vs 0.153 ms) but leave more dirty lines in L2 for
+                                             // the kernel that follows: in the benchmark step K2 then takes 0.149 instead of 0.146 ms
 
 struct ObjectiveParams {
   MgFinishSlot slots[MG_MAX_TERMS];
@@ -628,7 +630,7 @@ extern "C" int mg_masked_objective_f32(const float* pred, int64_t p_sb, int64_t 
   const size_t side_bytes = static_cast<size_t>(kMaxCapture) * rows * 2 * sizeof(float);
   const size_t stage_pair_bytes = static_cast<size_t>(2) * kStageRows * D * sizeof(float);
   // Default: a 2-stage ring + the side buffer (measured on B200 at D = 187: rows per CTA 131 / 160 / 200 / 262 / 400 ->
-  // 0.153 / 0.152 / 0.148 / 0.154 / 0.168 ms with 2 stages; a third stage at the same rows is slower).
+  // 0.153 / 0.152 / 0.148 / 0.154 / 0.168 ms with 2 stages; a third stage at the same rows is slower).  MG_OBJ_ROWS overrides.
   static int budget_kb = -1;
   if (budget_kb < 0) { const char* e = getenv("MG_OBJ_SMEM_KB"); budget_kb = e ? atoi(e) : 0; }
   const size_t budget = budget_kb > 0 ? static_cast<size_t>(budget_kb) * 1024 : 2 * stage_pair_bytes + side_bytes + 64;
