@@ -6,8 +6,9 @@ a forward pass that is one ``mg_linear_bf16`` launch with the bias and the sigmo
 
 Forward tolerance (stated in tests/test_gpu_parity.py): bf16 operands, fp32 accumulation -> <= 2 % of the output range
 against the fp32 layer, 2e-3 against the exact product of the bf16-rounded operands.
-The backward pass is two plain library GEMMs (dgrad, wgrad) through ``torch.matmul`` in bf16 -- cuBLAS, as the north
-star allows for plain GEMMs; the hand-written kernel is the fused forward.
+Backward: the input gradient ``g @ W`` runs through the same tcgen05 kernel (``y = g @ (W^T)^T`` with a transposed bf16
+copy of the weight); the weight gradient ``g^T @ x`` reduces over the frame axis, needs M-major operands and a split
+reduction, and stays a plain library GEMM (``torch.matmul`` in bf16, cuBLAS -- as the north star allows for plain GEMMs).
 """
 import torch
 
@@ -32,7 +33,16 @@ class _LinearFn(torch.autograd.Function):
             g = g * yf * (1. - yf)
         g16 = g.to(torch.bfloat16)
         k = ctx.k
-        grad_x = torch.matmul(g16, weight_bf16[:, :k]).to(ctx.x_dtype) if ctx.needs_input_grad[0] else None
+        grad_x = None
+        if ctx.needs_input_grad[0]:
+            # dgrad on the tensor cores: (M, N) @ (N, K) as the forward kernel sees it, x' = g16 (M, N'), w' = W^T (K, N')
+            n = g16.shape[1]
+            n_pad = (n + 7) // 8 * 8
+            g_op = g16 if n == n_pad else torch.nn.functional.pad(g16, (0, n_pad - n))
+            w_t = torch.zeros((k, n_pad), dtype=torch.bfloat16, device=g16.device)
+            w_t[:, :n] = weight_bf16[:, :k].t()
+            grad_x = ops.linear_bf16(g_op.contiguous(), w_t, None, act=None, out_dtype=torch.float32 if ctx.x_dtype == torch.float32
+                                     else torch.bfloat16)
         grad_w = torch.matmul(g16.t(), x_bf16[:, :k]).to(torch.float32) if ctx.needs_input_grad[1] else None
         grad_b = g.sum(dim=0) if ctx.has_bias and ctx.needs_input_grad[2] else None
         return grad_x, grad_w, grad_b, None, None, None
