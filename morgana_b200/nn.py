@@ -38,9 +38,11 @@ class _LinearFn(torch.autograd.Function):
             # dgrad on the tensor cores: (M, N) @ (N, K) as the forward kernel sees it, x' = g16 (M, N'), w' = W^T (K, N')
             n = g16.shape[1]
             n_pad = (n + 7) // 8 * 8
-            g_op = g16 if n == n_pad else torch.nn.functional.pad(g16, (0, n_pad - n))
-            w_t = torch.zeros((k, n_pad), dtype=torch.bfloat16, device=g16.device)
-            w_t[:, :n] = weight_bf16[:, :k].t()
+            if n == n_pad:                       # one transposing copy; the reduction length needs no padding
+                g_op, w_t = g16, weight_bf16[:, :k].t().contiguous()
+            else:                                # out_features not a multiple of 8 (the 1- / 3- / 187-wide heads)
+                g_op = torch.nn.functional.pad(g16, (0, n_pad - n))
+                w_t = torch.nn.functional.pad(weight_bf16[:, :k].t(), (0, n_pad - n))
             grad_x = ops.linear_bf16(g_op.contiguous(), w_t, None, act=None, out_dtype=torch.float32 if ctx.x_dtype == torch.float32
                                      else torch.bfloat16)
         grad_w = torch.matmul(g16.t(), x_bf16[:, :k]).to(torch.float32) if ctx.needs_input_grad[1] else None
