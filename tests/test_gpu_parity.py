@@ -728,7 +728,7 @@ def test_nn_linear_module_forward_backward(mg):
     for a, b in zip(ours, ref_linears):
         scale = b.weight.grad.abs().max().item()
         assert (a.weight.grad - b.weight.grad).abs().max().item() <= 5e-2 * scale + 1e-4
-    # the input gradient went through the tcgen05 kernel four times (dgrad of every layer)
+    # the input gradient of the 512-wide layer went through the tcgen05 kernel, the narrower ones through the library GEMM
     assert (xo.grad - xr.grad).abs().max().item() <= 5e-2 * xr.grad.abs().max().item() + 1e-6
     # the bf16 shadow follows parameter updates
     before = ours[0].weight_bf16().clone()
