@@ -82,6 +82,21 @@ int mg_upsample_norm_f32_bf16out(const float* x, int64_t x_stride_b, int64_t x_s
                                  const float* p0, const float* p1, int64_t param_stride_b, int norm_mode,
                                  void* out, int B, int P, int D, int64_t T, mg_stream_t stream);
 
+/* Packed (ragged) input -- "next" row 3: the items of the batch arrive as they are on the wire, utterance after utterance
+ * in one flat array, with no phone padding to read or to produce (the padded layout is what FilesDataset.collate_fn builds
+ * on the host, morgana/data.py:184-193).
+ *
+ * item_ends  (B,) int32: inclusive scan of the item counts (mg_dur_scan over the counts viewed as one (1, B) row).
+ * mg_dur_scan_packed: dur (sum_b n_items_b,) int64 / int32; ends (sum_b n_items_b,) int32 out, the scan restarting at every
+ *            utterance; n_frames / summary as for mg_dur_scan.
+ * mg_upsample_packed_norm_f32: x (sum_b n_items_b, D) fp32 with row stride x_stride_p; max_items >= every item count;
+ *            everything else as for mg_upsample_norm_f32 (same kernels, same results as padding first). */
+int mg_dur_scan_packed(const void* dur, int dur_is_i32, const int32_t* item_ends, int B, int32_t* ends, int64_t* n_frames,
+                       int64_t* summary, mg_stream_t stream);
+int mg_upsample_packed_norm_f32(const float* x, int64_t x_stride_p, const int32_t* item_ends, const int32_t* ends,
+                                const float* p0, const float* p1, int64_t param_stride_b, int norm_mode, float* out,
+                                int B, int max_items, int D, int64_t T, mg_stream_t stream);
+
 /* Dtype-agnostic expansion (the reference preserves any dtype): rows of row_bytes bytes are copied.
  * Strides in BYTES.  out is (B, T, row_bytes) contiguous. */
 int mg_upsample_bytes(const void* x, int64_t x_stride_b_bytes, int64_t x_stride_p_bytes, const int32_t* ends,

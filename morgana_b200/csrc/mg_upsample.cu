@@ -80,8 +80,7 @@ __device__ __forceinline__ Vec mg_norm_vec(Vec v, const float*, const float*, in
 
 // Stage this utterance's inclusive scan row in shared memory (or fall back to global for very long rows) and return
 // the pointer to search.  Must be called by the whole CTA.
-__device__ __forceinline__ const int32_t* mg_stage_ends(const int32_t* ends_row, int P, int32_t* smem_ends) {
-  const bool fits = P <= kMaxEndsSmem;
+__device__ __forceinline__ const int32_t* mg_stage_ends(const int32_t* ends_row, int P, int32_t* smem_ends, bool fits) {
   if (fits)
     for (int p = threadIdx.x; p < P; p += blockDim.x) smem_ends[p] = __ldg(ends_row + p);
   __syncthreads();   // unconditional: callers also rely on it to order their own shared-memory writes
@@ -109,7 +108,7 @@ __global__ void __launch_bounds__(kUpThreads)
 upsample_bulk_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t x_sp, const int32_t* __restrict__ ends,
                      const float* __restrict__ p0, const float* __restrict__ p1, int64_t p_sb,
                      unsigned char* __restrict__ out, int P, int nvec /* input row bytes / 16 */, int64_t T,
-                     int rows_per_cta, int zero_rows) {
+                     int rows_per_cta, int zero_rows, const int32_t* __restrict__ item_ends) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t row_bytes = static_cast<uint32_t>(nvec) * (OUT_BF16 ? 8u : 16u);   // OUTPUT row
   unsigned char* slots = smem;
@@ -120,7 +119,11 @@ upsample_bulk_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t 
   const int b = blockIdx.y;
   const int64_t t0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
   const int64_t t1 = min(t0 + rows_per_cta, T);
-  const int32_t* ends_row = ends + static_cast<int64_t>(b) * P;
+  const bool ends_fit = P <= kMaxEndsSmem;   // the host sized the shared-memory scan row from this (largest) item count
+  // padded items: row b of (B, P); packed items: a flat array, item_ends = inclusive scan of the item counts
+  const int64_t item_base = item_ends ? (b > 0 ? static_cast<int64_t>(__ldg(item_ends + b - 1)) : 0) : static_cast<int64_t>(b) * P;
+  if (item_ends) { P = static_cast<int>(static_cast<int64_t>(__ldg(item_ends + b)) - item_base); x_sb = 0; x += item_base * x_sp; }
+  const int32_t* ends_row = ends + item_base;
   const int64_t n_b = P > 0 ? static_cast<int64_t>(__ldg(ends_row + P - 1)) : 0;
   const int64_t valid_end = min(t1, n_b);
   unsigned char* out_b = out + static_cast<int64_t>(b) * T * row_bytes;
@@ -136,7 +139,7 @@ upsample_bulk_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t 
     mg_fence_proxy_async_smem();
   }
   const int32_t* e = ends_row;
-  if (t0 < valid_end) e = mg_stage_ends(ends_row, P, smem_ends);   // contains a __syncthreads
+  if (t0 < valid_end) e = mg_stage_ends(ends_row, P, smem_ends, ends_fit);   // contains a __syncthreads
   else if (has_padding) __syncthreads();
   if (has_padding && lane == 0) {
     int piece = 0;
@@ -222,7 +225,7 @@ __global__ void __launch_bounds__(kUpThreads)
 upsample_direct_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t x_sp, const int32_t* __restrict__ ends,
                        const float* __restrict__ p0, const float* __restrict__ p1, int64_t p_sb,
                        unsigned char* __restrict__ out, int P, int nvec /* row_bytes / sizeof(Vec) */, int64_t T,
-                       int rows_per_cta) {
+                       int rows_per_cta, const int32_t* __restrict__ item_ends) {
   extern __shared__ __align__(128) unsigned char smem[];
   int32_t* smem_ends = reinterpret_cast<int32_t*>(smem);
 
@@ -230,7 +233,10 @@ upsample_direct_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_
   const int b = blockIdx.y;
   const int64_t t0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
   const int64_t t1 = min(t0 + rows_per_cta, T);
-  const int32_t* ends_row = ends + static_cast<int64_t>(b) * P;
+  const bool ends_fit = P <= kMaxEndsSmem;
+  const int64_t item_base = item_ends ? (b > 0 ? static_cast<int64_t>(__ldg(item_ends + b - 1)) : 0) : static_cast<int64_t>(b) * P;
+  if (item_ends) { P = static_cast<int>(static_cast<int64_t>(__ldg(item_ends + b)) - item_base); x_sb = 0; x += item_base * x_sp; }
+  const int32_t* ends_row = ends + item_base;
   const int64_t n_b = P > 0 ? static_cast<int64_t>(__ldg(ends_row + P - 1)) : 0;
   const int64_t valid_end = min(t1, n_b);
   Vec* out_b = reinterpret_cast<Vec*>(out) + static_cast<int64_t>(b) * T * nvec;
@@ -245,7 +251,7 @@ upsample_direct_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_
   }
   if (t0 >= valid_end) return;   // CTA-uniform
 
-  const int32_t* e = mg_stage_ends(ends_row, P, smem_ends);
+  const int32_t* e = mg_stage_ends(ends_row, P, smem_ends, ends_fit);
   const float* q0 = p0 + static_cast<int64_t>(b) * p_sb;
   const float* q1 = p1 + static_cast<int64_t>(b) * p_sb;
   const int first_item = mg_item_of_frame(e, P, t0);
@@ -356,7 +362,8 @@ int mg_rows_per_cta(int64_t T, int B, int64_t row_bytes) {
 
 template <int MODE, bool OUT_BF16 = false>
 int launch_bulk(const unsigned char* x, int64_t x_sb, int64_t x_sp, const int32_t* ends, const float* p0, const float* p1,
-                int64_t p_sb, unsigned char* out, int B, int P, int64_t in_row_bytes, int64_t T, cudaStream_t stream) {
+                int64_t p_sb, unsigned char* out, int B, int P, int64_t in_row_bytes, int64_t T, cudaStream_t stream,
+                const int32_t* item_ends = nullptr) {
   const int64_t row_bytes = OUT_BF16 ? in_row_bytes / 2 : in_row_bytes;   // output row
   const int rows = mg_rows_per_cta(T, B, row_bytes);
   int zero_rows = static_cast<int>((16 * 1024) / row_bytes);
@@ -370,7 +377,7 @@ int launch_bulk(const unsigned char* x, int64_t x_sb, int64_t x_sp, const int32_
   }
   dim3 grid(static_cast<unsigned>((T + rows - 1) / rows), static_cast<unsigned>(B));
   kernel<<<grid, kUpThreads, smem, stream>>>(x, x_sb, x_sp, ends, p0, p1, p_sb, out, P, static_cast<int>(in_row_bytes / 16),
-                                              T, rows, zero_rows);
+                                              T, rows, zero_rows, item_ends);
   MG_LAUNCH_OK();
   return MG_OK;
 }
@@ -378,12 +385,12 @@ int launch_bulk(const unsigned char* x, int64_t x_sb, int64_t x_sp, const int32_
 template <typename Vec, int MODE>
 int launch_direct(const unsigned char* x, int64_t x_sb, int64_t x_sp, const int32_t* ends, const float* p0,
                   const float* p1, int64_t p_sb, unsigned char* out, int B, int P, int64_t row_bytes, int64_t T,
-                  cudaStream_t stream) {
+                  cudaStream_t stream, const int32_t* item_ends = nullptr) {
   const int rows = mg_rows_per_cta(T, B, row_bytes);
   const size_t smem = (P <= kMaxEndsSmem) ? static_cast<size_t>(P) * 4 : 0;
   dim3 grid(static_cast<unsigned>((T + rows - 1) / rows), static_cast<unsigned>(B));
   upsample_direct_kernel<Vec, MODE><<<grid, kUpThreads, smem, stream>>>(
-      x, x_sb, x_sp, ends, p0, p1, p_sb, out, P, static_cast<int>(row_bytes / sizeof(Vec)), T, rows);
+      x, x_sb, x_sp, ends, p0, p1, p_sb, out, P, static_cast<int>(row_bytes / sizeof(Vec)), T, rows, item_ends);
   MG_LAUNCH_OK();
   return MG_OK;
 }
@@ -435,6 +442,38 @@ extern "C" int mg_upsample_norm_f32(const float* x, int64_t x_stride_b, int64_t 
     case MG_NORM_NONE: return launch_direct<float, MG_NORM_NONE>(xb, x_sb, x_sp, ends, p0, p1, param_stride_b, ob, B, P, row_bytes, T, stream);
     case MG_NORM_MVN: return launch_direct<float, MG_NORM_MVN>(xb, x_sb, x_sp, ends, p0, p1, param_stride_b, ob, B, P, row_bytes, T, stream);
     default: return launch_direct<float, MG_NORM_MINMAX>(xb, x_sb, x_sp, ends, p0, p1, param_stride_b, ob, B, P, row_bytes, T, stream);
+  }
+}
+
+extern "C" int mg_upsample_packed_norm_f32(const float* x, int64_t x_stride_p, const int32_t* item_ends, const int32_t* ends,
+                                           const float* p0, const float* p1, int64_t param_stride_b, int norm_mode,
+                                           float* out, int B, int max_items, int D, int64_t T, mg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MG_REQUIRE(B >= 0 && max_items >= 0 && D >= 0 && T >= 0, "mg_upsample_packed_norm_f32: negative shape");
+  MG_REQUIRE(norm_mode >= MG_NORM_NONE && norm_mode <= MG_NORM_MINMAX, "mg_upsample_packed_norm_f32: bad norm_mode %d", norm_mode);
+  MG_REQUIRE(B <= 65535, "mg_upsample_packed_norm_f32: B=%d exceeds 65535 utterances per call", B);
+  if (B == 0 || T == 0 || D == 0) return MG_OK;
+  MG_REQUIRE(out != nullptr && item_ends != nullptr && (max_items == 0 || (x != nullptr && ends != nullptr)),
+             "mg_upsample_packed_norm_f32: NULL buffer");
+  MG_REQUIRE(norm_mode == MG_NORM_NONE || (p0 != nullptr && p1 != nullptr), "mg_upsample_packed_norm_f32: NULL parameters");
+  if (norm_mode == MG_NORM_NONE) { p0 = p1 = nullptr; param_stride_b = 0; }
+  const auto* xb = reinterpret_cast<const unsigned char*>(x);
+  auto* ob = reinterpret_cast<unsigned char*>(out);
+  const int64_t row_bytes = static_cast<int64_t>(D) * 4, x_sp = x_stride_p * 4;
+  const bool params_vec_ok = norm_mode == MG_NORM_NONE ||
+                             (mg_aligned(p0, 16) && mg_aligned(p1, 16) && (param_stride_b % 4) == 0);
+  // `max_items` bounds every utterance's item count (it sizes the shared-memory copy of the scan row)
+  if (bulk_eligible(x, 0, x_sp, out, row_bytes, max_items) && params_vec_ok) {
+    switch (norm_mode) {
+      case MG_NORM_NONE: return launch_bulk<MG_NORM_NONE>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
+      case MG_NORM_MVN: return launch_bulk<MG_NORM_MVN>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
+      default: return launch_bulk<MG_NORM_MINMAX>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
+    }
+  }
+  switch (norm_mode) {
+    case MG_NORM_NONE: return launch_direct<float, MG_NORM_NONE>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
+    case MG_NORM_MVN: return launch_direct<float, MG_NORM_MVN>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
+    default: return launch_direct<float, MG_NORM_MINMAX>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
   }
 }
 

@@ -183,6 +183,57 @@ def upsample(x, repeats, norm=None, max_len=None, path='auto', return_lengths=Fa
     return (out, n_frames) if return_lengths else out
 
 
+def upsample_packed(packed, packed_repeats, n_items, norm=None, max_len=None, max_items=None, return_lengths=False):
+    """K1 + K2 on the packed (ragged) wire format: ``packed`` (sum(n_items), D) float32 items and ``packed_repeats``
+    (sum(n_items),) durations, utterance after utterance; ``n_items`` (B,) item counts.  Equal to padding both to
+    (B, max(n_items), ...) and calling :func:`upsample`, without reading or producing the padding.
+
+    ``max_len`` / ``max_items``: the longest utterance in frames / items when the host knows them (no device->host read).
+    """
+    _require_cuda(packed, 'packed')
+    _require_cuda(packed_repeats, 'packed_repeats')
+    _require_cuda(n_items, 'n_items')
+    if packed.dim() != 2 or packed.dtype != torch.float32:
+        raise TypeError('packed must be a (total_items, feat_dim) float32 tensor')
+    if packed_repeats.dtype.is_floating_point or packed_repeats.dtype == torch.bool:
+        raise TypeError('repeats must be an integer tensor, got {}'.format(packed_repeats.dtype))
+    packed_repeats = packed_repeats.reshape(-1)
+    if packed_repeats.dtype not in (torch.int64, torch.int32):
+        packed_repeats = packed_repeats.to(torch.int64)
+    packed_repeats = packed_repeats.contiguous()
+    if packed_repeats.shape[0] != packed.shape[0]:
+        raise ValueError('{} durations for {} items'.format(packed_repeats.shape[0], packed.shape[0]))
+    if packed.shape[1] > 1 and packed.stride(1) != 1:
+        packed = packed.contiguous()
+    B, D, dev = n_items.shape[0], packed.shape[1], packed.device
+    item_ends, _, item_summary = dur_scan(n_items.reshape(1, B))
+    item_ends = item_ends.reshape(B)
+    ends = torch.empty((packed.shape[0],), dtype=torch.int32, device=dev)
+    n_frames = torch.empty((B,), dtype=torch.int64, device=dev)
+    summary = torch.empty((4,), dtype=torch.int64, device=dev)
+    with _device_of(packed):
+        check(lib.mg_dur_scan_packed(_ptr(packed_repeats), int(packed_repeats.dtype == torch.int32), _ptr(item_ends), B,
+                                     _ptr(ends), _ptr(n_frames), _ptr(summary), _stream()), 'mg_dur_scan_packed')
+    if max_len is None or max_items is None:
+        max_frames, n_negative, _, n_overflow = summary.tolist()        # the one device->host read, as in upsample()
+        largest, bad_counts, total_items, _ = item_summary.tolist()
+        if n_negative or bad_counts:
+            raise ValueError('repeats may not contain negative values.')
+        if n_overflow:
+            raise OverflowError('an utterance expands to more than 2**31 - 1 frames')
+        if total_items != packed.shape[0]:
+            raise ValueError('n_items sums to {} but {} items were given'.format(total_items, packed.shape[0]))
+        max_len = int(max_frames) if max_len is None else int(max_len)
+        max_items = int(largest) if max_items is None else int(max_items)
+    mode, p0, p1, p_sb = _norm_args(norm, D, B, dev)
+    out = torch.empty((B, int(max_len), D), dtype=torch.float32, device=dev)
+    with _device_of(packed):
+        check(lib.mg_upsample_packed_norm_f32(_ptr(packed), packed.stride(0), _ptr(item_ends), _ptr(ends), _ptr(p0), _ptr(p1),
+                                              p_sb, mode, _ptr(out), B, int(max_items), D, int(max_len), _stream()),
+              'mg_upsample_packed_norm_f32')
+    return (out, n_frames) if return_lengths else out
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # K0: on-device collate (packed rows -> zero-padded batch)
 # ----------------------------------------------------------------------------------------------------------------------

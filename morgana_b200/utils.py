@@ -76,6 +76,20 @@ class ExponentialMovingAverage(object):
         ops.ema_update(pairs, 1.0 - self.decay, plan=self._plan)
 
 
+def upsample_packed_to_repetitions(packed_feature, packed_repeats, n_items, normaliser=None, deltas=False, max_len=None,
+                                  max_items=None, return_lengths=False):
+    r"""``upsample_to_repetitions`` on the packed wire format (additive; "next" row 3 of the scope table): the items of the
+    batch as one ``(sum(n_items), feat_dim)`` float32 tensor, utterance after utterance, their durations as
+    ``(sum(n_items),)`` integers and the per-utterance item counts ``n_items (batch_size,)``.  Returns the same
+    ``(batch_size, max_frames, feat_dim)`` tensor as padding the items on the host first (``collate_fn``,
+    morgana/data.py:184-193) and calling :func:`upsample_to_repetitions` -- without the padding ever existing."""
+    norm = None
+    if normaliser is not None:
+        norm = normaliser if isinstance(normaliser, tuple) else normaliser.fused_params(deltas=deltas)
+    return ops.upsample_packed(packed_feature, packed_repeats, n_items, norm=norm, max_len=max_len, max_items=max_items,
+                               return_lengths=return_lengths)
+
+
 def batched_masked_select(sequence_feature, seq_len):
     r"""Feature vectors of all batch items that lie inside their sequence, as one ``(sum(seq_len), feat_dim)`` tensor
     (morgana/utils.py:147-166).  One scan + one row-copy kernel instead of mask / nonzero / advanced indexing."""

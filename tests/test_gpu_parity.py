@@ -362,6 +362,38 @@ def test_reductions_reuse_their_workspace_across_batch_sizes(mg):
     assert all(np.isfinite(results)) and min(results) > 0.
 
 
+@pytest.mark.parametrize('D,max_items', [(600, 40), (187, 25), (4, 9000), (8, 1)])
+@pytest.mark.parametrize('kind', [None, 'minmax'])
+def test_packed_items_equal_padded_items(mg, D, max_items, kind):
+    """"Next" row 3: K1 / K2 on the packed wire format (items utterance after utterance, no padding) give the tensor the
+    padded path gives, bit for bit, with and without the host-side hints; per-utterance parameters included."""
+    rng = np.random.default_rng(D + max_items)
+    B = 7
+    n_items = rng.integers(0, max_items + 1, B)
+    n_items[2] = 0                                            # an utterance without items
+    n_items[4] = max_items
+    P = int(n_items.max())
+    x = rng.random((B, P, D), dtype=np.float32)
+    dur = rng.integers(0, 5, (B, P))
+    valid = np.arange(P)[None, :] < n_items[:, None]
+    dur[~valid] = 0
+    x[~valid] = 0
+    lo = rng.standard_normal((B, D)).astype(np.float32)
+    hi = (lo + np.abs(rng.standard_normal((B, D))) + 0.1).astype(np.float32)
+    norm = None if kind is None else (kind, dev(lo), dev(hi))
+    padded, n_frames = mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=norm, return_lengths=True)
+    packed_x, packed_dur = dev(x[valid]), dev(dur[valid])
+    got, got_frames = mg.utils.upsample_packed_to_repetitions(packed_x, packed_dur, dev(n_items), normaliser=norm, return_lengths=True)
+    assert torch.equal(got, padded) and torch.equal(got_frames, n_frames)
+    hinted = mg.utils.upsample_packed_to_repetitions(packed_x, packed_dur.to(torch.int32), dev(n_items), normaliser=norm,
+                                                     max_len=padded.shape[1], max_items=P)
+    assert torch.equal(hinted, padded)
+    want = O.upsample_to_repetitions(x, dur) if kind is None else O.normalise_upsample(x, dur, kind, lo, hi)
+    assert np.array_equal(got.cpu().numpy(), want)
+    with pytest.raises(ValueError):
+        mg.utils.upsample_packed_to_repetitions(packed_x, packed_dur, dev(n_items + 1))      # counts do not match the items
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # a8 - a12 metrics
 # ----------------------------------------------------------------------------------------------------------------------
