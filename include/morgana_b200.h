@@ -90,10 +90,11 @@ int mg_upsample_norm_f32_bf16out(const float* x, int64_t x_stride_b, int64_t x_s
  * mg_dur_scan_packed: dur (sum_b n_items_b,) int64 / int32; ends (sum_b n_items_b,) int32 out, the scan restarting at every
  *            utterance; n_frames / summary as for mg_dur_scan.
  * mg_upsample_packed_norm_f32: x (sum_b n_items_b, D) fp32 with row stride x_stride_p; max_items >= every item count;
- *            everything else as for mg_upsample_norm_f32 (same kernels, same results as padding first). */
-int mg_dur_scan_packed(const void* dur, int dur_is_i32, const int32_t* item_ends, int B, int32_t* ends, int64_t* n_frames,
-                       int64_t* summary, mg_stream_t stream);
-int mg_upsample_packed_norm_f32(const float* x, int64_t x_stride_p, const int32_t* item_ends, const int32_t* ends,
+ *            everything else as for mg_upsample_norm_f32 (same kernels, same results as padding first).
+ * total_items = rows of dur / x / ends: item counts that overrun it are clamped on the device (never read past the arrays). */
+int mg_dur_scan_packed(const void* dur, int dur_is_i32, const int32_t* item_ends, int B, int64_t total_items, int32_t* ends,
+                       int64_t* n_frames, int64_t* summary, mg_stream_t stream);
+int mg_upsample_packed_norm_f32(const float* x, int64_t x_stride_p, const int32_t* item_ends, int64_t total_items, const int32_t* ends,
                                 const float* p0, const float* p1, int64_t param_stride_b, int norm_mode, float* out,
                                 int B, int max_items, int D, int64_t T, mg_stream_t stream);
 

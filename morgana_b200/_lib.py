@@ -65,8 +65,8 @@ PROTOTYPES = {
     'mg_dur_scan': (c_int, [c_void_p, c_int, c_i64, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     'mg_upsample_norm_f32': (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p,
                                      c_int, c_int, c_int, c_i64, c_int, c_void_p]),
-    'mg_dur_scan_packed': (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    'mg_upsample_packed_norm_f32': (c_int, [c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p,
+    'mg_dur_scan_packed': (c_int, [c_void_p, c_int, c_void_p, c_int, c_i64, c_void_p, c_void_p, c_void_p, c_void_p]),
+    'mg_upsample_packed_norm_f32': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p,
                                             c_int, c_int, c_int, c_i64, c_void_p]),
     'mg_upsample_norm_f32_bf16out': (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p,
                                              c_int, c_int, c_int, c_i64, c_void_p]),

@@ -14,14 +14,18 @@ template <typename DurT>
 __global__ void __launch_bounds__(kScanWarpsPerCta * 32)
 dur_scan_kernel(const DurT* __restrict__ dur, int64_t dur_stride_b, int B, int P, int32_t* __restrict__ ends,
                 int64_t* __restrict__ n_frames, unsigned long long* __restrict__ summary,
-                const int32_t* __restrict__ item_ends) {
+                const int32_t* __restrict__ item_ends, int64_t total_items) {
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * kScanWarpsPerCta + (threadIdx.x >> 5);
   if (b >= B) return;
   // Padded layout: utterance b's items are row b of a (B, P) array.  Packed (ragged) layout: its items follow those of
   // utterance b - 1 in one flat array; item_ends is the inclusive scan of the item counts.
-  const int64_t base = item_ends ? (b > 0 ? static_cast<int64_t>(__ldg(item_ends + b - 1)) : 0) : static_cast<int64_t>(b) * P;
-  if (item_ends) P = static_cast<int>(static_cast<int64_t>(__ldg(item_ends + b)) - base);
+  int64_t base = static_cast<int64_t>(b) * P;
+  if (item_ends) {   // counts that overrun the arrays are clamped (the host checks the total when it reads the summary back)
+    base = min(max(b > 0 ? static_cast<int64_t>(__ldg(item_ends + b - 1)) : 0, static_cast<int64_t>(0)), total_items);
+    const int64_t stop = min(max(static_cast<int64_t>(__ldg(item_ends + b)), base), total_items);
+    P = static_cast<int>(stop - base);
+  }
   const DurT* row = item_ends ? dur + base : dur + static_cast<int64_t>(b) * dur_stride_b;
   int32_t* ends_row = ends + base;
 
@@ -71,31 +75,32 @@ extern "C" int mg_dur_scan(const void* dur, int dur_is_i32, int64_t dur_stride_b
   auto* summary_u = reinterpret_cast<unsigned long long*>(summary);
   if (dur_is_i32) {
     dur_scan_kernel<int32_t><<<grid, kScanWarpsPerCta * 32, 0, stream>>>(static_cast<const int32_t*>(dur), dur_stride_b,
-                                                                        B, P, ends, n_frames, summary_u, nullptr);
+                                                                        B, P, ends, n_frames, summary_u, nullptr, 0);
   } else {
     dur_scan_kernel<long long><<<grid, kScanWarpsPerCta * 32, 0, stream>>>(static_cast<const long long*>(dur),
-                                                                          dur_stride_b, B, P, ends, n_frames, summary_u, nullptr);
+                                                                          dur_stride_b, B, P, ends, n_frames, summary_u, nullptr, 0);
   }
   MG_LAUNCH_OK();
   return MG_OK;
 }
 
-extern "C" int mg_dur_scan_packed(const void* dur, int dur_is_i32, const int32_t* item_ends, int B, int32_t* ends,
-                                  int64_t* n_frames, int64_t* summary, mg_stream_t stream_) {
+extern "C" int mg_dur_scan_packed(const void* dur, int dur_is_i32, const int32_t* item_ends, int B, int64_t total_items,
+                                  int32_t* ends, int64_t* n_frames, int64_t* summary, mg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  MG_REQUIRE(B >= 0, "mg_dur_scan_packed: negative batch size");
+  MG_REQUIRE(B >= 0 && total_items >= 0, "mg_dur_scan_packed: negative size");
   MG_REQUIRE(summary != nullptr, "mg_dur_scan_packed: summary is NULL");
   MG_CUDA_OK(cudaMemsetAsync(summary, 0, 4 * sizeof(int64_t), stream));
   if (B == 0) return MG_OK;
-  MG_REQUIRE(n_frames != nullptr && item_ends != nullptr && dur != nullptr && ends != nullptr, "mg_dur_scan_packed: NULL buffer");
+  MG_REQUIRE(n_frames != nullptr && item_ends != nullptr && (total_items == 0 || (dur != nullptr && ends != nullptr)),
+             "mg_dur_scan_packed: NULL buffer");
   const int grid = (B + kScanWarpsPerCta - 1) / kScanWarpsPerCta;
   auto* summary_u = reinterpret_cast<unsigned long long*>(summary);
   if (dur_is_i32) {
     dur_scan_kernel<int32_t><<<grid, kScanWarpsPerCta * 32, 0, stream>>>(static_cast<const int32_t*>(dur), 0, B, 0, ends,
-                                                                        n_frames, summary_u, item_ends);
+                                                                        n_frames, summary_u, item_ends, total_items);
   } else {
     dur_scan_kernel<long long><<<grid, kScanWarpsPerCta * 32, 0, stream>>>(static_cast<const long long*>(dur), 0, B, 0, ends,
-                                                                          n_frames, summary_u, item_ends);
+                                                                          n_frames, summary_u, item_ends, total_items);
   }
   MG_LAUNCH_OK();
   return MG_OK;

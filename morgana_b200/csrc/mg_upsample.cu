@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kUpThreads)
 upsample_bulk_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t x_sp, const int32_t* __restrict__ ends,
                      const float* __restrict__ p0, const float* __restrict__ p1, int64_t p_sb,
                      unsigned char* __restrict__ out, int P, int nvec /* input row bytes / 16 */, int64_t T,
-                     int rows_per_cta, int zero_rows, const int32_t* __restrict__ item_ends) {
+                     int rows_per_cta, int zero_rows, const int32_t* __restrict__ item_ends, int64_t total_items) {
   extern __shared__ __align__(128) unsigned char smem[];
   const uint32_t row_bytes = static_cast<uint32_t>(nvec) * (OUT_BF16 ? 8u : 16u);   // OUTPUT row
   unsigned char* slots = smem;
@@ -121,8 +121,14 @@ upsample_bulk_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t 
   const int64_t t1 = min(t0 + rows_per_cta, T);
   const bool ends_fit = P <= kMaxEndsSmem;   // the host sized the shared-memory scan row from this (largest) item count
   // padded items: row b of (B, P); packed items: a flat array, item_ends = inclusive scan of the item counts
-  const int64_t item_base = item_ends ? (b > 0 ? static_cast<int64_t>(__ldg(item_ends + b - 1)) : 0) : static_cast<int64_t>(b) * P;
-  if (item_ends) { P = static_cast<int>(static_cast<int64_t>(__ldg(item_ends + b)) - item_base); x_sb = 0; x += item_base * x_sp; }
+  int64_t item_base = static_cast<int64_t>(b) * P;
+  if (item_ends) {   // clamped to the arrays, and to the item count the host sized shared memory for
+    item_base = min(max(b > 0 ? static_cast<int64_t>(__ldg(item_ends + b - 1)) : 0, static_cast<int64_t>(0)), total_items);
+    const int64_t stop = min(max(static_cast<int64_t>(__ldg(item_ends + b)), item_base), total_items);
+    P = static_cast<int>(min(stop - item_base, static_cast<int64_t>(P)));
+    x_sb = 0;
+    x += item_base * x_sp;
+  }
   const int32_t* ends_row = ends + item_base;
   const int64_t n_b = P > 0 ? static_cast<int64_t>(__ldg(ends_row + P - 1)) : 0;
   const int64_t valid_end = min(t1, n_b);
@@ -225,7 +231,7 @@ __global__ void __launch_bounds__(kUpThreads)
 upsample_direct_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t x_sp, const int32_t* __restrict__ ends,
                        const float* __restrict__ p0, const float* __restrict__ p1, int64_t p_sb,
                        unsigned char* __restrict__ out, int P, int nvec /* row_bytes / sizeof(Vec) */, int64_t T,
-                       int rows_per_cta, const int32_t* __restrict__ item_ends) {
+                       int rows_per_cta, const int32_t* __restrict__ item_ends, int64_t total_items) {
   extern __shared__ __align__(128) unsigned char smem[];
   int32_t* smem_ends = reinterpret_cast<int32_t*>(smem);
 
@@ -234,8 +240,14 @@ upsample_direct_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_
   const int64_t t0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
   const int64_t t1 = min(t0 + rows_per_cta, T);
   const bool ends_fit = P <= kMaxEndsSmem;
-  const int64_t item_base = item_ends ? (b > 0 ? static_cast<int64_t>(__ldg(item_ends + b - 1)) : 0) : static_cast<int64_t>(b) * P;
-  if (item_ends) { P = static_cast<int>(static_cast<int64_t>(__ldg(item_ends + b)) - item_base); x_sb = 0; x += item_base * x_sp; }
+  int64_t item_base = static_cast<int64_t>(b) * P;
+  if (item_ends) {   // clamped to the arrays, and to the item count the host sized shared memory for
+    item_base = min(max(b > 0 ? static_cast<int64_t>(__ldg(item_ends + b - 1)) : 0, static_cast<int64_t>(0)), total_items);
+    const int64_t stop = min(max(static_cast<int64_t>(__ldg(item_ends + b)), item_base), total_items);
+    P = static_cast<int>(min(stop - item_base, static_cast<int64_t>(P)));
+    x_sb = 0;
+    x += item_base * x_sp;
+  }
   const int32_t* ends_row = ends + item_base;
   const int64_t n_b = P > 0 ? static_cast<int64_t>(__ldg(ends_row + P - 1)) : 0;
   const int64_t valid_end = min(t1, n_b);
@@ -363,7 +375,7 @@ int mg_rows_per_cta(int64_t T, int B, int64_t row_bytes) {
 template <int MODE, bool OUT_BF16 = false>
 int launch_bulk(const unsigned char* x, int64_t x_sb, int64_t x_sp, const int32_t* ends, const float* p0, const float* p1,
                 int64_t p_sb, unsigned char* out, int B, int P, int64_t in_row_bytes, int64_t T, cudaStream_t stream,
-                const int32_t* item_ends = nullptr) {
+                const int32_t* item_ends = nullptr, int64_t total_items = 0) {
   const int64_t row_bytes = OUT_BF16 ? in_row_bytes / 2 : in_row_bytes;   // output row
   const int rows = mg_rows_per_cta(T, B, row_bytes);
   int zero_rows = static_cast<int>((16 * 1024) / row_bytes);
@@ -377,7 +389,7 @@ int launch_bulk(const unsigned char* x, int64_t x_sb, int64_t x_sp, const int32_
   }
   dim3 grid(static_cast<unsigned>((T + rows - 1) / rows), static_cast<unsigned>(B));
   kernel<<<grid, kUpThreads, smem, stream>>>(x, x_sb, x_sp, ends, p0, p1, p_sb, out, P, static_cast<int>(in_row_bytes / 16),
-                                              T, rows, zero_rows, item_ends);
+                                              T, rows, zero_rows, item_ends, total_items);
   MG_LAUNCH_OK();
   return MG_OK;
 }
@@ -385,12 +397,12 @@ int launch_bulk(const unsigned char* x, int64_t x_sb, int64_t x_sp, const int32_
 template <typename Vec, int MODE>
 int launch_direct(const unsigned char* x, int64_t x_sb, int64_t x_sp, const int32_t* ends, const float* p0,
                   const float* p1, int64_t p_sb, unsigned char* out, int B, int P, int64_t row_bytes, int64_t T,
-                  cudaStream_t stream, const int32_t* item_ends = nullptr) {
+                  cudaStream_t stream, const int32_t* item_ends = nullptr, int64_t total_items = 0) {
   const int rows = mg_rows_per_cta(T, B, row_bytes);
   const size_t smem = (P <= kMaxEndsSmem) ? static_cast<size_t>(P) * 4 : 0;
   dim3 grid(static_cast<unsigned>((T + rows - 1) / rows), static_cast<unsigned>(B));
   upsample_direct_kernel<Vec, MODE><<<grid, kUpThreads, smem, stream>>>(
-      x, x_sb, x_sp, ends, p0, p1, p_sb, out, P, static_cast<int>(row_bytes / sizeof(Vec)), T, rows, item_ends);
+      x, x_sb, x_sp, ends, p0, p1, p_sb, out, P, static_cast<int>(row_bytes / sizeof(Vec)), T, rows, item_ends, total_items);
   MG_LAUNCH_OK();
   return MG_OK;
 }
@@ -445,11 +457,12 @@ extern "C" int mg_upsample_norm_f32(const float* x, int64_t x_stride_b, int64_t 
   }
 }
 
-extern "C" int mg_upsample_packed_norm_f32(const float* x, int64_t x_stride_p, const int32_t* item_ends, const int32_t* ends,
+extern "C" int mg_upsample_packed_norm_f32(const float* x, int64_t x_stride_p, const int32_t* item_ends, int64_t total_items,
+                                           const int32_t* ends,
                                            const float* p0, const float* p1, int64_t param_stride_b, int norm_mode,
                                            float* out, int B, int max_items, int D, int64_t T, mg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  MG_REQUIRE(B >= 0 && max_items >= 0 && D >= 0 && T >= 0, "mg_upsample_packed_norm_f32: negative shape");
+  MG_REQUIRE(B >= 0 && max_items >= 0 && D >= 0 && T >= 0 && total_items >= 0, "mg_upsample_packed_norm_f32: negative shape");
   MG_REQUIRE(norm_mode >= MG_NORM_NONE && norm_mode <= MG_NORM_MINMAX, "mg_upsample_packed_norm_f32: bad norm_mode %d", norm_mode);
   MG_REQUIRE(B <= 65535, "mg_upsample_packed_norm_f32: B=%d exceeds 65535 utterances per call", B);
   if (B == 0 || T == 0 || D == 0) return MG_OK;
@@ -465,15 +478,15 @@ extern "C" int mg_upsample_packed_norm_f32(const float* x, int64_t x_stride_p, c
   // `max_items` bounds every utterance's item count (it sizes the shared-memory copy of the scan row)
   if (bulk_eligible(x, 0, x_sp, out, row_bytes, max_items) && params_vec_ok) {
     switch (norm_mode) {
-      case MG_NORM_NONE: return launch_bulk<MG_NORM_NONE>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
-      case MG_NORM_MVN: return launch_bulk<MG_NORM_MVN>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
-      default: return launch_bulk<MG_NORM_MINMAX>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
+      case MG_NORM_NONE: return launch_bulk<MG_NORM_NONE>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends, total_items);
+      case MG_NORM_MVN: return launch_bulk<MG_NORM_MVN>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends, total_items);
+      default: return launch_bulk<MG_NORM_MINMAX>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends, total_items);
     }
   }
   switch (norm_mode) {
-    case MG_NORM_NONE: return launch_direct<float, MG_NORM_NONE>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
-    case MG_NORM_MVN: return launch_direct<float, MG_NORM_MVN>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
-    default: return launch_direct<float, MG_NORM_MINMAX>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends);
+    case MG_NORM_NONE: return launch_direct<float, MG_NORM_NONE>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends, total_items);
+    case MG_NORM_MVN: return launch_direct<float, MG_NORM_MVN>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends, total_items);
+    default: return launch_direct<float, MG_NORM_MINMAX>(xb, 0, x_sp, ends, p0, p1, param_stride_b, ob, B, max_items, row_bytes, T, stream, item_ends, total_items);
   }
 }
 

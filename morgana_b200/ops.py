@@ -213,22 +213,22 @@ def upsample_packed(packed, packed_repeats, n_items, norm=None, max_len=None, ma
     summary = torch.empty((4,), dtype=torch.int64, device=dev)
     with _device_of(packed):
         check(lib.mg_dur_scan_packed(_ptr(packed_repeats), int(packed_repeats.dtype == torch.int32), _ptr(item_ends), B,
-                                     _ptr(ends), _ptr(n_frames), _ptr(summary), _stream()), 'mg_dur_scan_packed')
+                                     packed.shape[0], _ptr(ends), _ptr(n_frames), _ptr(summary), _stream()), 'mg_dur_scan_packed')
     if max_len is None or max_items is None:
         max_frames, n_negative, _, n_overflow = summary.tolist()        # the one device->host read, as in upsample()
         largest, bad_counts, total_items, _ = item_summary.tolist()
-        if n_negative or bad_counts:
+        if bad_counts or total_items != packed.shape[0]:      # (the kernels clamp such counts to the arrays)
+            raise ValueError('n_items sums to {} but {} items were given'.format(total_items, packed.shape[0]))
+        if n_negative:
             raise ValueError('repeats may not contain negative values.')
         if n_overflow:
             raise OverflowError('an utterance expands to more than 2**31 - 1 frames')
-        if total_items != packed.shape[0]:
-            raise ValueError('n_items sums to {} but {} items were given'.format(total_items, packed.shape[0]))
         max_len = int(max_frames) if max_len is None else int(max_len)
         max_items = int(largest) if max_items is None else int(max_items)
     mode, p0, p1, p_sb = _norm_args(norm, D, B, dev)
     out = torch.empty((B, int(max_len), D), dtype=torch.float32, device=dev)
     with _device_of(packed):
-        check(lib.mg_upsample_packed_norm_f32(_ptr(packed), packed.stride(0), _ptr(item_ends), _ptr(ends), _ptr(p0), _ptr(p1),
+        check(lib.mg_upsample_packed_norm_f32(_ptr(packed), packed.stride(0), _ptr(item_ends), packed.shape[0], _ptr(ends), _ptr(p0), _ptr(p1),
                                               p_sb, mode, _ptr(out), B, int(max_items), D, int(max_len), _stream()),
               'mg_upsample_packed_norm_f32')
     return (out, n_frames) if return_lengths else out
