@@ -67,34 +67,43 @@ def _listify(obj):
     return [obj]
 
 
+def _names(collections):
+    """One collection name or several -> a list of names."""
+    if isinstance(collections, str) or not isinstance(collections, Iterable):
+        return [collections]
+    return list(collections)
+
+
 class Handler(StatefulMetric):
-    r"""Container of named metric collections 'all' / 'train' / 'valid' / 'test' (morgana/metrics.py:52-185)."""
+    r"""Named collections of metrics -- 'all', 'train', 'valid', 'test' and any added later -- driven as
+    ``handler.accumulate(mode, name=(tensors..., seq_len), ...)`` (morgana/metrics.py:52-185).  A metric object registered
+    in several collections is shared between them, exactly as in the reference."""
     def __init__(self, **metrics):
         StatefulMetric.__init__(self, hidden=False)
-        self.collections = {'all': metrics, 'train': {}, 'valid': {}, 'test': {}}
-        self.metrics = self.collections['all']
-        self.add_metrics(('train', 'valid'), **metrics)
+        self.collections = dict(all=metrics, train={}, valid={}, test={})
+        self.metrics = self.collections['all']              # alias: every metric ever registered
+        for mode in ('train', 'valid'):
+            self.collections[mode].update(metrics)
 
     def __getitem__(self, name):
-        if name in self.collections:
+        try:
             return self.collections[name]
-        raise ValueError("No collection found by the name {}".format(name))
+        except KeyError:
+            raise ValueError("No collection found by the name {}".format(name)) from None
 
     def add_metrics(self, collections=('all',), **kwargs):
-        if not isinstance(collections, Iterable) or isinstance(collections, str):
-            collections = [collections]
-        if 'all' in collections:
-            collections = self.collections.keys()
-        for collection_name in collections:
-            self.collections[collection_name].update(kwargs)
+        targets = _names(collections)
+        if 'all' in targets:                                # 'all' means every collection that exists
+            targets = list(self.collections)
+        for target in targets:
+            self.collections[target].update(kwargs)
         self.metrics.update(kwargs)
 
     def add_collection(self, collection, from_collections=tuple()):
-        if not isinstance(from_collections, Iterable) or isinstance(from_collections, str):
-            from_collections = [from_collections]
-        self.collections[collection] = {}
-        for from_collection in from_collections:
-            self[collection].update(self[from_collection])
+        merged = {}
+        for source in _names(from_collections):
+            merged.update(self[source])
+        self.collections[collection] = merged
 
     def reset_state(self, collection, *args):
         for metric in self[collection].values():
@@ -102,26 +111,26 @@ class Handler(StatefulMetric):
 
     def accumulate(self, collection, **kwargs):
         r"""``name=(inputs..., [kwargs dict])`` per metric; each accumulate is one launch, none of them synchronises."""
-        for metric_name, inputs in kwargs.items():
-            inputs = _listify(inputs)
-            if isinstance(inputs[-1], dict):
-                inputs, kwinputs = inputs[:-1], inputs[-1]
-            else:
-                kwinputs = dict()
-            self[collection][metric_name].accumulate(*inputs, **kwinputs)
+        members = self[collection]
+        for name, inputs in kwargs.items():
+            args = _listify(inputs)
+            options = args.pop() if isinstance(args[-1], dict) else {}
+            members[name].accumulate(*args, **options)
 
     def result(self, collection='all', *args):
         return {name: metric.result(*args) for name, metric in self[collection].items()}
 
+    def _visible(self, collection):
+        return ((name, metric) for name, metric in self[collection].items() if not metric.hidden)
+
     def results_as_json_dict(self, collection='all', prefix=''):
-        return {prefix + name: metric.result_as_json() for name, metric in self[collection].items() if not metric.hidden}
+        return {prefix + name: metric.result_as_json() for name, metric in self._visible(collection)}
 
     def results_as_str_dict(self, collection='all', prefix=''):
-        return {prefix + name: str(metric) for name, metric in self[collection].items() if not metric.hidden}
+        return {prefix + name: str(metric) for name, metric in self._visible(collection)}
 
     def __str__(self):
-        d = self.results_as_str_dict('all')
-        return ' | '.join('{} = {}'.format(name, value) for name, value in d.items())
+        return ' | '.join('{} = {}'.format(name, text) for name, text in self.results_as_str_dict('all').items())
 
 
 class Print(StatefulMetric):
