@@ -76,7 +76,8 @@ int mg_upsample_norm_f32(const float* x, int64_t x_stride_b, int64_t x_stride_p,
                          const float* p0, const float* p1, int64_t param_stride_b, int norm_mode,
                          float* out, int B, int P, int D, int64_t T, int path, mg_stream_t stream);
 
-/* The same fused op with a bfloat16 output (additive; not in the reference): the exact fp32 result rounded to nearest-even,
+/* The same fused op (morgana/utils.py:175-228 composed with data.py:533-534 / 579-583) with a bfloat16 output (additive; not
+ * in the reference): the exact fp32 result rounded to nearest-even,
  * written once at half the bytes -- the activation format of the tensor-core layers (K7).  D % 8 == 0; out (B, T, D) bf16. */
 int mg_upsample_norm_f32_bf16out(const float* x, int64_t x_stride_b, int64_t x_stride_p, const int32_t* ends,
                                  const float* p0, const float* p1, int64_t param_stride_b, int norm_mode,
@@ -98,7 +99,8 @@ int mg_upsample_packed_norm_f32(const float* x, int64_t x_stride_p, const int32_
                                 const float* p0, const float* p1, int64_t param_stride_b, int norm_mode, float* out,
                                 int B, int max_items, int D, int64_t T, mg_stream_t stream);
 
-/* Dtype-agnostic expansion (the reference preserves any dtype): rows of row_bytes bytes are copied.
+/* Dtype-agnostic expansion (the advanced-index gather of morgana/utils.py:226 preserves any dtype): rows of
+ * row_bytes bytes are copied.
  * Strides in BYTES.  out is (B, T, row_bytes) contiguous. */
 int mg_upsample_bytes(const void* x, int64_t x_stride_b_bytes, int64_t x_stride_p_bytes, const int32_t* ends,
                       void* out, int B, int P, int64_t row_bytes, int64_t T, int path, mg_stream_t stream);
@@ -320,7 +322,8 @@ int mg_mlpg_f32(const float* means, int64_t m_sb, int64_t m_st, const float* var
                 const int64_t* seq_len, float* out, int64_t o_sb, int64_t o_st, int B, int64_t T, int feat_dim, int padding,
                 void* workspace, int64_t workspace_bytes, mg_stream_t stream);
 
-/* fp32 -> bf16 row conversion with K padding (feeds K7 from the fp32 frame-rate features; pads K to ld_out with 0). */
+/* fp32 -> bf16 row conversion with K padding: feeds K7 from the fp32 frame-rate features and weights of the example models'
+ * nn.Linear layers (README.rst:65-73, models/RNN_SPSS.py:33-41); pads K to ld_out with 0. */
 int mg_cast_pad_bf16(const float* x, int64_t ldx, void* out, int64_t ld_out, int64_t rows, int K, mg_stream_t stream);
 
 #ifdef __cplusplus
