@@ -45,7 +45,8 @@ int mg_sm_count(void);
  * n_frames   (B,)   int64 out: sum_p dur[b, p] (what the reference calls repeated_lens).
  * summary    int64[4] out: [0] max_b n_frames (the T of the output), [1] number of negative durations (the reference
  *            raises ValueError for any, utils.py:220), [2] sum_b n_frames, [3] number of utterances whose total
- *            exceeds INT32_MAX (unsupported).  The caller reads it back (32 bytes) to size the output.
+ *            exceeds INT32_MAX (unsupported).  The caller reads it back (32 bytes) to size the output.  May be NULL when
+ *            the caller already knows the padded length (nothing is accumulated or cleared then).
  */
 int mg_dur_scan(const void* dur, int dur_is_i32, int64_t dur_stride_b, int B, int P,
                 int32_t* ends, int64_t* n_frames, int64_t* summary, mg_stream_t stream);

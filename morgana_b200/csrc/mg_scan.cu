@@ -53,6 +53,7 @@ dur_scan_kernel(const DurT* __restrict__ dur, int64_t dur_stride_b, int B, int P
 
   if (lane == 0) {
     n_frames[b] = carry;
+    if (summary == nullptr) return;   // the caller knows the padded length and trusts the durations: nothing to read back
     // Integer atomics: exact and order-independent.
     atomicMax(summary + 0, static_cast<unsigned long long>(carry));
     if (negatives) atomicAdd(summary + 1, static_cast<unsigned long long>(negatives));
@@ -67,8 +68,7 @@ extern "C" int mg_dur_scan(const void* dur, int dur_is_i32, int64_t dur_stride_b
                            int64_t* n_frames, int64_t* summary, mg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MG_REQUIRE(B >= 0 && P >= 0, "mg_dur_scan: negative shape (B=%d, P=%d)", B, P);
-  MG_REQUIRE(summary != nullptr, "mg_dur_scan: summary is NULL");
-  MG_CUDA_OK(cudaMemsetAsync(summary, 0, 4 * sizeof(int64_t), stream));
+  if (summary != nullptr) MG_CUDA_OK(cudaMemsetAsync(summary, 0, 4 * sizeof(int64_t), stream));
   if (B == 0) return MG_OK;
   MG_REQUIRE(n_frames != nullptr && (P == 0 || (dur != nullptr && ends != nullptr)), "mg_dur_scan: NULL buffer");
   const int grid = (B + kScanWarpsPerCta - 1) / kScanWarpsPerCta;
@@ -88,8 +88,7 @@ extern "C" int mg_dur_scan_packed(const void* dur, int dur_is_i32, const int32_t
                                   int32_t* ends, int64_t* n_frames, int64_t* summary, mg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MG_REQUIRE(B >= 0 && total_items >= 0, "mg_dur_scan_packed: negative size");
-  MG_REQUIRE(summary != nullptr, "mg_dur_scan_packed: summary is NULL");
-  MG_CUDA_OK(cudaMemsetAsync(summary, 0, 4 * sizeof(int64_t), stream));
+  if (summary != nullptr) MG_CUDA_OK(cudaMemsetAsync(summary, 0, 4 * sizeof(int64_t), stream));
   if (B == 0) return MG_OK;
   MG_REQUIRE(n_frames != nullptr && item_ends != nullptr && (total_items == 0 || (dur != nullptr && ends != nullptr)),
              "mg_dur_scan_packed: NULL buffer");

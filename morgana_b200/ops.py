@@ -65,14 +65,15 @@ def _prepare_repeats(repeats, batch_size):
     return repeats
 
 
-def dur_scan(repeats):
-    """K1.  Returns ``(ends int32 (B, P), n_frames int64 (B,), summary int64 (4,))``, all on the device."""
+def dur_scan(repeats, want_summary=True):
+    """K1.  Returns ``(ends int32 (B, P), n_frames int64 (B,), summary int64 (4,))``, all on the device; ``summary`` is
+    None (and neither cleared nor accumulated) with ``want_summary=False``."""
     repeats = _prepare_repeats(repeats, repeats.shape[0])
     B, P = repeats.shape
     dev = repeats.device
     ends = torch.empty((B, P), dtype=torch.int32, device=dev)
     n_frames = torch.empty((B,), dtype=torch.int64, device=dev)
-    summary = torch.empty((4,), dtype=torch.int64, device=dev)
+    summary = torch.empty((4,), dtype=torch.int64, device=dev) if want_summary else None
     with _device_of(repeats):
         check(lib.mg_dur_scan(_ptr(repeats), int(repeats.dtype == torch.int32), repeats.stride(0) if B else 0, B, P,
                               _ptr(ends), _ptr(n_frames), _ptr(summary), _stream()), 'mg_dur_scan')
@@ -114,7 +115,7 @@ def _upsample_forward(x, repeats, norm, max_len, path, out_dtype=None):
         raise ValueError('repeats has {} items per utterance, sequence_feature has {}'.format(repeats.shape[1], P))
     if repeats.device != x.device:
         raise RuntimeError('repeats and sequence_feature are on different devices')
-    ends, n_frames, summary = dur_scan(repeats)
+    ends, n_frames, summary = dur_scan(repeats, want_summary=max_len is None)
     if max_len is None:
         # The one permitted device->host read: 32 bytes that size the output (the reference syncs here too,
         # morgana/utils.py:199) and carry the validity flags.
