@@ -308,6 +308,28 @@ int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t ldw, const
                    int y_is_bf16, int M, int N, int K, int act, mg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * K7 backward -- what autograd runs for the same layers in the training step (README.rst:86-99, experiment_builder.py:470-479
+ *     loss.backward() over the nn.Linear / nn.Sigmoid modules of README.rst:65-73, models/RNN_SPSS.py:33,38,41):
+ *
+ * mg_act_grad_bf16      g = grad_y * (1 - y) * y (ATen's sigmoid_backward; y = NULL: g = grad_y) written as bf16 rows of
+ *                       ld_out = round_up(N, 8) columns (padding zero) -- the operand of both backward GEMMs -- and, when
+ *                       bias_grad != NULL, bias_grad[n] = sum_m g[m, n] from the fp32 values of the same pass (fp64 partial
+ *                       sums, fixed order).  grad_y / y are (M, N) fp32 or bf16 with row strides ldg / ldy (elements).
+ *                       workspace: mg_act_grad_workspace_bytes(M, N) bytes (only read when bias_grad != NULL).
+ * mg_linear_wgrad_bf16  grad_w[N, K] = g[M, N]^T @ x[M, K]: bf16 operands exactly as the forward pass holds them (row-major,
+ *                       frames outermost, row strides multiples of 8), fp32 accumulation in tensor memory; the frames are
+ *                       split over the SMs and the slices summed in slice order (deterministic).  grad_w fp32, row stride ldw.
+ *                       workspace: mg_linear_wgrad_workspace_bytes(M, N, K) bytes, 16-byte aligned, no initialisation needed.
+ */
+int64_t mg_act_grad_workspace_bytes(int64_t M, int N);
+int mg_act_grad_bf16(const void* grad_y, int grad_is_bf16, int64_t ldg, const void* y, int y_is_bf16, int64_t ldy,
+                     void* out, int64_t ld_out, float* bias_grad, int64_t M, int N, void* workspace, int64_t workspace_bytes,
+                     mg_stream_t stream);
+int64_t mg_linear_wgrad_workspace_bytes(int64_t M, int N, int K);
+int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, int64_t ldx, float* grad_w, int64_t ldw, int64_t M, int N,
+                         int K, void* workspace, int64_t workspace_bytes, mg_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * K8  batched MLPG ("next" row 1 of the scope table) -- replaces viz.synthesis.MLPG (morgana/viz/synthesis.py:79-180)
  *     with the reference's default windows [1], [-0.5, 0, 0.5], [1, -2, 1] (synthesis.py:122-127): for every utterance and
  *     static dimension, the pentadiagonal system (sum_k W_k^T diag(1/var_k) W_k) c = sum_k W_k^T (mean_k / var_k) is built

@@ -91,6 +91,12 @@ PROTOTYPES = {
                             c_int, c_void_p, c_i64, c_void_p]),
     'mg_linear_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int,
                                c_int, c_void_p]),
+    'mg_act_grad_workspace_bytes': (c_i64, [c_i64, c_int]),
+    'mg_act_grad_bf16': (c_int, [c_void_p, c_int, c_i64, c_void_p, c_int, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int,
+                                 c_void_p, c_i64, c_void_p]),
+    'mg_linear_wgrad_workspace_bytes': (c_i64, [c_i64, c_int, c_int]),
+    'mg_linear_wgrad_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p, c_i64,
+                                     c_void_p]),
     'mg_cast_pad_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_void_p]),
 }
 

@@ -1,0 +1,376 @@
+// K7 backward -- the weight gradient of the dense layers on the tcgen05 tensor cores, and the fused activation backward that
+// feeds it.
+//
+// Replaces what autograd runs for nn.Linear (+ nn.Sigmoid) in the example models' training step (reference README.rst:65-73,
+// 86-99; models/RNN_SPSS.py:33,38,41; experiment_builder.py:470-479 loss.backward()): SigmoidBackward, the bias gradient's
+// column sum and the cuBLAS sgemm `grad_y^T @ x`.
+//
+//   K7g  act_grad_kernel      g = grad_y * (1 - y) * y   (or g = grad_y), written as bf16 rows padded to 8 columns -- the
+//                             operand of both backward GEMMs -- and the bias gradient sum_m g[m, :] accumulated from the fp32
+//                             values in the same pass (fp64 per-thread partials, fixed-order finish).  HBM-bound: every
+//                             grad_y / y element is read once, 2 bytes written.
+//   K7w  wgrad_tcgen05_kernel dW[n, k] = sum_m g[m, n] * x[m, k].  The reduction runs over FRAMES, so both operands are
+//                             "MN-major" in tensor-core terms: a TMA box of 64 frames x 64 features (128-byte swizzle) IS
+//                             the canonical MN-major tile -- 8-frame groups 1024 bytes apart (stride byte offset), 64-feature
+//                             atoms one box apart (leading byte offset) -- so neither tensor is transposed in memory.
+//                             The output is tiny (N x K <= 512 x 640) and the reduction is ~10^5 long: the frames are split
+//                             over the SMs, each CTA owns one 128 x BLOCK_K accumulator in tensor memory for its slice, and
+//                             the slices are summed in a fixed order by a second, small kernel (deterministic).
+#include <stdlib.h>
+#include <string.h>
+
+#include "mg_common.cuh"
+#include "mg_tcgen05.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------------------------
+// K7g: activation backward + bf16 cast + bias gradient
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kActThreads = 256;
+constexpr int kActRowsPerCta = 512;    // rows of one CTA: long enough to amortise the column-sum finish, short enough to fill the GPU
+
+struct ActGradParams {
+  const void* grad_y;     // (M, N) fp32 or bf16, row stride ldg
+  const void* y;          // (M, N) fp32 or bf16 forward output (sigmoid), or NULL: g = grad_y
+  __nv_bfloat16* out;     // (M, ld_out) bf16, columns >= N zero
+  double* partial;        // (n_ctas, ld_out) column sums of this CTA's rows, or NULL
+  int64_t ldg, ldy, ld_out, M;
+  int N, grad_is_bf16, y_is_bf16;
+};
+
+__device__ __forceinline__ float load_elem(const void* base, int64_t idx, int is_bf16) {
+  return is_bf16 ? __bfloat162float(static_cast<const __nv_bfloat16*>(base)[idx]) : __ldcs(static_cast<const float*>(base) + idx);
+}
+
+// Thread t owns the 8-column group t % G of rows t / G, t / G + R, ... (G = ld_out / 8 groups per row, R = rows per pass):
+// always the same columns, so the bias gradient is 8 per-thread accumulators.
+template <bool VEC>
+__global__ void __launch_bounds__(kActThreads)
+act_grad_kernel(const ActGradParams prm) {
+  __shared__ double s_sum[kActThreads][9];   // padded: the finish reads a column of it
+  const int G = static_cast<int>(prm.ld_out / 8);
+  const int R = kActThreads / G;             // G <= 256 is checked by the host
+  const int tid = threadIdx.x;
+  const int grp = tid % G, lane_row = tid / G;
+  const bool active = lane_row < R;
+  const int c0 = grp * 8;
+  const int64_t r_begin = static_cast<int64_t>(blockIdx.x) * kActRowsPerCta;
+  const int64_t r_end = min(prm.M, r_begin + kActRowsPerCta);
+  double acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.;
+  if (active) {
+    for (int64_t r = r_begin + lane_row; r < r_end; r += R) {
+      float g[8];
+      if (VEC) {   // fp32 operands, rows 16-byte aligned, N a multiple of 8: two float4 per operand
+        const float4* gp = reinterpret_cast<const float4*>(static_cast<const float*>(prm.grad_y) + r * prm.ldg + c0);
+        const float4 a = mg_ld_stream_f4(gp), b = mg_ld_stream_f4(gp + 1);
+        g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+        if (prm.y != nullptr) {
+          const float4* yp = reinterpret_cast<const float4*>(static_cast<const float*>(prm.y) + r * prm.ldy + c0);
+          const float4 ya = mg_ld_stream_f4(yp), yb = mg_ld_stream_f4(yp + 1);
+          const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) g[j] = __fmul_rn(__fmul_rn(g[j], __fsub_rn(1.f, yv[j])), yv[j]);   // ATen sigmoid_backward: grad * (1 - y) * y
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          g[j] = 0.f;
+          if (c0 + j < prm.N) {
+            g[j] = load_elem(prm.grad_y, r * prm.ldg + c0 + j, prm.grad_is_bf16);
+            if (prm.y != nullptr) {
+              const float yv = load_elem(prm.y, r * prm.ldy + c0 + j, prm.y_is_bf16);
+              g[j] = __fmul_rn(__fmul_rn(g[j], __fsub_rn(1.f, yv)), yv);
+            }
+          }
+        }
+      }
+      __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[j] = __float2bfloat16_rn(g[j]); acc[j] += static_cast<double>(g[j]); }
+      *reinterpret_cast<uint4*>(prm.out + r * prm.ld_out + c0) = *reinterpret_cast<const uint4*>(v);
+    }
+  }
+  if (prm.partial == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s_sum[tid][j] = acc[j];
+  __syncthreads();
+  // column c of this CTA = sum over the R row-lanes that own group c / 8, in lane order
+  for (int c = tid; c < prm.ld_out; c += kActThreads) {
+    double s = 0.;
+    for (int l = 0; l < R; ++l) s += s_sum[l * G + c / 8][c % 8];
+    prm.partial[static_cast<int64_t>(blockIdx.x) * prm.ld_out + c] = s;
+  }
+}
+
+// bias_grad[c] = sum over CTAs in index order (fp64), rounded once.
+__global__ void __launch_bounds__(256)
+bias_grad_finish_kernel(const double* __restrict__ partial, int n_ctas, int64_t ld, int N, float* __restrict__ bias_grad) {
+  // a warp per column: lanes take CTAs lane, lane + 32, ... in order, then a fixed shuffle tree
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= N) return;
+  double s = 0.;
+  for (int i = lane; i < n_ctas; i += 32) s += partial[static_cast<int64_t>(i) * ld + warp];
+  s = mg_warp_sum(s);
+  if (lane == 0) bias_grad[warp] = static_cast<float>(s);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// K7w: weight gradient
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kWgTileN = 128;             // output rows (out_features) of one accumulator = TMEM lanes
+constexpr int kWgMaxTileK = 256;          // output columns (in_features) of one accumulator = N of the MMA
+constexpr int kWgFrames = 64;             // frames per shared-memory stage (4 MMAs of 16)
+constexpr int kWgAtom = 64;               // features per TMA box / swizzle atom (128 bytes of bf16)
+constexpr uint32_t kWgBoxBytes = kWgFrames * kWgAtom * 2;            // 8 KB
+constexpr int kWgMaxStages = 6;
+constexpr uint32_t kWgRingBytes = 192 * 1024;
+constexpr int kWgThreads = 192;           // TMA producer, MMA issuer, 4 epilogue warps
+constexpr size_t kWgSmem = kWgRingBytes + 1024;
+constexpr int kWgTmemCols = 256;
+
+struct WgradParams {
+  float* partial;          // (splits, n_tiles * 128, k_tiles * tile_k) fp32
+  int64_t M;
+  int N, K, tile_k, n_tiles, k_tiles, splits, blocks_per_split, n_fblocks, n_stages;
+  uint32_t stage_bytes;
+};
+
+// MN-major operand tile, 128-byte swizzle: 64-feature atoms `kWgBoxBytes` apart (leading byte offset), 8-frame groups 1024 bytes
+// apart (stride byte offset).  cute/atom/mma_traits_sm100.hpp: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.
+__device__ __forceinline__ uint64_t umma_smem_desc_mn(uint32_t smem_addr) {
+  uint64_t desc = 0;
+  desc |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  desc |= static_cast<uint64_t>(kWgBoxBytes >> 4) << 16;
+  desc |= static_cast<uint64_t>(1024 >> 4) << 32;
+  desc |= static_cast<uint64_t>(1) << 46;
+  desc |= static_cast<uint64_t>(2) << 61;
+  return desc;
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
+                     const __grid_constant__ WgradParams prm) {
+  extern __shared__ unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t s_full[kWgMaxStages], s_empty[kWgMaxStages], s_acc_full;
+  __shared__ uint32_t s_tmem_base;
+  unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x % (prm.n_tiles * prm.k_tiles), split = blockIdx.x / (prm.n_tiles * prm.k_tiles);
+  const int n0 = (tile / prm.k_tiles) * kWgTileN, k0 = (tile % prm.k_tiles) * prm.tile_k;
+  const int fb_begin = split * prm.blocks_per_split;
+  const int fb_end = min(prm.n_fblocks, fb_begin + prm.blocks_per_split);
+  const int n_blocks = fb_end - fb_begin;       // >= 1 by construction of the grid
+  const int kStages = prm.n_stages;
+  const int k_boxes = prm.tile_k / kWgAtom;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_x) : "memory");
+    for (int s = 0; s < kStages; ++s) { mg_mbar_init(&s_full[s], 1); mg_mbar_init(&s_empty[s], 1); }
+    mg_mbar_init(&s_acc_full, 1);
+    mg_mbar_fence_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mg_smem_addr(&s_tmem_base)), "n"(kWgTmemCols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = s_tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ===== TMA producer: per stage 2 boxes of g (128 out_features) and tile_k / 64 boxes of x
+      const uint32_t stage_tx = static_cast<uint32_t>(2 + k_boxes) * kWgBoxBytes;
+      for (int it = 0; it < n_blocks; ++it) {
+        const int s = it % kStages;
+        if (it >= kStages) mg_mbar_wait(&s_empty[s], static_cast<uint32_t>(((it / kStages) - 1) & 1));
+        unsigned char* a_tile = ring + static_cast<size_t>(s) * prm.stage_bytes;
+        const int f0 = (fb_begin + it) * kWgFrames;
+        mg_mbar_expect_tx(&s_full[s], stage_tx);
+        tma_load_2d(a_tile, &map_g, n0, f0, &s_full[s]);
+        tma_load_2d(a_tile + kWgBoxBytes, &map_g, n0 + kWgAtom, f0, &s_full[s]);
+        for (int j = 0; j < k_boxes; ++j)
+          tma_load_2d(a_tile + (2 + j) * kWgBoxBytes, &map_x, k0 + j * kWgAtom, f0, &s_full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ===== MMA issuer: D[128 x tile_k] += g_tile^T (MN-major A) * x_tile (MN-major B), 16 frames per MMA
+      uint32_t idesc = umma_instr_desc(prm.tile_k, kWgTileN);
+      idesc |= (1u << 15) | (1u << 16);         // A and B are MN-major
+      for (int it = 0; it < n_blocks; ++it) {
+        const int s = it % kStages;
+        mg_mbar_wait(&s_full[s], static_cast<uint32_t>((it / kStages) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_addr = mg_smem_addr(ring + static_cast<size_t>(s) * prm.stage_bytes);
+        const uint32_t b_addr = a_addr + 2 * kWgBoxBytes;
+#pragma unroll
+        for (int k = 0; k < kWgFrames / kUmmaK; ++k)   // 16 frames = two 8-frame groups = 2048 bytes further into every atom
+          umma_f16(tmem_base, umma_smem_desc_mn(a_addr + k * 2048), umma_smem_desc_mn(b_addr + k * 2048), idesc, (it | k) != 0 ? 1u : 0u);
+        umma_commit(&s_empty[s]);
+      }
+      umma_commit(&s_acc_full);
+    }
+  } else {
+    // ===== epilogue: warp w reads TMEM lanes 32 * (w % 4) ..; lane = out_feature row, 32 in_feature columns per load
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    mg_mbar_wait(&s_acc_full, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int64_t ld = static_cast<int64_t>(prm.k_tiles) * prm.tile_k;
+    float* dst_row = prm.partial + (static_cast<int64_t>(split) * prm.n_tiles * kWgTileN + n0 + row) * ld + k0;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+    for (int c0 = 0; c0 < prm.tile_k; c0 += 32) {
+      uint32_t a[32];
+      tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), a);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<uint4*>(dst_row + c0 + 4 * j) = make_uint4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+    }
+  }
+
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kWgTmemCols) : "memory");
+}
+
+// dW[n, k] = sum over frame slices in slice order (fp32, as the tensor cores accumulate), one thread per element.
+__global__ void __launch_bounds__(256)
+wgrad_finish_kernel(const float* __restrict__ partial, int splits, int64_t slice_elems, int64_t ld, int N, int K,
+                    float* __restrict__ grad_w, int64_t ldw) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= static_cast<int64_t>(N) * K) return;
+  const int n = static_cast<int>(idx / K), k = static_cast<int>(idx - static_cast<int64_t>(n) * K);
+  const float* p = partial + static_cast<int64_t>(n) * ld + k;
+  float s = 0.f;
+  for (int i = 0; i < splits; ++i) s = __fadd_rn(s, __ldg(p + i * slice_elems));
+  grad_w[static_cast<int64_t>(n) * ldw + k] = s;
+}
+
+struct WgradPlan {
+  int tile_k, n_tiles, k_tiles, splits, blocks_per_split, n_fblocks;
+  int64_t partial_elems;
+};
+
+WgradPlan plan_wgrad(int64_t M, int N, int K) {
+  WgradPlan p;
+  p.tile_k = K <= 64 ? 64 : (K <= 128 ? 128 : (K <= 192 ? 192 : 256));
+  p.n_tiles = (N + kWgTileN - 1) / kWgTileN;
+  p.k_tiles = (K + p.tile_k - 1) / p.tile_k;
+  p.n_fblocks = static_cast<int>((M + kWgFrames - 1) / kWgFrames);
+  const int tiles = p.n_tiles * p.k_tiles;
+  int splits = mg_cached_sm_count() / tiles;
+  if (splits < 1) splits = 1;
+  if (splits > p.n_fblocks) splits = p.n_fblocks > 0 ? p.n_fblocks : 1;
+  p.blocks_per_split = p.n_fblocks > 0 ? (p.n_fblocks + splits - 1) / splits : 1;
+  p.splits = p.n_fblocks > 0 ? (p.n_fblocks + p.blocks_per_split - 1) / p.blocks_per_split : 1;
+  p.partial_elems = static_cast<int64_t>(p.splits) * p.n_tiles * kWgTileN * p.k_tiles * p.tile_k;
+  return p;
+}
+
+int act_grad_ctas(int64_t M) { return static_cast<int>((M + kActRowsPerCta - 1) / kActRowsPerCta); }
+
+}  // namespace
+
+extern "C" int64_t mg_act_grad_workspace_bytes(int64_t M, int N) {
+  if (M <= 0 || N <= 0) return 0;
+  const int64_t ld = (static_cast<int64_t>(N) + 7) / 8 * 8;
+  return static_cast<int64_t>(act_grad_ctas(M)) * ld * static_cast<int64_t>(sizeof(double));
+}
+
+extern "C" int mg_act_grad_bf16(const void* grad_y, int grad_is_bf16, int64_t ldg, const void* y, int y_is_bf16, int64_t ldy,
+                                void* out, int64_t ld_out, float* bias_grad, int64_t M, int N, void* workspace,
+                                int64_t workspace_bytes, mg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MG_REQUIRE(M >= 0 && N >= 1, "mg_act_grad_bf16: bad shape (M=%lld, N=%d)", static_cast<long long>(M), N);
+  MG_REQUIRE(ld_out == (static_cast<int64_t>(N) + 7) / 8 * 8, "mg_act_grad_bf16: ld_out must be N rounded up to 8 (got %lld)",
+             static_cast<long long>(ld_out));
+  MG_REQUIRE(ld_out / 8 <= kActThreads, "mg_act_grad_bf16: N=%d exceeds %d features", N, kActThreads * 8);
+  MG_REQUIRE(ldg >= N && (y == nullptr || ldy >= N), "mg_act_grad_bf16: row strides must cover the row");
+  if (M == 0) {
+    if (bias_grad != nullptr) MG_CUDA_OK(cudaMemsetAsync(bias_grad, 0, sizeof(float) * N, stream));
+    return MG_OK;
+  }
+  MG_REQUIRE(grad_y != nullptr && out != nullptr && mg_aligned(out, 16), "mg_act_grad_bf16: NULL or misaligned buffer");
+  const int n_ctas = act_grad_ctas(M);
+  if (bias_grad != nullptr)
+    MG_REQUIRE(workspace != nullptr && workspace_bytes >= mg_act_grad_workspace_bytes(M, N),
+               "mg_act_grad_bf16: workspace of %lld bytes needed", static_cast<long long>(mg_act_grad_workspace_bytes(M, N)));
+  ActGradParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.grad_y = grad_y; prm.y = y; prm.out = static_cast<__nv_bfloat16*>(out);
+  prm.partial = bias_grad != nullptr ? static_cast<double*>(workspace) : nullptr;
+  prm.ldg = ldg; prm.ldy = ldy; prm.ld_out = ld_out; prm.M = M; prm.N = N;
+  prm.grad_is_bf16 = grad_is_bf16; prm.y_is_bf16 = y_is_bf16;
+  const bool vec = !grad_is_bf16 && (y == nullptr || !y_is_bf16) && N % 8 == 0 && ldg % 4 == 0 && mg_aligned(grad_y, 16) &&
+                   (y == nullptr || (ldy % 4 == 0 && mg_aligned(y, 16)));
+  if (vec) act_grad_kernel<true><<<n_ctas, kActThreads, 0, stream>>>(prm);
+  else act_grad_kernel<false><<<n_ctas, kActThreads, 0, stream>>>(prm);
+  MG_LAUNCH_OK();
+  if (bias_grad != nullptr) {
+    const int warps_per_cta = 256 / 32;
+    bias_grad_finish_kernel<<<(N + warps_per_cta - 1) / warps_per_cta, 256, 0, stream>>>(prm.partial, n_ctas, ld_out, N, bias_grad);
+    MG_LAUNCH_OK();
+  }
+  return MG_OK;
+}
+
+extern "C" int64_t mg_linear_wgrad_workspace_bytes(int64_t M, int N, int K) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  return plan_wgrad(M, N, K).partial_elems * static_cast<int64_t>(sizeof(float));
+}
+
+extern "C" int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, int64_t ldx, float* grad_w, int64_t ldw,
+                                    int64_t M, int N, int K, void* workspace, int64_t workspace_bytes, mg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "mg_linear_wgrad_bf16: bad shape (M=%lld, N=%d, K=%d)", static_cast<long long>(M), N, K);
+  MG_REQUIRE(M < (int64_t(1) << 31) - kWgFrames, "mg_linear_wgrad_bf16: too many frames");
+  MG_REQUIRE(grad_w != nullptr && ldw >= K, "mg_linear_wgrad_bf16: bad output");
+  if (M == 0) {
+    MG_CUDA_OK(cudaMemset2DAsync(grad_w, ldw * sizeof(float), 0, K * sizeof(float), N, stream));
+    return MG_OK;
+  }
+  MG_REQUIRE(g != nullptr && x != nullptr, "mg_linear_wgrad_bf16: NULL buffer");
+  MG_REQUIRE(ldg % 8 == 0 && ldx % 8 == 0 && ldg >= N && ldx >= K && mg_aligned(g, 16) && mg_aligned(x, 16),
+             "mg_linear_wgrad_bf16: operand rows must be 16-byte aligned and cover the row (ldg=%lld, ldx=%lld)",
+             static_cast<long long>(ldg), static_cast<long long>(ldx));
+  const WgradPlan plan = plan_wgrad(M, N, K);
+  MG_REQUIRE(workspace != nullptr && workspace_bytes >= plan.partial_elems * static_cast<int64_t>(sizeof(float)) && mg_aligned(workspace, 16),
+             "mg_linear_wgrad_bf16: workspace of %lld bytes needed", static_cast<long long>(plan.partial_elems * sizeof(float)));
+
+  CUtensorMap map_g, map_x;
+  int rc = make_map(&map_g, g, M, N, ldg, kWgAtom, kWgFrames, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  if (rc != MG_OK) return rc;
+  rc = make_map(&map_x, x, M, K, ldx, kWgAtom, kWgFrames, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  if (rc != MG_OK) return rc;
+
+  WgradParams prm;
+  memset(&prm, 0, sizeof(prm));
+  prm.partial = static_cast<float*>(workspace);
+  prm.M = M; prm.N = N; prm.K = K; prm.tile_k = plan.tile_k; prm.n_tiles = plan.n_tiles; prm.k_tiles = plan.k_tiles;
+  prm.splits = plan.splits; prm.blocks_per_split = plan.blocks_per_split; prm.n_fblocks = plan.n_fblocks;
+  prm.stage_bytes = static_cast<uint32_t>(2 + plan.tile_k / kWgAtom) * kWgBoxBytes;     // a multiple of 8 KB
+  prm.n_stages = static_cast<int>(kWgRingBytes / prm.stage_bytes);
+  if (prm.n_stages > kWgMaxStages) prm.n_stages = kWgMaxStages;
+
+  static bool attr_done[64] = {};
+  int device = 0;
+  MG_CUDA_OK(cudaGetDevice(&device));
+  if (!attr_done[device & 63]) {
+    MG_CUDA_OK(cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWgSmem)));
+    attr_done[device & 63] = true;
+  }
+  const unsigned grid = static_cast<unsigned>(plan.splits * plan.n_tiles * plan.k_tiles);
+  wgrad_tcgen05_kernel<<<grid, kWgThreads, kWgSmem, stream>>>(map_g, map_x, prm);
+  MG_LAUNCH_OK();
+  const int64_t slice = static_cast<int64_t>(plan.n_tiles) * kWgTileN * plan.k_tiles * plan.tile_k;
+  const int64_t elems = static_cast<int64_t>(N) * K;
+  wgrad_finish_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, stream>>>(
+      prm.partial, plan.splits, slice, static_cast<int64_t>(plan.k_tiles) * plan.tile_k, N, K, grad_w, ldw);
+  MG_LAUNCH_OK();
+  return MG_OK;
+}

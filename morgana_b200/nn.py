@@ -7,8 +7,10 @@ a forward pass that is one ``mg_linear_bf16`` launch with the bias and the sigmo
 Forward tolerance (stated in tests/test_gpu_parity.py): bf16 operands, fp32 accumulation -> <= 2 % of the output range
 against the fp32 layer, 2e-3 against the exact product of the bf16-rounded operands.
 Backward: the input gradient ``g @ W`` runs through the same tcgen05 kernel (``y = g @ (W^T)^T`` with a transposed bf16
-copy of the weight); the weight gradient ``g^T @ x`` reduces over the frame axis, needs M-major operands and a split
-reduction, and stays a plain library GEMM (``torch.matmul`` in bf16, cuBLAS -- as the north star allows for plain GEMMs).
+copy of the weight) where the reduction is long enough; the sigmoid's backward, the bf16 cast of the gradient and the bias
+gradient are one pass (``mg_act_grad_bf16``); the weight gradient ``g^T @ x`` reduces over the frame axis: MN-major tcgen05
+operands straight from the row-major tensors, frames split over the SMs, slices summed in a fixed order
+(``mg_linear_wgrad_bf16``).
 """
 import torch
 
@@ -30,30 +32,30 @@ class _LinearFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_y):
         x_bf16, weight_bf16, y = ctx.saved_tensors
-        g = grad_y.to(torch.float32)
-        if ctx.act == 'sigmoid':
-            yf = y.to(torch.float32)
-            g = g * yf * (1. - yf)
-        g16 = g.to(torch.bfloat16)
-        k = ctx.k
+        k, n = ctx.k, weight_bf16.shape[0]
+        if grad_y.dtype not in (torch.float32, torch.bfloat16):
+            grad_y = grad_y.to(torch.float32)
+        if grad_y.stride(0) < n:                 # expanded gradients (e.g. of a plain .sum())
+            grad_y = grad_y.contiguous()
+        # K7g: sigmoid backward, the bf16 operand of both GEMMs (rows padded to 8 columns) and the bias gradient, one pass
+        g16, grad_b = ops.act_grad_bf16(grad_y, y if ctx.act == 'sigmoid' else None,
+                                        want_bias_grad=ctx.has_bias and ctx.needs_input_grad[2])
         grad_x = None
-        n = g16.shape[1]
         if ctx.needs_input_grad[0] and n < _DGRAD_MIN_REDUCTION:
             # short reductions (the 128- / 32- / 1-wide layers): two K blocks per tile leave the persistent pipeline mostly
             # filling and draining -- the library GEMM is faster there (README MLP training step 0.81 vs 0.86 ms)
-            grad_x = torch.matmul(g16, weight_bf16[:, :k]).to(ctx.x_dtype)
+            grad_x = torch.matmul(g16[:, :n], weight_bf16[:, :k]).to(ctx.x_dtype)
         elif ctx.needs_input_grad[0]:
             # dgrad on the tensor cores: (M, N) @ (N, K) as the forward kernel sees it, x' = g16 (M, N'), w' = W^T (K, N')
-            n_pad = (n + 7) // 8 * 8
-            if n == n_pad:                       # one transposing copy; the reduction length needs no padding
-                g_op, w_t = g16, weight_bf16[:, :k].t().contiguous()
-            else:                                # out_features not a multiple of 8 (the 1- / 3- / 187-wide heads)
-                g_op = torch.nn.functional.pad(g16, (0, n_pad - n))
-                w_t = torch.nn.functional.pad(weight_bf16[:, :k].t(), (0, n_pad - n))
-            grad_x = ops.linear_bf16(g_op.contiguous(), w_t, None, act=None, out_dtype=torch.float32 if ctx.x_dtype == torch.float32
+            n_pad = g16.shape[1]
+            w_t = weight_bf16[:, :k].t()
+            w_t = w_t.contiguous() if n == n_pad else torch.nn.functional.pad(w_t, (0, n_pad - n))
+            grad_x = ops.linear_bf16(g16, w_t, None, act=None, out_dtype=torch.float32 if ctx.x_dtype == torch.float32
                                      else torch.bfloat16)
-        grad_w = torch.matmul(g16.t(), x_bf16[:, :k]).to(torch.float32) if ctx.needs_input_grad[1] else None
-        grad_b = g.sum(dim=0) if ctx.has_bias and ctx.needs_input_grad[2] else None
+        grad_w = None
+        if ctx.needs_input_grad[1]:
+            # K7w: g^T @ x over the frame axis, both operands as they lie in memory (MN-major tcgen05 operands)
+            grad_w = ops.linear_wgrad_bf16(g16, x_bf16, out_features=n, in_features=k)
         return grad_x, grad_w, grad_b, None, None, None
 
 

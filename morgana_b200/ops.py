@@ -646,6 +646,66 @@ def linear_bf16(x, weight, bias=None, act=None, out_dtype=torch.float32):
     return y
 
 
+def act_grad_bf16(grad_y, y=None, want_bias_grad=True):
+    """K7 backward, first step: ``g = grad_y * (1 - y) * y`` (sigmoid; ``y=None``: ``g = grad_y``) as bf16 rows padded to a
+    multiple of 8 columns, and ``g.sum(0)`` (float32, from the unrounded values) in the same pass.
+
+    grad_y, y : (M, N) float32 or bfloat16.  Returns ``(g_bf16 (M, round_up(N, 8)), bias_grad (N,) or None)``.
+    """
+    _require_cuda(grad_y, 'grad_y')
+    if grad_y.dim() != 2 or (y is not None and y.shape != grad_y.shape):
+        raise ValueError('act_grad_bf16 takes 2-D tensors of one shape')
+    for name, t in (('grad_y', grad_y), ('y', y)):
+        if t is not None and t.dtype not in (torch.float32, torch.bfloat16):
+            raise TypeError('{}: float32 or bfloat16 expected, got {}'.format(name, t.dtype))
+    if grad_y.shape[1] > 1 and grad_y.stride(1) != 1:
+        grad_y = grad_y.contiguous()
+    if y is not None and y.shape[1] > 1 and y.stride(1) != 1:
+        y = y.contiguous()
+    M, N = grad_y.shape
+    ld_out = (N + 7) // 8 * 8
+    dev = grad_y.device
+    out = torch.empty((M, ld_out), dtype=torch.bfloat16, device=dev)
+    bias_grad = torch.empty((N,), dtype=torch.float32, device=dev) if want_bias_grad else None
+    ws_bytes = lib.mg_act_grad_workspace_bytes(M, N) if want_bias_grad else 0
+    ws = torch.empty((max(ws_bytes, 8) // 8,), dtype=torch.float64, device=dev)
+    with _device_of(grad_y):
+        check(lib.mg_act_grad_bf16(_ptr(grad_y), int(grad_y.dtype == torch.bfloat16), grad_y.stride(0) if M else N,
+                                   _ptr(y), int(y is not None and y.dtype == torch.bfloat16),
+                                   y.stride(0) if (y is not None and M) else N, _ptr(out), ld_out, _ptr(bias_grad), M, N,
+                                   _ptr(ws), ws.numel() * 8, _stream()), 'mg_act_grad_bf16')
+    return out, bias_grad
+
+
+def linear_wgrad_bf16(g, x, out_features=None, in_features=None):
+    """K7 backward, weight gradient: ``g[:, :N].T @ x[:, :K]`` -> (N, K) float32 on the tcgen05 tensor cores.
+
+    g : (M, >= N) bfloat16, x : (M, >= K) bfloat16, both row-major with row strides that are multiples of 8 -- the layouts
+    :func:`act_grad_bf16` and :func:`cast_pad_bf16` produce; nothing is transposed in memory.
+    """
+    _require_cuda(g, 'g')
+    _require_cuda(x, 'x')
+    if g.dim() != 2 or x.dim() != 2 or g.shape[0] != x.shape[0]:
+        raise ValueError('linear_wgrad_bf16 takes 2-D operands with one row per frame')
+    if g.dtype != torch.bfloat16 or x.dtype != torch.bfloat16:
+        raise TypeError('linear_wgrad_bf16 takes bfloat16 operands')
+    M = g.shape[0]
+    N = g.shape[1] if out_features is None else int(out_features)
+    K = x.shape[1] if in_features is None else int(in_features)
+    if not (0 < N <= g.shape[1] and 0 < K <= x.shape[1]):
+        raise ValueError('out_features / in_features exceed the operands')
+    for name, t in (('g', g), ('x', x)):
+        if M and (t.stride(1) != 1 or t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0):
+            raise ValueError('{}: rows must be contiguous, 16-byte aligned, with a stride that is a multiple of 8'.format(name))
+    grad_w = torch.empty((N, K), dtype=torch.float32, device=g.device)
+    ws_bytes = lib.mg_linear_wgrad_workspace_bytes(M, N, K)
+    ws = torch.empty((max(ws_bytes, 16) // 4,), dtype=torch.float32, device=g.device)
+    with _device_of(g):
+        check(lib.mg_linear_wgrad_bf16(_ptr(g), g.stride(0) if M else 8, _ptr(x), x.stride(0) if M else 8, _ptr(grad_w), K, M, N, K,
+                                       _ptr(ws), ws.numel() * 4, _stream()), 'mg_linear_wgrad_bf16')
+    return grad_w
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # K8: batched MLPG
 # ----------------------------------------------------------------------------------------------------------------------

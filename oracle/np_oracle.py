@@ -391,6 +391,20 @@ def linear(x, weight, bias=None, act=None):
     return y
 
 
+
+def sigmoid_grad(grad_y, y):
+    """ATen's ``sigmoid_backward``: ``(grad_y * (1 - y)) * y`` with every operation rounded in the operands' dtype -- what
+    autograd runs for nn.Sigmoid in the models' training step (reference README.rst:65-73, experiment_builder.py:470-479)."""
+    grad_y, y = np.asarray(grad_y), np.asarray(y)
+    one = np.asarray(1, y.dtype)
+    return (grad_y * (one - y)) * y
+
+
+def linear_wgrad(g, x):
+    """Weight gradient of ``y = x W^T + b``: ``g^T x`` summed over the frame axis, in float64; the bias gradient is
+    ``g.sum(0)`` (autograd of nn.Linear in the reference's training step, experiment_builder.py:470-479)."""
+    return np.asarray(g, np.float64).T @ np.asarray(x, np.float64)
+
 # ----------------------------------------------------------------------------------------------------------------
 # "next" row 1: viz.synthesis.MLPG  (morgana/viz/synthesis.py:79-180)
 # PARITY UNPINNED: the reference solves the system with `bandmat` (unpinned in setup.py:12, absent from this image and

@@ -681,6 +681,54 @@ def test_linear_tcgen05_vs_oracle(mg, M, K, N, act):
     np.testing.assert_allclose(y16, exact_on_rounded, rtol=1e-2, atol=1e-2)
 
 
+@pytest.mark.parametrize('M,N', [(70, 64), (1000, 512), (45, 187), (19, 1), (700, 3), (4097, 199), (0, 16)])
+@pytest.mark.parametrize('act', [None, 'sigmoid'])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_act_grad_bf16_vs_oracle(mg, M, N, act, dtype):
+    """K7g: sigmoid backward + bf16 cast + bias gradient in one pass.  The bf16 rows are the round-to-nearest-even of the
+    fp32 ATen formula (bit-exact); the bias gradient is the fp64 column sum of the unrounded values, rounded once."""
+    rng = np.random.default_rng(M + N)
+    grad = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32)).to(dtype)
+    y = torch.from_numpy(rng.random((M, N), dtype=np.float32)).to(dtype) if act else None
+    g16, bias_grad = mg.ops.act_grad_bf16(grad.cuda(), None if y is None else y.cuda())
+    n_pad = (N + 7) // 8 * 8
+    assert g16.shape == (M, n_pad) and g16.dtype == torch.bfloat16 and bias_grad.shape == (N,)
+    g32 = grad.float().numpy() if y is None else O.sigmoid_grad(grad.float().numpy(), y.float().numpy())
+    assert g32.dtype == np.float32
+    want16 = torch.from_numpy(g32).to(torch.bfloat16)
+    assert torch.equal(g16[:, :N].cpu().view(torch.int16), want16.view(torch.int16))
+    assert not g16[:, N:].any()
+    want_bias = g32.astype(np.float64).sum(0)
+    np.testing.assert_allclose(bias_grad.cpu().numpy(), want_bias, rtol=1e-6, atol=1e-6 * np.abs(g32).sum(0).max() if M else 0)
+    only, none = mg.ops.act_grad_bf16(grad.cuda(), None if y is None else y.cuda(), want_bias_grad=False)
+    assert none is None and torch.equal(only, g16)
+
+
+@pytest.mark.parametrize('M,N,K', [(70, 64, 600), (33, 48, 609), (45, 187, 256), (19, 1, 32), (5000, 512, 600), (257, 256, 512),
+                                   (128, 32, 128), (5, 16, 8), (4097, 199, 640), (20001, 128, 512), (1, 3, 64), (9000, 130, 130)])
+def test_linear_wgrad_tcgen05_vs_oracle(mg, M, N, K):
+    """K7w: g^T @ x over the frame axis with MN-major tcgen05 operands.  Against the fp64 product of the same bf16 operands
+    only the fp32 accumulation differs: 1e-4 of the largest entry; and the split reduction has a fixed order (same bits twice)."""
+    rng = np.random.default_rng(M + N + K)
+    g = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32))
+    x = torch.from_numpy(rng.random((M, K), dtype=np.float32))
+    g16 = mg.ops.act_grad_bf16(g.cuda(), None, want_bias_grad=False)[0]
+    x16 = mg.ops.cast_pad_bf16(x.cuda())
+    got = mg.ops.linear_wgrad_bf16(g16, x16, out_features=N, in_features=K)
+    assert got.shape == (N, K) and got.dtype == torch.float32
+    want = O.linear_wgrad(g16[:, :N].float().cpu().numpy(), x16[:, :K].float().cpu().numpy())
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * max(1.0, np.abs(want).max()))
+    again = mg.ops.linear_wgrad_bf16(g16, x16, out_features=N, in_features=K)
+    assert torch.equal(got, again)
+
+
+def test_linear_wgrad_empty_batch_is_zero(mg):
+    g16 = torch.zeros((0, 16), dtype=torch.bfloat16, device='cuda')
+    x16 = torch.zeros((0, 64), dtype=torch.bfloat16, device='cuda')
+    got = mg.ops.linear_wgrad_bf16(g16, x16, out_features=12, in_features=60)
+    assert got.shape == (12, 60) and not got.any()
+
+
 def test_linear_golden(mg, golden):
     g = golden('linear')
     for case in ['readme_l1', 'rnn_in', 'out187', 'out1']:
@@ -760,7 +808,9 @@ def test_nn_linear_module_forward_backward(mg):
     for a, b in zip(ours, ref_linears):
         scale = b.weight.grad.abs().max().item()
         assert (a.weight.grad - b.weight.grad).abs().max().item() <= 5e-2 * scale + 1e-4
-    # the input gradient of the 512-wide layer went through the tcgen05 kernel, the narrower ones through the library GEMM
+        assert (a.bias.grad - b.bias.grad).abs().max().item() <= 5e-2 * b.bias.grad.abs().max().item() + 1e-4
+    # weight gradients: tcgen05 (MN-major operands); the input gradient of the 512-wide layer too, the narrower ones
+    # through the library GEMM
     assert (xo.grad - xr.grad).abs().max().item() <= 5e-2 * xr.grad.abs().max().item() + 1e-6
     # the bf16 shadow follows parameter updates
     before = ours[0].weight_bf16().clone()
