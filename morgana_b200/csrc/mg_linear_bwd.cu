@@ -28,14 +28,14 @@ namespace {
 // K7g: activation backward + bf16 cast + bias gradient
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kActThreads = 256;
-constexpr int kActRowsPerCta = 512;    // rows of one CTA: long enough to amortise the column-sum finish, short enough to fill the GPU
+constexpr int kActMinRowsPerCta = 128; // rows of one CTA at least; the grid is one wave of 3 CTAs per SM when there are enough rows
 
 struct ActGradParams {
   const void* grad_y;     // (M, N) fp32 or bf16, row stride ldg
   const void* y;          // (M, N) fp32 or bf16 forward output (sigmoid), or NULL: g = grad_y
   __nv_bfloat16* out;     // (M, ld_out) bf16, columns >= N zero
   double* partial;        // (n_ctas, ld_out) column sums of this CTA's rows, or NULL
-  int64_t ldg, ldy, ld_out, M;
+  int64_t ldg, ldy, ld_out, M, rows_per_cta;
   int N, grad_is_bf16, y_is_bf16;
 };
 
@@ -46,7 +46,43 @@ __device__ __forceinline__ float load_elem(const void* base, int64_t idx, int is
 // Thread t owns the 8-column group t % G of rows t / G, t / G + R, ... (G = ld_out / 8 groups per row, R = rows per pass):
 // always the same columns, so the bias gradient is 8 per-thread accumulators.
 template <bool VEC>
-__global__ void __launch_bounds__(kActThreads)
+__device__ __forceinline__ void act_grad_load(const ActGradParams& prm, int64_t r, int c0, float (&g)[8], float (&yv)[8]) {
+  if (VEC) {   // fp32 operands, rows 16-byte aligned, N a multiple of 8: two float4 per operand
+    const float4* gp = reinterpret_cast<const float4*>(static_cast<const float*>(prm.grad_y) + r * prm.ldg + c0);
+    const float4 a = mg_ld_stream_f4(gp), b = mg_ld_stream_f4(gp + 1);
+    g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
+    if (prm.y != nullptr) {
+      const float4* yp = reinterpret_cast<const float4*>(static_cast<const float*>(prm.y) + r * prm.ldy + c0);
+      const float4 ya = mg_ld_stream_f4(yp), yb = mg_ld_stream_f4(yp + 1);
+      yv[0] = ya.x; yv[1] = ya.y; yv[2] = ya.z; yv[3] = ya.w; yv[4] = yb.x; yv[5] = yb.y; yv[6] = yb.z; yv[7] = yb.w;
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      g[j] = 0.f;
+      yv[j] = 0.f;
+      if (c0 + j < prm.N) {
+        g[j] = load_elem(prm.grad_y, r * prm.ldg + c0 + j, prm.grad_is_bf16);
+        if (prm.y != nullptr) yv[j] = load_elem(prm.y, r * prm.ldy + c0 + j, prm.y_is_bf16);
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ void act_grad_finish_row(const ActGradParams& prm, int64_t r, int c0, float (&g)[8], const float (&yv)[8],
+                                                    double (&acc)[8]) {
+  if (prm.y != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) g[j] = __fmul_rn(__fmul_rn(g[j], __fsub_rn(1.f, yv[j])), yv[j]);   // ATen sigmoid_backward: grad * (1 - y) * y
+  }
+  __align__(16) __nv_bfloat16 v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { v[j] = __float2bfloat16_rn(g[j]); acc[j] += static_cast<double>(g[j]); }
+  *reinterpret_cast<uint4*>(prm.out + r * prm.ld_out + c0) = *reinterpret_cast<const uint4*>(v);
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kActThreads, 3)
 act_grad_kernel(const ActGradParams prm) {
   __shared__ double s_sum[kActThreads][9];   // padded: the finish reads a column of it
   const int G = static_cast<int>(prm.ld_out / 8);
@@ -55,42 +91,24 @@ act_grad_kernel(const ActGradParams prm) {
   const int grp = tid % G, lane_row = tid / G;
   const bool active = lane_row < R;
   const int c0 = grp * 8;
-  const int64_t r_begin = static_cast<int64_t>(blockIdx.x) * kActRowsPerCta;
-  const int64_t r_end = min(prm.M, r_begin + kActRowsPerCta);
+  const int64_t r_begin = static_cast<int64_t>(blockIdx.x) * prm.rows_per_cta;
+  const int64_t r_end = min(prm.M, r_begin + prm.rows_per_cta);
   double acc[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) acc[j] = 0.;
   if (active) {
-    for (int64_t r = r_begin + lane_row; r < r_end; r += R) {
-      float g[8];
-      if (VEC) {   // fp32 operands, rows 16-byte aligned, N a multiple of 8: two float4 per operand
-        const float4* gp = reinterpret_cast<const float4*>(static_cast<const float*>(prm.grad_y) + r * prm.ldg + c0);
-        const float4 a = mg_ld_stream_f4(gp), b = mg_ld_stream_f4(gp + 1);
-        g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
-        if (prm.y != nullptr) {
-          const float4* yp = reinterpret_cast<const float4*>(static_cast<const float*>(prm.y) + r * prm.ldy + c0);
-          const float4 ya = mg_ld_stream_f4(yp), yb = mg_ld_stream_f4(yp + 1);
-          const float yv[8] = {ya.x, ya.y, ya.z, ya.w, yb.x, yb.y, yb.z, yb.w};
-#pragma unroll
-          for (int j = 0; j < 8; ++j) g[j] = __fmul_rn(__fmul_rn(g[j], __fsub_rn(1.f, yv[j])), yv[j]);   // ATen sigmoid_backward: grad * (1 - y) * y
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          g[j] = 0.f;
-          if (c0 + j < prm.N) {
-            g[j] = load_elem(prm.grad_y, r * prm.ldg + c0 + j, prm.grad_is_bf16);
-            if (prm.y != nullptr) {
-              const float yv = load_elem(prm.y, r * prm.ldy + c0 + j, prm.y_is_bf16);
-              g[j] = __fmul_rn(__fmul_rn(g[j], __fsub_rn(1.f, yv)), yv);
-            }
-          }
-        }
-      }
-      __align__(16) __nv_bfloat16 v[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) { v[j] = __float2bfloat16_rn(g[j]); acc[j] += static_cast<double>(g[j]); }
-      *reinterpret_cast<uint4*>(prm.out + r * prm.ld_out + c0) = *reinterpret_cast<const uint4*>(v);
+    int64_t r = r_begin + lane_row;
+    for (; r + R < r_end; r += 2 * R) {       // two rows in flight per thread (128 bytes of loads with a sigmoid)
+      float g0[8], y0[8], g1[8], y1[8];
+      act_grad_load<VEC>(prm, r, c0, g0, y0);
+      act_grad_load<VEC>(prm, r + R, c0, g1, y1);
+      act_grad_finish_row(prm, r, c0, g0, y0, acc);
+      act_grad_finish_row(prm, r + R, c0, g1, y1, acc);
+    }
+    if (r < r_end) {
+      float g0[8], y0[8];
+      act_grad_load<VEC>(prm, r, c0, g0, y0);
+      act_grad_finish_row(prm, r, c0, g0, y0, acc);
     }
   }
   if (prm.partial == nullptr) return;
@@ -150,6 +168,11 @@ __device__ __forceinline__ uint64_t umma_smem_desc_mn(uint32_t smem_addr) {
   return desc;
 }
 
+// PAIR: the two CTAs of a cluster (one TPC) share a 256 x tile_k accumulator: each loads its own 128 out_features of g and HALF
+// of the x tile, the leader issues tcgen05.mma.cta_group::2 (M = 256), each CTA's tensor memory receives its own 128 rows.
+// Per output element a third less crosses L2 -> shared memory, which is what bounds the single-CTA form at 600 -> 512
+// (12 tiles x 48 KB per 64 frames = 3.1 GB in 0.255 ms: the chip's ~12 TB/s L2 limit).
+template <bool PAIR>
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_constant__ CUtensorMap map_x,
                      const __grid_constant__ WgradParams prm) {
@@ -158,13 +181,18 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
   __shared__ uint32_t s_tmem_base;
   unsigned char* ring = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = blockIdx.x % (prm.n_tiles * prm.k_tiles), split = blockIdx.x / (prm.n_tiles * prm.k_tiles);
-  const int n0 = (tile / prm.k_tiles) * kWgTileN, k0 = (tile % prm.k_tiles) * prm.tile_k;
+  const int cta_rank = PAIR ? static_cast<int>(cluster_ctarank()) : 0;
+  const bool leader = cta_rank == 0;
+  const int unit = PAIR ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);   // (tile, frame slice) of this CTA / pair
+  const int tile = unit % (prm.n_tiles * prm.k_tiles), split = unit / (prm.n_tiles * prm.k_tiles);
+  constexpr int kRows = PAIR ? 2 * kWgTileN : kWgTileN;        // out_features of one (pair-)tile
+  const int n0 = (tile / prm.k_tiles) * kRows + cta_rank * kWgTileN, k0 = (tile % prm.k_tiles) * prm.tile_k;
   const int fb_begin = split * prm.blocks_per_split;
   const int fb_end = min(prm.n_fblocks, fb_begin + prm.blocks_per_split);
   const int n_blocks = fb_end - fb_begin;       // >= 1 by construction of the grid
   const int kStages = prm.n_stages;
-  const int k_boxes = prm.tile_k / kWgAtom;
+  const int k_boxes = prm.tile_k / kWgAtom / (PAIR ? 2 : 1);   // boxes of x this CTA loads per stage
+  const int k_load0 = k0 + cta_rank * k_boxes * kWgAtom;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
@@ -174,32 +202,45 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
     mg_mbar_fence_init();
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mg_smem_addr(&s_tmem_base)), "n"(kWgTmemCols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mg_smem_addr(&s_tmem_base)), "n"(kWgTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mg_smem_addr(&s_tmem_base)), "n"(kWgTmemCols) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
+  if (PAIR) cluster_sync_all(); else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = s_tmem_base;
 
   if (warp == 0) {
-    if (lane == 0) {   // ===== TMA producer: per stage 2 boxes of g (128 out_features) and tile_k / 64 boxes of x
+    if (lane == 0) {   // ===== TMA producer: per stage 2 boxes of g (this CTA's 128 out_features) and its boxes of x
       const uint32_t stage_tx = static_cast<uint32_t>(2 + k_boxes) * kWgBoxBytes;
       for (int it = 0; it < n_blocks; ++it) {
         const int s = it % kStages;
         if (it >= kStages) mg_mbar_wait(&s_empty[s], static_cast<uint32_t>(((it / kStages) - 1) & 1));
         unsigned char* a_tile = ring + static_cast<size_t>(s) * prm.stage_bytes;
         const int f0 = (fb_begin + it) * kWgFrames;
-        mg_mbar_expect_tx(&s_full[s], stage_tx);
-        tma_load_2d(a_tile, &map_g, n0, f0, &s_full[s]);
-        tma_load_2d(a_tile + kWgBoxBytes, &map_g, n0 + kWgAtom, f0, &s_full[s]);
-        for (int j = 0; j < k_boxes; ++j)
-          tma_load_2d(a_tile + (2 + j) * kWgBoxBytes, &map_x, k0 + j * kWgAtom, f0, &s_full[s]);
+        if (PAIR) {
+          if (leader) mg_mbar_expect_tx(&s_full[s], 2 * stage_tx);     // both CTAs' bytes are counted on the leader's barrier
+          tma_load_2d_pair(a_tile, &map_g, n0, f0, &s_full[s]);
+          tma_load_2d_pair(a_tile + kWgBoxBytes, &map_g, n0 + kWgAtom, f0, &s_full[s]);
+          for (int j = 0; j < k_boxes; ++j)
+            tma_load_2d_pair(a_tile + (2 + j) * kWgBoxBytes, &map_x, k_load0 + j * kWgAtom, f0, &s_full[s]);
+        } else {
+          mg_mbar_expect_tx(&s_full[s], stage_tx);
+          tma_load_2d(a_tile, &map_g, n0, f0, &s_full[s]);
+          tma_load_2d(a_tile + kWgBoxBytes, &map_g, n0 + kWgAtom, f0, &s_full[s]);
+          for (int j = 0; j < k_boxes; ++j)
+            tma_load_2d(a_tile + (2 + j) * kWgBoxBytes, &map_x, k_load0 + j * kWgAtom, f0, &s_full[s]);
+        }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ===== MMA issuer: D[128 x tile_k] += g_tile^T (MN-major A) * x_tile (MN-major B), 16 frames per MMA
-      uint32_t idesc = umma_instr_desc(prm.tile_k, kWgTileN);
+    if (lane == 0 && leader) {   // ===== MMA issuer: D[rows x tile_k] += g_tile^T (MN-major A) * x_tile (MN-major B), 16 frames per MMA
+      uint32_t idesc = umma_instr_desc(prm.tile_k, kRows);
       idesc |= (1u << 15) | (1u << 16);         // A and B are MN-major
       for (int it = 0; it < n_blocks; ++it) {
         const int s = it % kStages;
@@ -208,11 +249,13 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
         const uint32_t a_addr = mg_smem_addr(ring + static_cast<size_t>(s) * prm.stage_bytes);
         const uint32_t b_addr = a_addr + 2 * kWgBoxBytes;
 #pragma unroll
-        for (int k = 0; k < kWgFrames / kUmmaK; ++k)   // 16 frames = two 8-frame groups = 2048 bytes further into every atom
-          umma_f16(tmem_base, umma_smem_desc_mn(a_addr + k * 2048), umma_smem_desc_mn(b_addr + k * 2048), idesc, (it | k) != 0 ? 1u : 0u);
-        umma_commit(&s_empty[s]);
+        for (int k = 0; k < kWgFrames / kUmmaK; ++k) {   // 16 frames = two 8-frame groups = 2048 bytes further into every atom
+          if (PAIR) umma_f16_pair(tmem_base, umma_smem_desc_mn(a_addr + k * 2048), umma_smem_desc_mn(b_addr + k * 2048), idesc, (it | k) != 0 ? 1u : 0u);
+          else umma_f16(tmem_base, umma_smem_desc_mn(a_addr + k * 2048), umma_smem_desc_mn(b_addr + k * 2048), idesc, (it | k) != 0 ? 1u : 0u);
+        }
+        if (PAIR) umma_commit_pair(&s_empty[s]); else umma_commit(&s_empty[s]);
       }
-      umma_commit(&s_acc_full);
+      if (PAIR) umma_commit_pair(&s_acc_full); else umma_commit(&s_acc_full);
     }
   } else {
     // ===== epilogue: warp w reads TMEM lanes 32 * (w % 4) ..; lane = out_feature row, 32 in_feature columns per load
@@ -221,7 +264,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
     mg_mbar_wait(&s_acc_full, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const int64_t ld = static_cast<int64_t>(prm.k_tiles) * prm.tile_k;
-    float* dst_row = prm.partial + (static_cast<int64_t>(split) * prm.n_tiles * kWgTileN + n0 + row) * ld + k0;
+    float* dst_row = prm.partial + (static_cast<int64_t>(split) * prm.n_tiles * kRows + n0 + row) * ld + k0;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
     for (int c0 = 0; c0 < prm.tile_k; c0 += 32) {
       uint32_t a[32];
@@ -234,8 +277,11 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
   }
 
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-  __syncthreads();
-  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kWgTmemCols) : "memory");
+  if (PAIR) cluster_sync_all(); else __syncthreads();
+  if (warp == 2) {
+    if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kWgTmemCols) : "memory");
+    else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kWgTmemCols) : "memory");
+  }
 }
 
 // dW[n, k] = sum over frame slices in slice order (fp32, as the tensor cores accumulate), one thread per element.
@@ -252,27 +298,39 @@ wgrad_finish_kernel(const float* __restrict__ partial, int splits, int64_t slice
 }
 
 struct WgradPlan {
-  int tile_k, n_tiles, k_tiles, splits, blocks_per_split, n_fblocks;
+  int tile_k, n_tiles, k_tiles, splits, blocks_per_split, n_fblocks, tile_rows;
+  bool pair;
   int64_t partial_elems;
 };
 
 WgradPlan plan_wgrad(int64_t M, int N, int K) {
   WgradPlan p;
   p.tile_k = K <= 64 ? 64 : (K <= 128 ? 128 : (K <= 192 ? 192 : 256));
-  p.n_tiles = (N + kWgTileN - 1) / kWgTileN;
+  // CTA pairs (256-row tiles) where there are at least two 128-row tiles to pair and the x tile splits into whole atoms
+  const int sms = mg_cached_sm_count();
+  p.pair = N > kWgTileN && p.tile_k % (2 * kWgAtom) == 0 && sms % 2 == 0;
+  { const char* e = getenv("MG_WGRAD_PAIR"); if (e) p.pair = atoi(e) != 0 && p.tile_k % (2 * kWgAtom) == 0 && sms % 2 == 0; }
+  p.tile_rows = p.pair ? 2 * kWgTileN : kWgTileN;
+  p.n_tiles = (N + p.tile_rows - 1) / p.tile_rows;
   p.k_tiles = (K + p.tile_k - 1) / p.tile_k;
   p.n_fblocks = static_cast<int>((M + kWgFrames - 1) / kWgFrames);
   const int tiles = p.n_tiles * p.k_tiles;
-  int splits = mg_cached_sm_count() / tiles;
+  int splits = (p.pair ? sms / 2 : sms) / tiles;
   if (splits < 1) splits = 1;
   if (splits > p.n_fblocks) splits = p.n_fblocks > 0 ? p.n_fblocks : 1;
   p.blocks_per_split = p.n_fblocks > 0 ? (p.n_fblocks + splits - 1) / splits : 1;
   p.splits = p.n_fblocks > 0 ? (p.n_fblocks + p.blocks_per_split - 1) / p.blocks_per_split : 1;
-  p.partial_elems = static_cast<int64_t>(p.splits) * p.n_tiles * kWgTileN * p.k_tiles * p.tile_k;
+  p.partial_elems = static_cast<int64_t>(p.splits) * p.n_tiles * p.tile_rows * p.k_tiles * p.tile_k;
   return p;
 }
 
-int act_grad_ctas(int64_t M) { return static_cast<int>((M + kActRowsPerCta - 1) / kActRowsPerCta); }
+// One resident wave: 3 CTAs per SM (<= 85 registers x 256 threads, two rows in flight per thread), each with an equal share of the rows.
+int64_t act_grad_rows_per_cta(int64_t M) {
+  const int64_t slots = static_cast<int64_t>(mg_cached_sm_count()) * 3;
+  int64_t rows = (M + slots - 1) / slots;
+  return rows < kActMinRowsPerCta ? kActMinRowsPerCta : rows;
+}
+int act_grad_ctas(int64_t M) { const int64_t rows = act_grad_rows_per_cta(M); return static_cast<int>((M + rows - 1) / rows); }
 
 }  // namespace
 
@@ -304,7 +362,7 @@ extern "C" int mg_act_grad_bf16(const void* grad_y, int grad_is_bf16, int64_t ld
   memset(&prm, 0, sizeof(prm));
   prm.grad_y = grad_y; prm.y = y; prm.out = static_cast<__nv_bfloat16*>(out);
   prm.partial = bias_grad != nullptr ? static_cast<double*>(workspace) : nullptr;
-  prm.ldg = ldg; prm.ldy = ldy; prm.ld_out = ld_out; prm.M = M; prm.N = N;
+  prm.ldg = ldg; prm.ldy = ldy; prm.ld_out = ld_out; prm.M = M; prm.N = N; prm.rows_per_cta = act_grad_rows_per_cta(M);
   prm.grad_is_bf16 = grad_is_bf16; prm.y_is_bf16 = y_is_bf16;
   const bool vec = !grad_is_bf16 && (y == nullptr || !y_is_bf16) && N % 8 == 0 && ldg % 4 == 0 && mg_aligned(grad_y, 16) &&
                    (y == nullptr || (ldy % 4 == 0 && mg_aligned(y, 16)));
@@ -353,7 +411,7 @@ extern "C" int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, i
   prm.partial = static_cast<float*>(workspace);
   prm.M = M; prm.N = N; prm.K = K; prm.tile_k = plan.tile_k; prm.n_tiles = plan.n_tiles; prm.k_tiles = plan.k_tiles;
   prm.splits = plan.splits; prm.blocks_per_split = plan.blocks_per_split; prm.n_fblocks = plan.n_fblocks;
-  prm.stage_bytes = static_cast<uint32_t>(2 + plan.tile_k / kWgAtom) * kWgBoxBytes;     // a multiple of 8 KB
+  prm.stage_bytes = static_cast<uint32_t>(2 + plan.tile_k / kWgAtom / (plan.pair ? 2 : 1)) * kWgBoxBytes;     // a multiple of 8 KB
   prm.n_stages = static_cast<int>(kWgRingBytes / prm.stage_bytes);
   if (prm.n_stages > kWgMaxStages) prm.n_stages = kWgMaxStages;
 
@@ -361,13 +419,31 @@ extern "C" int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, i
   int device = 0;
   MG_CUDA_OK(cudaGetDevice(&device));
   if (!attr_done[device & 63]) {
-    MG_CUDA_OK(cudaFuncSetAttribute(wgrad_tcgen05_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWgSmem)));
+    MG_CUDA_OK(cudaFuncSetAttribute(wgrad_tcgen05_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWgSmem)));
+    MG_CUDA_OK(cudaFuncSetAttribute(wgrad_tcgen05_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kWgSmem)));
     attr_done[device & 63] = true;
   }
-  const unsigned grid = static_cast<unsigned>(plan.splits * plan.n_tiles * plan.k_tiles);
-  wgrad_tcgen05_kernel<<<grid, kWgThreads, kWgSmem, stream>>>(map_g, map_x, prm);
+  const unsigned units = static_cast<unsigned>(plan.splits * plan.n_tiles * plan.k_tiles);
+  if (plan.pair) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * units);
+    cfg.blockDim = dim3(kWgThreads);
+    cfg.dynamicSmemBytes = kWgSmem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MG_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_tcgen05_kernel<true>, map_g, map_x, prm));
+  } else {
+    wgrad_tcgen05_kernel<false><<<units, kWgThreads, kWgSmem, stream>>>(map_g, map_x, prm);
+  }
   MG_LAUNCH_OK();
-  const int64_t slice = static_cast<int64_t>(plan.n_tiles) * kWgTileN * plan.k_tiles * plan.tile_k;
+  const int64_t slice = static_cast<int64_t>(plan.n_tiles) * plan.tile_rows * plan.k_tiles * plan.tile_k;
   const int64_t elems = static_cast<int64_t>(N) * K;
   wgrad_finish_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, stream>>>(
       prm.partial, plan.splits, slice, static_cast<int64_t>(plan.k_tiles) * plan.tile_k, N, K, grad_w, ldw);

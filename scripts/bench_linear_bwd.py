@@ -1,5 +1,5 @@
 """K7 backward against what autograd runs today: sigmoid backward + cast + bias sum (ATen) and the cuBLAS bf16 wgrad GEMM."""
-import sys, torch
+import os, sys, torch
 sys.path.insert(0, '.')
 import morgana_b200 as mg
 def timeit(fn, n_iter=20):
@@ -21,6 +21,11 @@ for (K, N, act) in [(600, 512, 'sigmoid'), (512, 128, 'sigmoid'), (128, 32, 'sig
         return g.to(torch.bfloat16), g.sum(0)
     t_act_ref = timeit(aten_act)
     g16, _ = mg.ops.act_grad_bf16(grad, y)
+    os.environ['MG_WGRAD_PAIR'] = '0'
+    t_w1 = timeit(lambda: mg.ops.linear_wgrad_bf16(g16, x16, out_features=N, in_features=K))
+    os.environ['MG_WGRAD_PAIR'] = '1'
+    t_w2 = timeit(lambda: mg.ops.linear_wgrad_bf16(g16, x16, out_features=N, in_features=K))
+    del os.environ['MG_WGRAD_PAIR']
     t_w = timeit(lambda: mg.ops.linear_wgrad_bf16(g16, x16, out_features=N, in_features=K))
     gT = g16[:, :N]
     t_w_ref = timeit(lambda: torch.matmul(gT.t(), x16).float())
@@ -28,5 +33,5 @@ for (K, N, act) in [(600, 512, 'sigmoid'), (512, 128, 'sigmoid'), (128, 32, 'sig
     flops = 2.0 * M * N * K
     act_bytes = M * N * (4 + (4 if act else 0) + 2)
     w_bytes = M * (g16.shape[1] + K) * 2
-    print('M=%d K=%d N=%d act=%s | K7g %.3f ms (%.2f TB/s) vs ATen %.3f ms | K7w %.3f ms (%.0f TF/s, %.2f TB/s) vs cuBLAS bf16 %.3f ms | max diff vs fp32 matmul %.3g'
-          % (M, K, N, act, t_act, act_bytes / t_act / 1e9, t_act_ref, t_w, flops / t_w / 1e9, w_bytes / t_w / 1e9, t_w_ref, err))
+    print('M=%d K=%d N=%d act=%s | K7g %.3f ms (%.2f TB/s) vs ATen %.3f ms | K7w %.3f ms (single %.3f, pair %.3f; %.0f TF/s, %.2f TB/s) vs cuBLAS bf16 %.3f ms | max diff vs fp32 matmul %.3g'
+          % (M, K, N, act, t_act, act_bytes / t_act / 1e9, t_act_ref, t_w, t_w1, t_w2, flops / t_w / 1e9, w_bytes / t_w / 1e9, t_w_ref, err))
