@@ -208,7 +208,7 @@ def test_interleaved_calls_with_changing_shapes(mg, seed):
     rmse_sum = rmse_count = 0.
     obj_sum = obj_count = 0.
     for step in range(60):
-        op = rng.integers(0, 14)
+        op = rng.integers(0, 15)
         B, T = int(rng.integers(1, 70)), int(rng.integers(1, 130))
         n = rng.integers(1, T + 1, B)
         if op == 0:      # K1 + K2, fused normalisation
@@ -338,12 +338,49 @@ def test_interleaved_calls_with_changing_shapes(mg, seed):
             assert np.array_equal(normed.cpu().numpy(), O.normalise_minmax(x, lo, hi)), step
             fused = mg.utils.upsample_to_repetitions(dev(x), dev(dur), normaliser=('minmax', dev(lo), dev(hi)))
             assert torch.equal(fused, mg.utils.upsample_to_repetitions(normed, dev(dur))), step
+        elif op == 13:   # K7 backward: activation gradient + bias gradient (K7g), weight gradient as single CTAs / pairs (K7w)
+            os.environ['MG_WGRAD_PAIR'] = str(int(rng.integers(0, 2)))
+            M, K, N = int(rng.integers(1, 3000)), int(rng.choice([8, 40, 64, 256, 600])), int(rng.choice([1, 3, 32, 187, 300, 512]))
+            grad_y = rng.standard_normal((M, N)).astype(np.float32)
+            y = rng.random((M, N), dtype=np.float32) if rng.integers(0, 2) else None
+            x16 = ops.cast_pad_bf16(dev(rng.random((M, K), dtype=np.float32)))
+            g16, bias_grad = ops.act_grad_bf16(dev(grad_y), None if y is None else dev(y))
+            g32 = grad_y if y is None else O.sigmoid_grad(grad_y, y)
+            assert torch.equal(g16[:, :N].cpu().view(torch.int16), torch.from_numpy(g32).to(torch.bfloat16).view(torch.int16)), step
+            np.testing.assert_allclose(bias_grad.cpu().numpy(), g32.astype(np.float64).sum(0), rtol=1e-6, atol=1e-6 * np.abs(g32).sum(0).max())
+            got = ops.linear_wgrad_bf16(g16, x16, out_features=N, in_features=K)
+            want = O.linear_wgrad(g16[:, :N].float().cpu().numpy(), x16[:, :K].float().cpu().numpy())
+            np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-4, atol=1e-4 * max(1.0, np.abs(want).max()))
+            del os.environ['MG_WGRAD_PAIR']
         else:            # K3
             D = int(rng.choice([1, 9, 187, 600]))
             x = rng.standard_normal((B, T, D)).astype(np.float32)
             mean, std = rng.standard_normal(D).astype(np.float32), (rng.random(D) + 0.1).astype(np.float32)
             assert np.array_equal(mg.data.normalise_mvn(dev(x), dev(mean), dev(std)).cpu().numpy(), O.normalise_mvn(x, mean, std)), step
             assert np.array_equal(mg.data.denormalise_mvn(dev(x), dev(mean), dev(std)).cpu().numpy(), O.denormalise_mvn(x, mean, std)), step
+
+
+@pytest.mark.parametrize('pair', ['0', '1'])
+def test_linear_backward_full_size_is_exact_on_integers(mg, monkeypatch, pair):
+    """K7g / K7w at the config-2 frame count (348,928 frames, 600 -> 512): with one-hot gradient rows and small integer
+    features every product and every partial sum is an integer below 2**24, so bf16 operands, fp32 accumulation in tensor
+    memory and the split reduction must reproduce the integer result exactly -- any dropped, duplicated or misplaced frame,
+    feature atom or slice shows up as a wrong integer."""
+    from morgana_b200 import ops
+    monkeypatch.setenv('MG_WGRAD_PAIR', pair)
+    M, N, K = 256 * 1363, 512, 600
+    g = torch.Generator(device='cuda').manual_seed(5)
+    x_int = torch.randint(0, 256, (M, K), generator=g, device='cuda')
+    hot = torch.randint(0, N, (M,), generator=g, device='cuda')
+    grad_y = torch.zeros((M, N), device='cuda')
+    grad_y[torch.arange(M, device='cuda'), hot] = 3.
+    g16, bias_grad = ops.act_grad_bf16(grad_y, None)
+    assert torch.equal(g16.float(), grad_y)
+    assert torch.equal(bias_grad, 3. * torch.bincount(hot, minlength=N).float())
+    got = ops.linear_wgrad_bf16(g16, x_int.to(torch.bfloat16), out_features=N, in_features=K)
+    want = torch.zeros((N, K), dtype=torch.int64, device='cuda').index_add_(0, hot, 3 * x_int)
+    assert int(want.max()) < 2 ** 24
+    assert torch.equal(got.to(torch.int64), want) and torch.equal(got, want.float())
 
 
 def test_path_replays_from_a_cuda_graph_on_a_side_stream(mg):
