@@ -18,6 +18,8 @@ _lib.define('normalise(Tensor x, Tensor p0, Tensor p1, str kind, bool inverse) -
 _lib.define('masked_loss(Tensor predictions, Tensor targets, Tensor? seq_len, str kind) -> Tensor')
 _lib.define('ema_update(Tensor(a!)[] shadow, Tensor[] params, float one_minus_decay) -> ()')
 _lib.define('linear_bf16(Tensor x, Tensor weight, Tensor? bias, str act, bool bf16_out) -> Tensor')
+_lib.define('act_grad_bf16(Tensor grad_y, Tensor? y) -> (Tensor, Tensor)')
+_lib.define('linear_wgrad_bf16(Tensor g, Tensor x, int out_features, int in_features) -> Tensor')
 _lib.define('mlpg(Tensor means, Tensor variances, int padding_size, Tensor? seq_len) -> Tensor')
 
 
@@ -51,13 +53,23 @@ def _linear_bf16(x, weight, bias, act, bf16_out):
                            out_dtype=torch.bfloat16 if bf16_out else torch.float32)
 
 
+def _act_grad_bf16(grad_y, y):
+    return ops.act_grad_bf16(grad_y, y)
+
+
+def _linear_wgrad_bf16(g, x, out_features, in_features):
+    return ops.linear_wgrad_bf16(g, x, out_features=out_features, in_features=in_features)
+
+
 def _mlpg(means, variances, padding_size, seq_len):
     return ops.mlpg(means, variances, padding_size=padding_size, seq_len=seq_len)
 
 
 for _name, _fn in [('dur_scan', _dur_scan), ('upsample_norm', _upsample_norm), ('pad_collate', _pad_collate),
                    ('normalise', _normalise), ('masked_loss', _masked_loss), ('ema_update', _ema_update),
-                   ('linear_bf16', _linear_bf16), ('mlpg', _mlpg)]:
+                   ('linear_bf16', _linear_bf16), ('act_grad_bf16', _act_grad_bf16),
+                   ('linear_wgrad_bf16', _linear_wgrad_bf16), ('mlpg', _mlpg)]:
     _lib.impl(_name, _fn, 'CUDA')
 
-OPERATORS = ('dur_scan', 'upsample_norm', 'pad_collate', 'normalise', 'masked_loss', 'ema_update', 'linear_bf16', 'mlpg')
+OPERATORS = ('dur_scan', 'upsample_norm', 'pad_collate', 'normalise', 'masked_loss', 'ema_update', 'linear_bf16',
+             'act_grad_bf16', 'linear_wgrad_bf16', 'mlpg')

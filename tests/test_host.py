@@ -56,6 +56,9 @@ def test_sass_uses_bulk_copy_engine(mg):
     sass = subprocess.run([cuobjdump, '-sass', _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert 'sm_100a' in sass
     assert 'UBLKCP' in sass
+    # the dense layers run on the 5th-generation tensor cores, forward and weight gradient, single CTAs and CTA pairs
+    for mnemonic in ('UTCHMMA', 'UTCHMMA.2CTA', 'UTMALDG.2D', 'LDTM'):
+        assert mnemonic in sass, mnemonic
 
 
 def test_no_cpu_path(mg):
