@@ -10,7 +10,7 @@
 //                             values in the same pass (fp64 per-thread partials, fixed-order finish).  HBM-bound: every
 //                             grad_y / y element is read once, 2 bytes written.
 //   K7w  wgrad_tcgen05_kernel dW[n, k] = sum_m g[m, n] * x[m, k].  The reduction runs over FRAMES, so both operands are
-//                             "MN-major" in tensor-core terms: a TMA box of 64 frames x 64 features (128-byte swizzle) IS
+//                             "MN-major" in tensor-core terms: a TMA box of 128 frames x 64 features (128-byte swizzle) IS
 //                             the canonical MN-major tile -- 8-frame groups 1024 bytes apart (stride byte offset), 64-feature
 //                             atoms one box apart (leading byte offset) -- so neither tensor is transposed in memory.
 //                             The output is tiny (N x K <= 512 x 640) and the reduction is ~10^5 long: the frames are split
@@ -45,17 +45,31 @@ __device__ __forceinline__ float load_elem(const void* base, int64_t idx, int is
 
 // Thread t owns the 8-column group t % G of rows t / G, t / G + R, ... (G = ld_out / 8 groups per row, R = rows per pass):
 // always the same columns, so the bias gradient is 8 per-thread accumulators.
+// 8 consecutive elements of a row as floats: two 16-byte loads of fp32 or one of bf16 (read-once data: no L1 allocation).
+__device__ __forceinline__ void load8(const void* base, int64_t idx, int is_bf16, float (&v)[8]) {
+  if (is_bf16) {
+    uint4 raw;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(raw.x), "=r"(raw.y), "=r"(raw.z), "=r"(raw.w)
+                 : "l"(static_cast<const __nv_bfloat16*>(base) + idx));
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {   // bf16 -> fp32 is a 16-bit shift
+      v[2 * j] = __uint_as_float(w[j] << 16);
+      v[2 * j + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+    }
+  } else {
+    const float4* p = reinterpret_cast<const float4*>(static_cast<const float*>(base) + idx);
+    const float4 a = mg_ld_stream_f4(p), b = mg_ld_stream_f4(p + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  }
+}
+
 template <bool VEC>
 __device__ __forceinline__ void act_grad_load(const ActGradParams& prm, int64_t r, int c0, float (&g)[8], float (&yv)[8]) {
-  if (VEC) {   // fp32 operands, rows 16-byte aligned, N a multiple of 8: two float4 per operand
-    const float4* gp = reinterpret_cast<const float4*>(static_cast<const float*>(prm.grad_y) + r * prm.ldg + c0);
-    const float4 a = mg_ld_stream_f4(gp), b = mg_ld_stream_f4(gp + 1);
-    g[0] = a.x; g[1] = a.y; g[2] = a.z; g[3] = a.w; g[4] = b.x; g[5] = b.y; g[6] = b.z; g[7] = b.w;
-    if (prm.y != nullptr) {
-      const float4* yp = reinterpret_cast<const float4*>(static_cast<const float*>(prm.y) + r * prm.ldy + c0);
-      const float4 ya = mg_ld_stream_f4(yp), yb = mg_ld_stream_f4(yp + 1);
-      yv[0] = ya.x; yv[1] = ya.y; yv[2] = ya.z; yv[3] = ya.w; yv[4] = yb.x; yv[5] = yb.y; yv[6] = yb.z; yv[7] = yb.w;
-    }
+  if (VEC) {   // rows 16-byte aligned in both operands, N a multiple of 8
+    load8(prm.grad_y, r * prm.ldg + c0, prm.grad_is_bf16, g);
+    if (prm.y != nullptr) load8(prm.y, r * prm.ldy + c0, prm.y_is_bf16, yv);
   } else {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -123,16 +137,23 @@ act_grad_kernel(const ActGradParams prm) {
   }
 }
 
-// bias_grad[c] = sum over CTAs in index order (fp64), rounded once.
+// bias_grad[c] = sum of the per-CTA column sums (fp64), rounded once.  Block = 32 columns x 8 lanes: lane l adds CTAs l, l + 8, ...
+// in order (a warp reads 32 consecutive doubles), the 8 lane sums are added in lane order.
 __global__ void __launch_bounds__(256)
 bias_grad_finish_kernel(const double* __restrict__ partial, int n_ctas, int64_t ld, int N, float* __restrict__ bias_grad) {
-  // a warp per column: lanes take CTAs lane, lane + 32, ... in order, then a fixed shuffle tree
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= N) return;
+  __shared__ double s_part[8][33];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), l = threadIdx.x >> 5;
   double s = 0.;
-  for (int i = lane; i < n_ctas; i += 32) s += partial[static_cast<int64_t>(i) * ld + warp];
-  s = mg_warp_sum(s);
-  if (lane == 0) bias_grad[warp] = static_cast<float>(s);
+  if (col < N)
+    for (int i = l; i < n_ctas; i += 8) s += partial[static_cast<int64_t>(i) * ld + col];
+  s_part[l][threadIdx.x & 31] = s;
+  __syncthreads();
+  if (l == 0 && col < N) {
+    double t = 0.;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) t += s_part[j][threadIdx.x];
+    bias_grad[col] = static_cast<float>(t);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -140,9 +161,8 @@ bias_grad_finish_kernel(const double* __restrict__ partial, int n_ctas, int64_t 
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kWgTileN = 128;             // output rows (out_features) of one accumulator = TMEM lanes
 constexpr int kWgMaxTileK = 256;          // output columns (in_features) of one accumulator = N of the MMA
-constexpr int kWgFrames = 64;             // frames per shared-memory stage (4 MMAs of 16)
+constexpr int kWgFrames = 128;            // frames per shared-memory stage (8 MMAs of 16 per barrier round trip; 64: 0.231 vs 0.214 ms at 512 x 600); MG_WGRAD_FRAMES=64
 constexpr int kWgAtom = 64;               // features per TMA box / swizzle atom (128 bytes of bf16)
-constexpr uint32_t kWgBoxBytes = kWgFrames * kWgAtom * 2;            // 8 KB
 constexpr int kWgMaxStages = 6;
 constexpr uint32_t kWgRingBytes = 192 * 1024;
 constexpr int kWgThreads = 192;           // TMA producer, MMA issuer, 4 epilogue warps
@@ -152,16 +172,16 @@ constexpr int kWgTmemCols = 256;
 struct WgradParams {
   float* partial;          // (splits, n_tiles * 128, k_tiles * tile_k) fp32
   int64_t M;
-  int N, K, tile_k, n_tiles, k_tiles, splits, blocks_per_split, n_fblocks, n_stages;
-  uint32_t stage_bytes;
+  int N, K, tile_k, n_tiles, k_tiles, splits, blocks_per_split, n_fblocks, n_stages, frames;
+  uint32_t stage_bytes, box_bytes;   // box = frames x 64 features of bf16
 };
 
-// MN-major operand tile, 128-byte swizzle: 64-feature atoms `kWgBoxBytes` apart (leading byte offset), 8-frame groups 1024 bytes
+// MN-major operand tile, 128-byte swizzle: 64-feature atoms one box apart (leading byte offset), 8-frame groups 1024 bytes
 // apart (stride byte offset).  cute/atom/mma_traits_sm100.hpp: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units.
-__device__ __forceinline__ uint64_t umma_smem_desc_mn(uint32_t smem_addr) {
+__device__ __forceinline__ uint64_t umma_smem_desc_mn(uint32_t smem_addr, uint32_t box_bytes) {
   uint64_t desc = 0;
   desc |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
-  desc |= static_cast<uint64_t>(kWgBoxBytes >> 4) << 16;
+  desc |= static_cast<uint64_t>(box_bytes >> 4) << 16;
   desc |= static_cast<uint64_t>(1024 >> 4) << 32;
   desc |= static_cast<uint64_t>(1) << 46;
   desc |= static_cast<uint64_t>(2) << 61;
@@ -193,6 +213,7 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
   const int kStages = prm.n_stages;
   const int k_boxes = prm.tile_k / kWgAtom / (PAIR ? 2 : 1);   // boxes of x this CTA loads per stage
   const int k_load0 = k0 + cta_rank * k_boxes * kWgAtom;
+  const uint32_t kBox = prm.box_bytes;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_g) : "memory");
@@ -217,24 +238,24 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
 
   if (warp == 0) {
     if (lane == 0) {   // ===== TMA producer: per stage 2 boxes of g (this CTA's 128 out_features) and its boxes of x
-      const uint32_t stage_tx = static_cast<uint32_t>(2 + k_boxes) * kWgBoxBytes;
+      const uint32_t stage_tx = static_cast<uint32_t>(2 + k_boxes) * kBox;
       for (int it = 0; it < n_blocks; ++it) {
         const int s = it % kStages;
         if (it >= kStages) mg_mbar_wait(&s_empty[s], static_cast<uint32_t>(((it / kStages) - 1) & 1));
         unsigned char* a_tile = ring + static_cast<size_t>(s) * prm.stage_bytes;
-        const int f0 = (fb_begin + it) * kWgFrames;
+        const int f0 = (fb_begin + it) * prm.frames;
         if (PAIR) {
           if (leader) mg_mbar_expect_tx(&s_full[s], 2 * stage_tx);     // both CTAs' bytes are counted on the leader's barrier
           tma_load_2d_pair(a_tile, &map_g, n0, f0, &s_full[s]);
-          tma_load_2d_pair(a_tile + kWgBoxBytes, &map_g, n0 + kWgAtom, f0, &s_full[s]);
+          tma_load_2d_pair(a_tile + kBox, &map_g, n0 + kWgAtom, f0, &s_full[s]);
           for (int j = 0; j < k_boxes; ++j)
-            tma_load_2d_pair(a_tile + (2 + j) * kWgBoxBytes, &map_x, k_load0 + j * kWgAtom, f0, &s_full[s]);
+            tma_load_2d_pair(a_tile + (2 + j) * kBox, &map_x, k_load0 + j * kWgAtom, f0, &s_full[s]);
         } else {
           mg_mbar_expect_tx(&s_full[s], stage_tx);
           tma_load_2d(a_tile, &map_g, n0, f0, &s_full[s]);
-          tma_load_2d(a_tile + kWgBoxBytes, &map_g, n0 + kWgAtom, f0, &s_full[s]);
+          tma_load_2d(a_tile + kBox, &map_g, n0 + kWgAtom, f0, &s_full[s]);
           for (int j = 0; j < k_boxes; ++j)
-            tma_load_2d(a_tile + (2 + j) * kWgBoxBytes, &map_x, k_load0 + j * kWgAtom, f0, &s_full[s]);
+            tma_load_2d(a_tile + (2 + j) * kBox, &map_x, k_load0 + j * kWgAtom, f0, &s_full[s]);
         }
       }
     }
@@ -247,11 +268,10 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
         mg_mbar_wait(&s_full[s], static_cast<uint32_t>((it / kStages) & 1));
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t a_addr = mg_smem_addr(ring + static_cast<size_t>(s) * prm.stage_bytes);
-        const uint32_t b_addr = a_addr + 2 * kWgBoxBytes;
-#pragma unroll
-        for (int k = 0; k < kWgFrames / kUmmaK; ++k) {   // 16 frames = two 8-frame groups = 2048 bytes further into every atom
-          if (PAIR) umma_f16_pair(tmem_base, umma_smem_desc_mn(a_addr + k * 2048), umma_smem_desc_mn(b_addr + k * 2048), idesc, (it | k) != 0 ? 1u : 0u);
-          else umma_f16(tmem_base, umma_smem_desc_mn(a_addr + k * 2048), umma_smem_desc_mn(b_addr + k * 2048), idesc, (it | k) != 0 ? 1u : 0u);
+        const uint32_t b_addr = a_addr + 2 * kBox;
+        for (int k = 0; k < prm.frames / kUmmaK; ++k) {   // 16 frames = two 8-frame groups = 2048 bytes further into every atom
+          if (PAIR) umma_f16_pair(tmem_base, umma_smem_desc_mn(a_addr + k * 2048, kBox), umma_smem_desc_mn(b_addr + k * 2048, kBox), idesc, (it | k) != 0 ? 1u : 0u);
+          else umma_f16(tmem_base, umma_smem_desc_mn(a_addr + k * 2048, kBox), umma_smem_desc_mn(b_addr + k * 2048, kBox), idesc, (it | k) != 0 ? 1u : 0u);
         }
         if (PAIR) umma_commit_pair(&s_empty[s]); else umma_commit(&s_empty[s]);
       }
@@ -284,21 +304,75 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
   }
 }
 
-// dW[n, k] = sum over frame slices in slice order (fp32, as the tensor cores accumulate), one thread per element.
+// dW[n, k] = sum over frame slices in slice order (fp32, as the tensor cores accumulate).  One thread per 4 consecutive k
+// (the slices' rows are 16-byte aligned; the output row only when ldw % 4 == 0), four slices' loads in flight, added in order.
 __global__ void __launch_bounds__(256)
 wgrad_finish_kernel(const float* __restrict__ partial, int splits, int64_t slice_elems, int64_t ld, int N, int K,
-                    float* __restrict__ grad_w, int64_t ldw) {
+                    float* __restrict__ grad_w, int64_t ldw, int vec_out) {
+  const int groups = (K + 3) / 4;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= static_cast<int64_t>(N) * K) return;
-  const int n = static_cast<int>(idx / K), k = static_cast<int>(idx - static_cast<int64_t>(n) * K);
-  const float* p = partial + static_cast<int64_t>(n) * ld + k;
-  float s = 0.f;
-  for (int i = 0; i < splits; ++i) s = __fadd_rn(s, __ldg(p + i * slice_elems));
-  grad_w[static_cast<int64_t>(n) * ldw + k] = s;
+  if (idx >= static_cast<int64_t>(N) * groups) return;
+  const int n = static_cast<int>(idx / groups), k = static_cast<int>(idx - static_cast<int64_t>(n) * groups) * 4;
+  const float4* p = reinterpret_cast<const float4*>(partial + static_cast<int64_t>(n) * ld + k);   // ld >= round_up(K, 64)
+  const int64_t step = slice_elems / 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  int i = 0;
+  for (; i + 4 <= splits; i += 4) {
+    const float4 a = __ldcg(p + i * step), b = __ldcg(p + (i + 1) * step), c = __ldcg(p + (i + 2) * step), d = __ldcg(p + (i + 3) * step);
+    s.x = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s.x, a.x), b.x), c.x), d.x);
+    s.y = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s.y, a.y), b.y), c.y), d.y);
+    s.z = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s.z, a.z), b.z), c.z), d.z);
+    s.w = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(s.w, a.w), b.w), c.w), d.w);
+  }
+  for (; i < splits; ++i) {
+    const float4 a = __ldcg(p + i * step);
+    s.x = __fadd_rn(s.x, a.x); s.y = __fadd_rn(s.y, a.y); s.z = __fadd_rn(s.z, a.z); s.w = __fadd_rn(s.w, a.w);
+  }
+  float* out = grad_w + static_cast<int64_t>(n) * ldw + k;
+  if (vec_out && k + 4 <= K) {
+    *reinterpret_cast<float4*>(out) = s;
+  } else {
+    const float v[4] = {s.x, s.y, s.z, s.w};
+    for (int j = 0; j < 4 && k + j < K; ++j) out[j] = v[j];
+  }
+}
+
+// The same sum for many slices (small layers: one or two tiles, up to #SMs slices): a warp per output group, lane l adds slices
+// l, l + 32, ... in order, then a fixed shuffle tree -- the chain per thread is splits / 32 loads instead of splits.
+__global__ void __launch_bounds__(256)
+wgrad_finish_warp_kernel(const float* __restrict__ partial, int splits, int64_t slice_elems, int64_t ld, int N, int K,
+                         float* __restrict__ grad_w, int64_t ldw, int vec_out) {
+  const int groups = (K + 3) / 4;
+  const int64_t idx = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (idx >= static_cast<int64_t>(N) * groups) return;      // whole warps leave together
+  const int n = static_cast<int>(idx / groups), k = static_cast<int>(idx - static_cast<int64_t>(n) * groups) * 4;
+  const float4* p = reinterpret_cast<const float4*>(partial + static_cast<int64_t>(n) * ld + k);
+  const int64_t step = slice_elems / 4;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = lane; i < splits; i += 32) {
+    const float4 a = __ldcg(p + i * step);
+    s.x = __fadd_rn(s.x, a.x); s.y = __fadd_rn(s.y, a.y); s.z = __fadd_rn(s.z, a.z); s.w = __fadd_rn(s.w, a.w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    s.x = __fadd_rn(s.x, __shfl_xor_sync(MG_FULL_MASK, s.x, o));
+    s.y = __fadd_rn(s.y, __shfl_xor_sync(MG_FULL_MASK, s.y, o));
+    s.z = __fadd_rn(s.z, __shfl_xor_sync(MG_FULL_MASK, s.z, o));
+    s.w = __fadd_rn(s.w, __shfl_xor_sync(MG_FULL_MASK, s.w, o));
+  }
+  if (lane != 0) return;
+  float* out = grad_w + static_cast<int64_t>(n) * ldw + k;
+  if (vec_out && k + 4 <= K) {
+    *reinterpret_cast<float4*>(out) = s;
+  } else {
+    const float v[4] = {s.x, s.y, s.z, s.w};
+    for (int j = 0; j < 4 && k + j < K; ++j) out[j] = v[j];
+  }
 }
 
 struct WgradPlan {
-  int tile_k, n_tiles, k_tiles, splits, blocks_per_split, n_fblocks, tile_rows;
+  int tile_k, n_tiles, k_tiles, splits, blocks_per_split, n_fblocks, tile_rows, frames;
   bool pair;
   int64_t partial_elems;
 };
@@ -306,6 +380,7 @@ struct WgradPlan {
 WgradPlan plan_wgrad(int64_t M, int N, int K) {
   WgradPlan p;
   p.tile_k = K <= 64 ? 64 : (K <= 128 ? 128 : (K <= 192 ? 192 : 256));
+  { const char* e = getenv("MG_WGRAD_TILE_K"); if (e && (atoi(e) == 64 || atoi(e) == 128 || atoi(e) == 192 || atoi(e) == 256) && atoi(e) < p.tile_k) p.tile_k = atoi(e); }
   // CTA pairs (256-row tiles) where there are at least two 128-row tiles to pair and the x tile splits into whole atoms
   const int sms = mg_cached_sm_count();
   p.pair = N > kWgTileN && p.tile_k % (2 * kWgAtom) == 0 && sms % 2 == 0;
@@ -313,7 +388,9 @@ WgradPlan plan_wgrad(int64_t M, int N, int K) {
   p.tile_rows = p.pair ? 2 * kWgTileN : kWgTileN;
   p.n_tiles = (N + p.tile_rows - 1) / p.tile_rows;
   p.k_tiles = (K + p.tile_k - 1) / p.tile_k;
-  p.n_fblocks = static_cast<int>((M + kWgFrames - 1) / kWgFrames);
+  p.frames = kWgFrames;
+  { const char* e = getenv("MG_WGRAD_FRAMES"); if (e && atoi(e) == 64) p.frames = 64; }
+  p.n_fblocks = static_cast<int>((M + p.frames - 1) / p.frames);
   const int tiles = p.n_tiles * p.k_tiles;
   int splits = (p.pair ? sms / 2 : sms) / tiles;
   if (splits < 1) splits = 1;
@@ -364,14 +441,14 @@ extern "C" int mg_act_grad_bf16(const void* grad_y, int grad_is_bf16, int64_t ld
   prm.partial = bias_grad != nullptr ? static_cast<double*>(workspace) : nullptr;
   prm.ldg = ldg; prm.ldy = ldy; prm.ld_out = ld_out; prm.M = M; prm.N = N; prm.rows_per_cta = act_grad_rows_per_cta(M);
   prm.grad_is_bf16 = grad_is_bf16; prm.y_is_bf16 = y_is_bf16;
-  const bool vec = !grad_is_bf16 && (y == nullptr || !y_is_bf16) && N % 8 == 0 && ldg % 4 == 0 && mg_aligned(grad_y, 16) &&
-                   (y == nullptr || (ldy % 4 == 0 && mg_aligned(y, 16)));
+  // 16-byte row segments in both operands: strides of 4 fp32 / 8 bf16 elements
+  const bool vec = N % 8 == 0 && ldg % (grad_is_bf16 ? 8 : 4) == 0 && mg_aligned(grad_y, 16) &&
+                   (y == nullptr || (ldy % (y_is_bf16 ? 8 : 4) == 0 && mg_aligned(y, 16)));
   if (vec) act_grad_kernel<true><<<n_ctas, kActThreads, 0, stream>>>(prm);
   else act_grad_kernel<false><<<n_ctas, kActThreads, 0, stream>>>(prm);
   MG_LAUNCH_OK();
   if (bias_grad != nullptr) {
-    const int warps_per_cta = 256 / 32;
-    bias_grad_finish_kernel<<<(N + warps_per_cta - 1) / warps_per_cta, 256, 0, stream>>>(prm.partial, n_ctas, ld_out, N, bias_grad);
+    bias_grad_finish_kernel<<<(N + 31) / 32, 256, 0, stream>>>(prm.partial, n_ctas, ld_out, N, bias_grad);
     MG_LAUNCH_OK();
   }
   return MG_OK;
@@ -386,7 +463,7 @@ extern "C" int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, i
                                     int64_t M, int N, int K, void* workspace, int64_t workspace_bytes, mg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "mg_linear_wgrad_bf16: bad shape (M=%lld, N=%d, K=%d)", static_cast<long long>(M), N, K);
-  MG_REQUIRE(M < (int64_t(1) << 31) - kWgFrames, "mg_linear_wgrad_bf16: too many frames");
+  MG_REQUIRE(M < (int64_t(1) << 31) - 128, "mg_linear_wgrad_bf16: too many frames");
   MG_REQUIRE(grad_w != nullptr && ldw >= K, "mg_linear_wgrad_bf16: bad output");
   if (M == 0) {
     MG_CUDA_OK(cudaMemset2DAsync(grad_w, ldw * sizeof(float), 0, K * sizeof(float), N, stream));
@@ -401,9 +478,9 @@ extern "C" int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, i
              "mg_linear_wgrad_bf16: workspace of %lld bytes needed", static_cast<long long>(plan.partial_elems * sizeof(float)));
 
   CUtensorMap map_g, map_x;
-  int rc = make_map(&map_g, g, M, N, ldg, kWgAtom, kWgFrames, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  int rc = make_map(&map_g, g, M, N, ldg, kWgAtom, plan.frames, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   if (rc != MG_OK) return rc;
-  rc = make_map(&map_x, x, M, K, ldx, kWgAtom, kWgFrames, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
+  rc = make_map(&map_x, x, M, K, ldx, kWgAtom, plan.frames, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2);
   if (rc != MG_OK) return rc;
 
   WgradParams prm;
@@ -411,7 +488,9 @@ extern "C" int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, i
   prm.partial = static_cast<float*>(workspace);
   prm.M = M; prm.N = N; prm.K = K; prm.tile_k = plan.tile_k; prm.n_tiles = plan.n_tiles; prm.k_tiles = plan.k_tiles;
   prm.splits = plan.splits; prm.blocks_per_split = plan.blocks_per_split; prm.n_fblocks = plan.n_fblocks;
-  prm.stage_bytes = static_cast<uint32_t>(2 + plan.tile_k / kWgAtom / (plan.pair ? 2 : 1)) * kWgBoxBytes;     // a multiple of 8 KB
+  prm.frames = plan.frames;
+  prm.box_bytes = static_cast<uint32_t>(plan.frames) * kWgAtom * 2;
+  prm.stage_bytes = static_cast<uint32_t>(2 + plan.tile_k / kWgAtom / (plan.pair ? 2 : 1)) * prm.box_bytes;     // a multiple of 8 KB
   prm.n_stages = static_cast<int>(kWgRingBytes / prm.stage_bytes);
   if (prm.n_stages > kWgMaxStages) prm.n_stages = kWgMaxStages;
 
@@ -444,9 +523,15 @@ extern "C" int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, i
   }
   MG_LAUNCH_OK();
   const int64_t slice = static_cast<int64_t>(plan.n_tiles) * plan.tile_rows * plan.k_tiles * plan.tile_k;
-  const int64_t elems = static_cast<int64_t>(N) * K;
-  wgrad_finish_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, stream>>>(
-      prm.partial, plan.splits, slice, static_cast<int64_t>(plan.k_tiles) * plan.tile_k, N, K, grad_w, ldw);
+  const int64_t elems = static_cast<int64_t>(N) * ((K + 3) / 4);
+  const int vec_out = (ldw % 4 == 0 && mg_aligned(grad_w, 16)) ? 1 : 0;
+  const int64_t ld_partial = static_cast<int64_t>(plan.k_tiles) * plan.tile_k;
+  if (plan.splits > 16)
+    wgrad_finish_warp_kernel<<<static_cast<unsigned>((elems * 32 + 255) / 256), 256, 0, stream>>>(
+        prm.partial, plan.splits, slice, ld_partial, N, K, grad_w, ldw, vec_out);
+  else
+    wgrad_finish_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, stream>>>(
+        prm.partial, plan.splits, slice, ld_partial, N, K, grad_w, ldw, vec_out);
   MG_LAUNCH_OK();
   return MG_OK;
 }

@@ -706,12 +706,14 @@ def test_act_grad_bf16_vs_oracle(mg, M, N, act, dtype):
 
 @pytest.mark.parametrize('M,N,K', [(70, 64, 600), (33, 48, 609), (45, 187, 256), (19, 1, 32), (5000, 512, 600), (257, 256, 512),
                                    (128, 32, 128), (5, 16, 8), (4097, 199, 640), (20001, 128, 512), (1, 3, 64), (9000, 130, 130)])
-@pytest.mark.parametrize('pair', [None, '0', '1'])
-def test_linear_wgrad_tcgen05_vs_oracle(mg, monkeypatch, M, N, K, pair):
+@pytest.mark.parametrize('pair,frames', [(None, None), ('0', None), ('1', None), ('1', '64'), ('0', '64')])
+def test_linear_wgrad_tcgen05_vs_oracle(mg, monkeypatch, M, N, K, pair, frames):
     """K7w: g^T @ x over the frame axis with MN-major tcgen05 operands, as single CTAs and as CTA pairs (cta_group::2).  Against the fp64 product of the same bf16 operands
     only the fp32 accumulation differs: 1e-4 of the largest entry; and the split reduction has a fixed order (same bits twice)."""
     if pair is not None:
         monkeypatch.setenv('MG_WGRAD_PAIR', pair)
+    if frames is not None:
+        monkeypatch.setenv('MG_WGRAD_FRAMES', frames)
     rng = np.random.default_rng(M + N + K)
     g = torch.from_numpy(rng.standard_normal((M, N)).astype(np.float32))
     x = torch.from_numpy(rng.random((M, K), dtype=np.float32))
