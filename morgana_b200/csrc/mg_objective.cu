@@ -168,7 +168,8 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
   __shared__ unsigned s_special[32];          // per 32 columns: which need general_one()
   __shared__ int s_cap_col[kMaxCapture];      // columns copied to the side buffer during the stream
   __shared__ int s_sp_col[kMaxSpecial];       // special columns served from the side buffer
-  __shared__ short s_sp_mask[kSpecialInfo], s_sp_width[kSpecialInfo];   // per special column, by ballot position
+  constexpr int kInfo = MAXT <= 256 ? 256 : kSpecialInfo;   // ballot positions in use: D rounded up to a warp
+  __shared__ short s_sp_mask[kInfo], s_sp_width[kInfo];   // per special column, by ballot position
   __shared__ int s_n_cap, s_n_sp, s_n_special;
   __shared__ bool s_is_last;
 
@@ -237,7 +238,7 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
     if (lane == 0) s_special[c0 >> 5] = bits;
     if (special) {   // at most a handful of columns: park (mask column, root-group width) by position in the ballot word
       const int slot = (c0 >> 5) * 32 + __popc(bits & ((1u << lane) - 1));
-      if (slot < kSpecialInfo) { s_sp_mask[slot] = col.mask_col; s_sp_width[slot] = col.metric_kind == MG_RED_ROOT_SQDIFF ? col.width : 1; }
+      if (slot < kInfo) { s_sp_mask[slot] = col.mask_col; s_sp_width[slot] = col.metric_kind == MG_RED_ROOT_SQDIFF ? col.width : 1; }
     }
   }
   __syncthreads();
@@ -257,7 +258,7 @@ masked_objective_kernel(const __grid_constant__ ObjectiveParams prm) {
         todo &= todo - 1;
         const int info = w * 32 + rank_in_word++;
         ++n_special;
-        if (n_sp == kMaxSpecial || info >= kSpecialInfo) continue;
+        if (n_sp == kMaxSpecial || info >= kInfo) continue;
         const int mask_col = s_sp_mask[info], width = s_sp_width[info];
         const int saved = n_cap;
         bool ok = capture(k) >= 0 && (mask_col == MG_COL_NONE || capture(mask_col) >= 0);
