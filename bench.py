@@ -12,7 +12,8 @@ U{1..30}, 600-dim labels; SURVEY.md section 8d, seed 1234):
 
 `value` is whole-job valid frames/s with inputs resident in HBM (CUDA events, max over ranks); `e2e` is the same metric
 through the public Python API from pinned HOST buffers with the host<->device copies inside the timed region;
-`roofline` describes the dominant kernel (K2) from CUDA events around its launches inside the timed region;
+`roofline` describes the dominant kernel (K2) from CUDA events around its launches inside the timed region
+(`roofline_k4b`: the same for the step's other kernel);
 `cpu_baseline` / `--impl reference` time the reference's own op chain (oracle/aten_chain.py) on the host cores.
 Prints exactly one JSON line on rank 0.
 """
@@ -268,10 +269,18 @@ def run_ours(args, rank, world, local_rank):
         else:
             out, n_frames = mg.utils.upsample_to_repetitions(batch['lab'], batch['dur'], normaliser=normaliser,
                                                              max_len=batch['T'], return_lengths=True)
-        loss, grad = objective(batch['pred'], batch['target'], n_frames)
+        if time_k2 is not None:   # K4b (+ the 2 us fill of its result records) between its own pair of events
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            o0.record(stream)
+            loss, grad = objective(batch['pred'], batch['target'], n_frames)
+            o1.record(stream)
+            k4b_events.append((o0, o1))
+        else:
+            loss, grad = objective(batch['pred'], batch['target'], n_frames)
         return out, loss, grad
 
     pending = []
+    k4b_events = []
 
     def exchange():
         """The path's one collective: SUM of the packed loss / metric-sum records over ranks (NCCL over NVLink).  It is
@@ -298,6 +307,7 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- timed region: exactly K steps, device-resident inputs ---------------------------------------------------------
     k2_events = []
+    del k4b_events[:]
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     frames_done = 0
     barrier()
@@ -321,6 +331,10 @@ def run_ours(args, rank, world, local_rank):
         hb = host_batches[i % N_ROTATING_BATCHES]
         k2_bytes.append(4 * 600 * (args.batch_size * hb['T'] + hb['n_phones']) + 4 * args.batch_size * hb['P'] + 8 * 600)
     k2_avg_bytes = sum(k2_bytes) / len(k2_bytes)
+    k4b_avg_ms = sum(a.elapsed_time(b) for a, b in k4b_events) / len(k4b_events)
+    k4b_avg_bytes = sum(4 * 187 * (2 * host_batches[i % N_ROTATING_BATCHES]['frames'] +
+                                   args.batch_size * host_batches[i % N_ROTATING_BATCHES]['T'])
+                        for i in range(args.steps)) / args.steps   # valid rows of pred + target read, the whole gradient written
 
     # ---- end-to-end: the public API from pinned host buffers, copies inside the timed region ------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 30)
@@ -418,6 +432,12 @@ def run_ours(args, rank, world, local_rank):
                      'frac_of_8000_nominal': achieved / 8000.0, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk_src,
                      'algorithmic_bytes_per_launch': k2_avg_bytes, 'avg_launch_ms': k2_avg_ms,
                      'share_of_step': k2_avg_ms / (elapsed_ms / args.steps)},
+        # the step's other kernel, for the record (same method: CUDA events on the launching stream, algorithmic bytes)
+        'roofline_k4b': {'bound': 'hbm', 'kernel': 'masked_objective_kernel<GRAD> (K4b: 3 x mse + bce + gradient + 4 metrics)',
+                         'achieved': k4b_avg_bytes / (k4b_avg_ms * 1e-3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                         'frac': k4b_avg_bytes / (k4b_avg_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
+                         'algorithmic_bytes_per_launch': k4b_avg_bytes, 'avg_launch_ms': k4b_avg_ms,
+                         'share_of_step': k4b_avg_ms / (elapsed_ms / args.steps)},
     }
     if world == 1 and not args.no_cpu_baseline:
         sample, frames = make_cpu_sample(args.batch_size, CPU_SAMPLE_UTTS)
