@@ -352,6 +352,67 @@ upsample_bwd_kernel(const float* __restrict__ grad_out, const int32_t* __restric
   }
 }
 
+// Row-streaming form for rows of up to 32 * NS float4 (D <= 640 at NS = 5): a lane owns the NS vectors lane, lane + 32, ... of
+// EVERY row, so a warp reads whole contiguous rows (2400 bytes at D = 600) with two rows -- 2 * NS 16-byte loads per lane -- in
+// flight, instead of walking the item's rows once per 512-byte column strip.  Same ascending-t order per element: same bits.
+template <int MODE, int NS>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+upsample_bwd_rows_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ ends, const float* __restrict__ p0,
+                         const float* __restrict__ p1, int64_t p_sb, float* __restrict__ grad_x, int64_t n_items_total,
+                         int P, int nvec, int64_t T) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * kBwdWarps + (threadIdx.x >> 5);
+  if (w >= n_items_total) return;
+  const int b = static_cast<int>(w / P), p = static_cast<int>(w % P);
+  const int32_t* e = ends + static_cast<int64_t>(b) * P;
+  const int64_t start = p > 0 ? static_cast<int64_t>(__ldg(e + p - 1)) : 0;
+  const int64_t stop = static_cast<int64_t>(__ldg(e + p));
+  const float4* g = reinterpret_cast<const float4*>(grad_out) + static_cast<int64_t>(b) * T * nvec;
+  float4 acc[NS];
+#pragma unroll
+  for (int s = 0; s < NS; ++s) acc[s] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto add = [](float4& a, const float4& v) {
+    a.x = __fadd_rn(a.x, v.x); a.y = __fadd_rn(a.y, v.y); a.z = __fadd_rn(a.z, v.z); a.w = __fadd_rn(a.w, v.w);
+  };
+  int64_t t = start;
+  for (; t + 2 <= stop; t += 2) {
+    float4 v0[NS], v1[NS];
+    const float4* r0 = g + t * nvec;
+    const float4* r1 = r0 + nvec;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const int i = lane + 32 * s;
+      if (i < nvec) { v0[s] = __ldcs(r0 + i); v1[s] = __ldcs(r1 + i); }
+    }
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (lane + 32 * s < nvec) { add(acc[s], v0[s]); add(acc[s], v1[s]); }
+  }
+  if (t < stop) {
+    const float4* r0 = g + t * nvec;
+#pragma unroll
+    for (int s = 0; s < NS; ++s)
+      if (lane + 32 * s < nvec) add(acc[s], __ldcs(r0 + lane + 32 * s));
+  }
+  const float* q0 = p0 + static_cast<int64_t>(b) * p_sb;
+  const float* q1 = p1 + static_cast<int64_t>(b) * p_sb;
+  float4* gx = reinterpret_cast<float4*>(grad_x) + w * nvec;
+#pragma unroll
+  for (int s = 0; s < NS; ++s) {
+    const int i = lane + 32 * s;
+    if (i >= nvec) continue;
+    float4 o = acc[s];
+    if (MODE != MG_NORM_NONE) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(q0) + i), c = __ldg(reinterpret_cast<const float4*>(q1) + i);
+      o.x = __fdiv_rn(o.x, mg_denominator(MODE, a.x, c.x));
+      o.y = __fdiv_rn(o.y, mg_denominator(MODE, a.y, c.y));
+      o.z = __fdiv_rn(o.z, mg_denominator(MODE, a.z, c.z));
+      o.w = __fdiv_rn(o.w, mg_denominator(MODE, a.w, c.w));
+    }
+    gx[i] = o;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // Host side
 // ------------------------------------------------------------------------------------------------------------------
@@ -555,7 +616,28 @@ extern "C" int mg_upsample_norm_bwd_f32(const float* grad_out, const int32_t* en
 #define MG_BWD(VEC, MODE, NV)                                                                                   \
   upsample_bwd_kernel<VEC, MODE><<<grid, kBwdWarps * 32, 0, stream>>>(grad_out, ends, p0, p1, param_stride_b, \
                                                                        grad_x, n_items, P, NV, T)
-  if (vec4) {
+  static int rows_form = -1;   // MG_UPSAMPLE_BWD_ROWS=0: the column-strip kernel for every shape (measurements)
+  if (rows_form < 0) { const char* env = getenv("MG_UPSAMPLE_BWD_ROWS"); rows_form = env ? atoi(env) : 1; }
+  const bool params_vec = norm_mode == MG_NORM_NONE || (mg_aligned(p0, 16) && mg_aligned(p1, 16) && param_stride_b % 4 == 0);
+  if (vec4 && rows_form && D / 4 <= 160 && params_vec) {
+    const int nvec = D / 4, ns = (nvec + 31) / 32;
+#define MG_BWD_ROWS(MODE, NS)                                                                                        \
+  upsample_bwd_rows_kernel<MODE, NS><<<grid, kBwdWarps * 32, 0, stream>>>(grad_out, ends, p0, p1, param_stride_b, \
+                                                                           grad_x, n_items, P, nvec, T)
+#define MG_BWD_ROWS_MODE(NS)                                              \
+  do {                                                                    \
+    if (norm_mode == MG_NORM_NONE) MG_BWD_ROWS(MG_NORM_NONE, NS);         \
+    else if (norm_mode == MG_NORM_MVN) MG_BWD_ROWS(MG_NORM_MVN, NS);      \
+    else MG_BWD_ROWS(MG_NORM_MINMAX, NS);                                 \
+  } while (0)
+    if (ns == 1) MG_BWD_ROWS_MODE(1);
+    else if (ns == 2) MG_BWD_ROWS_MODE(2);
+    else if (ns == 3) MG_BWD_ROWS_MODE(3);
+    else if (ns == 4) MG_BWD_ROWS_MODE(4);
+    else MG_BWD_ROWS_MODE(5);
+#undef MG_BWD_ROWS_MODE
+#undef MG_BWD_ROWS
+  } else if (vec4) {
     if (norm_mode == MG_NORM_NONE) MG_BWD(float4, MG_NORM_NONE, D / 4);
     else if (norm_mode == MG_NORM_MVN) MG_BWD(float4, MG_NORM_MVN, D / 4);
     else MG_BWD(float4, MG_NORM_MINMAX, D / 4);
