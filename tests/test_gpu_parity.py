@@ -654,6 +654,35 @@ def test_fused_objective_matches_drop_in_composition(mg):
         assert rel_err(got.result(), float(want.result())) <= REL
 
 
+@pytest.mark.parametrize('lo,hi,width', [(4, 184, 187), (1, 60, 60), (3, 100, 101), (2, 9, 12), (0, 5, 9)])
+@pytest.mark.parametrize('mode', ['0', '1'])
+def test_wide_column_slices_stream_flat(mg, monkeypatch, lo, hi, width, mode):
+    """The slices LSTMAcousticModel.loss takes of one (B, T, 187) tensor (models/RNN_SPSS.py:133-135) and MelCepDistortion's
+    target[..., 1:] (metrics.py:690): at least half of the row -> the flat masked stream; same values as thread-per-column."""
+    monkeypatch.setenv('MG_RED_SLICE_MODE', mode)
+    rng = np.random.default_rng(lo + hi + width)
+    B, T = 7, 61
+    n = rng.integers(0, T + 1, B)
+    n[0], n[1] = T, 1
+    p = rng.standard_normal((B, T, width)).astype(np.float32)
+    y = rng.standard_normal((B, T, width)).astype(np.float32)
+    pd, yd = dev(p).requires_grad_(), dev(y)
+    for kind in ('mse', 'l1'):
+        n_pos = np.maximum(n, 1)
+        loss = getattr(mg.losses, kind)(pd[..., lo:hi], yd[..., lo:hi], dev(n_pos))
+        want = O.masked_loss(p[..., lo:hi], y[..., lo:hi], n_pos, kind)
+        assert abs(loss.item() - want) <= 1e-6 * abs(want)
+        grad, = torch.autograd.grad(loss, pd)
+        want_grad = np.zeros_like(p)
+        want_grad[..., lo:hi] = O.masked_loss_grad(p[..., lo:hi], y[..., lo:hi], n_pos, kind)
+        np.testing.assert_allclose(grad.cpu().numpy(), want_grad, rtol=3e-6, atol=1e-12)
+    rmse = mg.metrics.RMSE()
+    rmse.reset_state()
+    rmse.accumulate(yd[..., lo:hi], pd.detach()[..., lo:hi], seq_len=dev(n))
+    s_, c_ = O.rmse_acc(y[..., lo:hi], p[..., lo:hi], n)
+    assert float(rmse.count) == c_ and abs(float(rmse.sum) - s_) <= 2e-6 * s_
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # a14: dense layers on tcgen05 (bf16 operands, fp32 accumulate).  Tolerances: (1) against the fp64 product of the
 # bf16-ROUNDED operands only accumulation order and the sigmoid approximation differ: 2e-3 absolute on O(1) activations;
