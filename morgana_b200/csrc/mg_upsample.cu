@@ -356,7 +356,7 @@ upsample_bwd_kernel(const float* __restrict__ grad_out, const int32_t* __restric
 // EVERY row, so a warp reads whole contiguous rows (2400 bytes at D = 600) with two rows -- 2 * NS 16-byte loads per lane -- in
 // flight, instead of walking the item's rows once per 512-byte column strip.  Same ascending-t order per element: same bits.
 template <int MODE, int NS>
-__global__ void __launch_bounds__(kBwdWarps * 32)
+__global__ void __launch_bounds__(kBwdWarps * 32, 3)   // <= 85 registers: three CTAs per SM (86 registers gave two)
 upsample_bwd_rows_kernel(const float* __restrict__ grad_out, const int32_t* __restrict__ ends, const float* __restrict__ p0,
                          const float* __restrict__ p1, int64_t p_sb, float* __restrict__ grad_x, int64_t n_items_total,
                          int P, int nvec, int64_t T) {
