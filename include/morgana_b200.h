@@ -345,6 +345,10 @@ int mg_mlpg_f32(const float* means, int64_t m_sb, int64_t m_st, const float* var
                 const int64_t* seq_len, float* out, int64_t o_sb, int64_t o_st, int B, int64_t T, int feat_dim, int padding,
                 void* workspace, int64_t workspace_bytes, mg_stream_t stream);
 
+/* utils.both_voiced_mask (morgana/utils.py:169-172): out[i] = 1 when every feature is non-zero at i (~torch.eq(x, 0.), so NaN
+ * counts as voiced), else 0.  features: HOST array of n_features (<= 8) DEVICE pointers to contiguous fp32 tensors of n elements. */
+int mg_both_nonzero_u8(const float* const* features, int n_features, int64_t n, unsigned char* out, mg_stream_t stream);
+
 /* fp32 -> bf16 row conversion with K padding: feeds K7 from the fp32 frame-rate features and weights of the example models'
  * nn.Linear layers (README.rst:65-73, models/RNN_SPSS.py:33-41); pads K to ld_out with 0. */
 int mg_cast_pad_bf16(const float* x, int64_t ldx, void* out, int64_t ld_out, int64_t rows, int K, mg_stream_t stream);

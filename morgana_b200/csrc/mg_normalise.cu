@@ -128,3 +128,45 @@ extern "C" int mg_normalise_f32(const float* x, const float* p0, const float* p1
   }
   return launch<1>(x, p0, p1, norm_mode, inverse, out, 0, numel, D, rows_per_param, stream);
 }
+
+
+// ---- utils.both_voiced_mask (reference morgana/utils.py:169-172): out[i] = all_k (feature_k[i] != 0), one byte per element ----
+namespace {
+
+constexpr int kMaxVoicedFeatures = 8;
+struct VoicedParams {
+  const float* features[kMaxVoicedFeatures];
+  int n_features;
+  int64_t n;
+  unsigned char* out;
+};
+
+__global__ void __launch_bounds__(256)
+both_nonzero_kernel(const VoicedParams prm) {
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < prm.n;
+       i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    bool voiced = true;
+    for (int k = 0; k < prm.n_features; ++k) voiced = voiced && !(__ldg(prm.features[k] + i) == 0.f);   // ~torch.eq(x, 0.): NaN counts as voiced
+    prm.out[i] = voiced ? 1 : 0;
+  }
+}
+
+}  // namespace
+
+extern "C" int mg_both_nonzero_u8(const float* const* features, int n_features, int64_t n, unsigned char* out, mg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MG_REQUIRE(n_features >= 1 && n_features <= kMaxVoicedFeatures, "mg_both_nonzero_u8: %d features outside [1, %d]", n_features, kMaxVoicedFeatures);
+  MG_REQUIRE(n >= 0, "mg_both_nonzero_u8: negative size");
+  if (n == 0) return MG_OK;
+  MG_REQUIRE(features != nullptr && out != nullptr, "mg_both_nonzero_u8: NULL buffer");
+  VoicedParams prm;
+  prm.n_features = n_features; prm.n = n; prm.out = out;
+  for (int k = 0; k < kMaxVoicedFeatures; ++k) prm.features[k] = k < n_features ? features[k] : nullptr;
+  for (int k = 0; k < n_features; ++k) MG_REQUIRE(features[k] != nullptr, "mg_both_nonzero_u8: feature %d is NULL", k);
+  int64_t blocks = (n + 255) / 256;
+  const int64_t cap = static_cast<int64_t>(mg_cached_sm_count()) * 8;
+  if (blocks > cap) blocks = cap;
+  both_nonzero_kernel<<<static_cast<unsigned>(blocks), 256, 0, stream>>>(prm);
+  MG_LAUNCH_OK();
+  return MG_OK;
+}

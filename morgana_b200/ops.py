@@ -591,6 +591,26 @@ def ema_update(pairs, one_minus_decay, plan=None):
                                     _stream()), 'mg_ema_update_f32')
 
 
+def both_nonzero(features):
+    """uint8 tensor of the features' shape: 1 where every feature is non-zero (reference utils.py:169-172)."""
+    if not features:
+        raise RuntimeError('both_voiced_mask needs at least one sequence feature')     # torch.stack([]) raises too
+    if len(features) > 8:
+        raise NotImplementedError('both_voiced_mask takes at most 8 sequence features')
+    shape = features[0].shape
+    tensors = []
+    for f in features:
+        _require_cuda(f, 'sequence_feature')
+        if f.shape != shape:
+            raise RuntimeError('stack expects each tensor to be equal size, but got {} and {}'.format(list(shape), list(f.shape)))
+        tensors.append(f.to(torch.float32).contiguous())
+    out = torch.empty(shape, dtype=torch.uint8, device=features[0].device)
+    table = (ctypes.c_void_p * len(tensors))(*[t.data_ptr() for t in tensors])
+    with _device_of(out):
+        check(lib.mg_both_nonzero_u8(table, len(tensors), out.numel(), _ptr(out), _stream()), 'mg_both_nonzero_u8')
+    return out
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # K7: dense layers
 # ----------------------------------------------------------------------------------------------------------------------

@@ -48,6 +48,15 @@ def sequence_mask(seq_len, max_len=None, dtype=torch.ByteTensor, device=None):
     return mask[:, :, None].type(dtype)
 
 
+def both_voiced_mask(*sequence_features, dtype=torch.ByteTensor):
+    r"""Whether the sequence features are non-zero at the same time (reference ``utils.py:169-172``), computed on the device.
+
+    As in the reference the result is cast with ``.type(dtype)``: the default ``torch.ByteTensor`` is a CPU tensor type, so
+    the mask lands on the host exactly as the reference's does; pass ``torch.cuda.ByteTensor`` / ``torch.uint8`` to keep it
+    on the device."""
+    return ops.both_nonzero(list(sequence_features)).type(dtype)
+
+
 class ExponentialMovingAverage(object):
     """EMA of a model's trainable parameters, updated by one multi-tensor kernel (morgana/utils.py:421-456).
 

@@ -379,6 +379,14 @@ def ema_update(shadow, param, decay):
 # a14  nn.Linear (+ Sigmoid)  (README.rst:65-73, models/RNN_SPSS.py:33-41)
 # ----------------------------------------------------------------------------------------------------------------
 
+def both_voiced_mask(*sequence_features, dtype=np.uint8):
+    """``prod_k (feature_k != 0)`` cast to ``dtype`` (reference morgana/utils.py:169-172; NaN != 0 is True)."""
+    voiced = np.ones(np.asarray(sequence_features[0]).shape, dtype=bool)
+    for feature in sequence_features:
+        voiced &= ~(np.asarray(feature) == 0.)
+    return voiced.astype(dtype)
+
+
 def linear(x, weight, bias=None, act=None):
     """``y = x W^T + b`` with an optional sigmoid, carried in float64 (the GEMM parity target)."""
     y = np.asarray(x, np.float64) @ np.asarray(weight, np.float64).T

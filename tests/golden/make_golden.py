@@ -101,6 +101,24 @@ def sequence_mask_cases():
     return out
 
 
+def voiced_mask_cases():
+    """utils.both_voiced_mask (reference utils.py:169-172)."""
+    g = gen(77)
+    out = {}
+    a = torch.randn(5, 23, 1, generator=g)
+    b = torch.randn(5, 23, 1, generator=g)
+    c = torch.randn(5, 23, 1, generator=g)
+    a[torch.rand(5, 23, 1, generator=g) < 0.3] = 0.
+    b[torch.rand(5, 23, 1, generator=g) < 0.3] = 0.
+    c[torch.rand(5, 23, 1, generator=g) < 0.3] = 0.
+    a[0, 0, 0], b[0, 1, 0] = float('nan'), -0.
+    out['voiced_a'], out['voiced_b'], out['voiced_c'] = a.numpy(), b.numpy(), c.numpy()
+    out['voiced_mask_ab'] = utils.both_voiced_mask(a, b).numpy()
+    out['voiced_mask_abc_f32'] = utils.both_voiced_mask(a, b, c, dtype=torch.FloatTensor).numpy()
+    out['voiced_mask_a'] = utils.both_voiced_mask(a).numpy()
+    return out
+
+
 def normaliser_cases():
     out = {}
     g = gen(100)
@@ -440,6 +458,12 @@ def signature_cases():
 
 def main():
     import json
+    if '--only' in sys.argv:      # add one group without rewriting the other archives
+        name = sys.argv[sys.argv.index('--only') + 1]
+        arrays = {'voiced_mask': voiced_mask_cases}[name]()
+        np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
+        print('%-14s %4d arrays' % (name, len(arrays)))
+        return
     with open(os.path.join(HERE, 'signatures.json'), 'w') as f:
         json.dump(signature_cases(), f, indent=1, sort_keys=True)
     print('signatures.json written')
@@ -447,6 +471,7 @@ def main():
         'segments': segment_cases(),
         'upsample': upsample_cases(),
         'sequence_mask': sequence_mask_cases(),
+        'voiced_mask': voiced_mask_cases(),
         'normalise': normaliser_cases(),
         'losses': loss_cases(),
         'metrics': metric_cases(),

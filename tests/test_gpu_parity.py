@@ -654,6 +654,23 @@ def test_fused_objective_matches_drop_in_composition(mg):
         assert rel_err(got.result(), float(want.result())) <= REL
 
 
+def test_both_voiced_mask_golden(mg, golden):
+    """utils.both_voiced_mask against outputs of the reference (utils.py:169-172): NaN and -0. included, dtype argument kept."""
+    g = golden('voiced_mask')
+    a, b, c = dev(g['voiced_a']), dev(g['voiced_b']), dev(g['voiced_c'])
+    got = mg.utils.both_voiced_mask(a, b)
+    assert got.dtype == torch.uint8 and np.array_equal(got.cpu().numpy(), g['voiced_mask_ab'])
+    got = mg.utils.both_voiced_mask(a, b, c, dtype=torch.cuda.FloatTensor)
+    assert got.dtype == torch.float32 and np.array_equal(got.cpu().numpy(), g['voiced_mask_abc_f32'])
+    assert np.array_equal(mg.utils.both_voiced_mask(a).cpu().numpy(), g['voiced_mask_a'])
+    big = torch.randn(64, 1200, 1, device='cuda')
+    big[big.abs() < 0.3] = 0.
+    other = torch.randn(64, 1200, 1, device='cuda').round()
+    on_device = mg.utils.both_voiced_mask(big, other, dtype=torch.uint8)       # a dtype (not a CPU tensor type) keeps the device
+    assert on_device.is_cuda and torch.equal(on_device.bool(), (big != 0) & (other != 0))
+    assert not mg.utils.both_voiced_mask(big, other).is_cuda                 # the reference's default lands on the host
+
+
 @pytest.mark.parametrize('lo,hi,width', [(4, 184, 187), (1, 60, 60), (3, 100, 101), (2, 9, 12), (0, 5, 9)])
 @pytest.mark.parametrize('mode', ['0', '1'])
 def test_wide_column_slices_stream_flat(mg, monkeypatch, lo, hi, width, mode):

@@ -63,6 +63,14 @@ def test_sequence_mask(golden):
     assert np.array_equal(O.sequence_mask(seq_len, 4), g['mask_len4_u8'])
 
 
+def test_both_voiced_mask(golden):
+    g = golden('voiced_mask')
+    a, b, c = g['voiced_a'], g['voiced_b'], g['voiced_c']
+    assert np.array_equal(O.both_voiced_mask(a, b), g['voiced_mask_ab']) and O.both_voiced_mask(a, b).dtype == g['voiced_mask_ab'].dtype
+    assert np.array_equal(O.both_voiced_mask(a, b, c, dtype=np.float32), g['voiced_mask_abc_f32'])
+    assert np.array_equal(O.both_voiced_mask(a), g['voiced_mask_a'])
+
+
 @pytest.mark.parametrize('case', ['btd', 'td', 'btd187', 'sd'])
 def test_normalisers_bit_exact(golden, case):
     g = golden('normalise')
