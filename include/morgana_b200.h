@@ -345,6 +345,15 @@ int mg_mlpg_f32(const float* means, int64_t m_sb, int64_t m_st, const float* var
                 const int64_t* seq_len, float* out, int64_t o_sb, int64_t o_st, int B, int64_t T, int feat_dim, int padding,
                 void* workspace, int64_t workspace_bytes, mg_stream_t stream);
 
+/* losses.KLD_standard_normal (morgana/losses.py:64-67): loss = mean over rows of -0.5 * sum_d (1 + log_variance - mean^2 -
+ * exp(log_variance)), mean / log_variance contiguous (rows, latent_dim) fp32.  loss: one float on the device (or NULL).
+ * grad_mean / grad_log_variance: both NULL, or outputs of the operands' shape = d loss / d operand times *grad_scale_dev
+ * (NULL: 1).  workspace: mg_kld_workspace_bytes(rows * latent_dim) bytes, 8-byte aligned; fixed summation order. */
+int64_t mg_kld_workspace_bytes(int64_t n);
+int mg_kld_standard_normal_f32(const float* mean, const float* log_variance, int64_t rows, int latent_dim, float* loss,
+                               float* grad_mean, float* grad_log_variance, const float* grad_scale_dev, void* workspace,
+                               int64_t workspace_bytes, mg_stream_t stream);
+
 /* utils.both_voiced_mask (morgana/utils.py:169-172): out[i] = 1 when every feature is non-zero at i (~torch.eq(x, 0.), so NaN
  * counts as voiced), else 0.  features: HOST array of n_features (<= 8) DEVICE pointers to contiguous fp32 tensors of n elements. */
 int mg_both_nonzero_u8(const float* const* features, int n_features, int64_t n, unsigned char* out, mg_stream_t stream);

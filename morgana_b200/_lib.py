@@ -97,6 +97,9 @@ PROTOTYPES = {
     'mg_linear_wgrad_workspace_bytes': (c_i64, [c_i64, c_int, c_int]),
     'mg_linear_wgrad_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p, c_i64,
                                      c_void_p]),
+    'mg_kld_workspace_bytes': (c_i64, [c_i64]),
+    'mg_kld_standard_normal_f32': (c_int, [c_void_p, c_void_p, c_i64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_i64,
+                                           c_void_p]),
     'mg_both_nonzero_u8': (c_int, [ctypes.POINTER(c_void_p), c_int, c_i64, c_void_p, c_void_p]),
     'mg_cast_pad_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_void_p]),
 }

@@ -3,7 +3,7 @@
 ``mse(predictions, targets, seq_len=None)`` and ``bce(...)`` keep the reference's signature and semantics --
 ``mean over (batch, feature) of [ sum over valid frames / number of valid frames ]`` -- and return a 0-dim float32 tensor
 that supports ``.backward()``.  ``l1`` is the same wrapper around the absolute error; ``ce`` takes logits and class
-indices (``morgana/losses.py:59-61``).
+indices (``morgana/losses.py:59-61``); ``KLD_standard_normal`` is the unmasked latent-space term (``morgana/losses.py:64-67``).
 """
 from morgana_b200 import ops
 
@@ -27,3 +27,8 @@ def ce(predictions, targets, seq_len=None):
     """Masked cross-entropy of ``(batch_size, seq_len, n_classes)`` logits against ``(batch_size, seq_len)`` int64 class
     indices (morgana/losses.py:59-61: ``F.cross_entropy`` over the transposed logits, one value per frame)."""
     return ops.masked_loss(predictions, targets, seq_len, 'ce')
+
+
+def KLD_standard_normal(mean, log_variance):
+    r"""KL-divergence of :math:`\mathbb{N}` (`mean`, `log_variance`) with :math:`\mathbb{N}(0, 1)` (morgana/losses.py:64-67)."""
+    return ops.kld_standard_normal(mean, log_variance)

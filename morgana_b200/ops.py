@@ -550,6 +550,48 @@ def masked_loss(predictions, targets, seq_len=None, kind='mse'):
     return _MaskedLossFn.apply(predictions, targets, seq_len, _LOSS_KINDS[kind])
 
 
+class _KldFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, mean, log_variance):
+        rows, latent = mean.numel() // mean.shape[-1], mean.shape[-1]
+        loss = torch.empty((), dtype=torch.float32, device=mean.device)
+        ws = torch.empty((max(lib.mg_kld_workspace_bytes(mean.numel()), 8) // 8,), dtype=torch.float64, device=mean.device)
+        with _device_of(mean):
+            check(lib.mg_kld_standard_normal_f32(_ptr(mean), _ptr(log_variance), rows, latent, _ptr(loss), None, None, None,
+                                                 _ptr(ws), ws.numel() * 8, _stream()), 'mg_kld_standard_normal_f32')
+        ctx.save_for_backward(mean, log_variance)
+        ctx.set_materialize_grads(False)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        if grad_output is None:
+            return None, None
+        mean, log_variance = ctx.saved_tensors
+        rows, latent = mean.numel() // mean.shape[-1], mean.shape[-1]
+        grad_mean, grad_lv = torch.empty_like(mean), torch.empty_like(log_variance)
+        scale = grad_output.detach().to(torch.float32).contiguous()
+        ws = torch.empty((max(lib.mg_kld_workspace_bytes(mean.numel()), 8) // 8,), dtype=torch.float64, device=mean.device)
+        with _device_of(mean):
+            check(lib.mg_kld_standard_normal_f32(_ptr(mean), _ptr(log_variance), rows, latent, None, _ptr(grad_mean), _ptr(grad_lv),
+                                                 _ptr(scale), _ptr(ws), ws.numel() * 8, _stream()), 'mg_kld_standard_normal_f32')
+        return grad_mean, grad_lv
+
+
+def kld_standard_normal(mean, log_variance):
+    """``mean over rows of -0.5 * sum_d (1 + log_variance - mean**2 - exp(log_variance))`` (reference losses.py:64-67)."""
+    _require_cuda(mean, 'mean')
+    _require_cuda(log_variance, 'log_variance')
+    if mean.dtype != torch.float32 or log_variance.dtype != torch.float32:
+        raise TypeError('morgana_b200 losses take float32 tensors, got {} and {}'.format(mean.dtype, log_variance.dtype))
+    if mean.shape != log_variance.shape or mean.dim() < 1:
+        raise RuntimeError('mean and log_variance must share a (..., latent_dim) shape, got {} and {}'
+                           .format(tuple(mean.shape), tuple(log_variance.shape)))
+    if mean.numel() == 0:
+        return torch.full((), float('nan'), dtype=torch.float32, device=mean.device)      # torch.mean of nothing
+    return _KldFn.apply(mean.contiguous(), log_variance.contiguous())
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # K6: multi-tensor EMA
 # ----------------------------------------------------------------------------------------------------------------------

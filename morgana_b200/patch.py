@@ -37,8 +37,9 @@ def patch(morgana=None):
             _swap(morgana.utils, name, getattr(_utils, name))
     _swap(morgana.losses, 'mse', _losses.mse)
     _swap(morgana.losses, 'bce', _losses.bce)
-    if hasattr(morgana.losses, 'ce'):
-        _swap(morgana.losses, 'ce', _losses.ce)
+    for name in ('ce', 'KLD_standard_normal'):
+        if hasattr(morgana.losses, name):
+            _swap(morgana.losses, name, getattr(_losses, name))
     for name in ('normalise_mvn', 'denormalise_mvn', 'normalise_minmax', 'denormalise_minmax'):
         _swap(morgana.data, name, getattr(_data, name))
     if hasattr(morgana, 'viz') and hasattr(morgana.viz, 'synthesis'):

@@ -379,6 +379,15 @@ def ema_update(shadow, param, decay):
 # a14  nn.Linear (+ Sigmoid)  (README.rst:65-73, models/RNN_SPSS.py:33-41)
 # ----------------------------------------------------------------------------------------------------------------
 
+def kld_standard_normal(mean, log_variance):
+    """``mean over rows of -0.5 * sum_d (1 + lv - mean**2 - exp(lv))`` in float64, with its gradients w.r.t. both operands
+    (reference morgana/losses.py:64-67).  Returns ``(loss, grad_mean, grad_log_variance)``."""
+    m, lv = np.asarray(mean, np.float64), np.asarray(log_variance, np.float64)
+    rows = m.size // m.shape[-1]
+    loss = float((-0.5 * (1. + lv - m ** 2 - np.exp(lv)).sum(-1)).mean())
+    return loss, m / rows, 0.5 * (np.exp(lv) - 1.) / rows
+
+
 def both_voiced_mask(*sequence_features, dtype=np.uint8):
     """``prod_k (feature_k != 0)`` cast to ``dtype`` (reference morgana/utils.py:169-172; NaN != 0 is True)."""
     voiced = np.ones(np.asarray(sequence_features[0]).shape, dtype=bool)

@@ -119,6 +119,21 @@ def voiced_mask_cases():
     return out
 
 
+def kld_cases():
+    """losses.KLD_standard_normal (reference losses.py:64-67) with autograd gradients of both operands."""
+    g = gen(78)
+    out = {}
+    for tag, shape in (('2d', (32, 16)), ('3d', (4, 37, 5)), ('row', (1, 3))):
+        mean = torch.randn(*shape, generator=g).requires_grad_()
+        lv = (0.5 * torch.randn(*shape, generator=g)).requires_grad_()
+        loss = losses.KLD_standard_normal(mean, lv)
+        (0.25 * loss).backward()
+        out['kld_%s_mean' % tag], out['kld_%s_lv' % tag] = mean.detach().numpy(), lv.detach().numpy()
+        out['kld_%s_loss' % tag] = loss.detach().numpy()
+        out['kld_%s_grad_mean' % tag], out['kld_%s_grad_lv' % tag] = mean.grad.numpy(), lv.grad.numpy()
+    return out
+
+
 def normaliser_cases():
     out = {}
     g = gen(100)
@@ -419,8 +434,9 @@ def signature_cases():
     import inspect
     from morgana.viz import synthesis
     names = {
-        'utils': ['upsample_to_repetitions', 'sequence_mask', 'batched_masked_select', 'get_segment_ends', 'split_to_segments'],
-        'losses': ['mse', 'bce', 'ce'],
+        'utils': ['upsample_to_repetitions', 'sequence_mask', 'batched_masked_select', 'get_segment_ends', 'split_to_segments',
+                  'both_voiced_mask'],
+        'losses': ['mse', 'bce', 'ce', 'KLD_standard_normal'],
         'data': ['normalise_mvn', 'denormalise_mvn', 'normalise_minmax', 'denormalise_minmax'],
         'viz.synthesis': ['MLPG'],
     }
@@ -460,7 +476,12 @@ def main():
     import json
     if '--only' in sys.argv:      # add one group without rewriting the other archives
         name = sys.argv[sys.argv.index('--only') + 1]
-        arrays = {'voiced_mask': voiced_mask_cases}[name]()
+        if name == 'signatures':
+            with open(os.path.join(HERE, 'signatures.json'), 'w') as f:
+                json.dump(signature_cases(), f, indent=1, sort_keys=True)
+            print('signatures.json written')
+            return
+        arrays = {'voiced_mask': voiced_mask_cases, 'kld': kld_cases}[name]()
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
         print('%-14s %4d arrays' % (name, len(arrays)))
         return
@@ -472,6 +493,7 @@ def main():
         'upsample': upsample_cases(),
         'sequence_mask': sequence_mask_cases(),
         'voiced_mask': voiced_mask_cases(),
+        'kld': kld_cases(),
         'normalise': normaliser_cases(),
         'losses': loss_cases(),
         'metrics': metric_cases(),

@@ -654,6 +654,34 @@ def test_fused_objective_matches_drop_in_composition(mg):
         assert rel_err(got.result(), float(want.result())) <= REL
 
 
+@pytest.mark.parametrize('tag', ['2d', '3d', 'row'])
+def test_kld_standard_normal_golden(mg, golden, tag):
+    """losses.KLD_standard_normal against outputs and autograd gradients of the reference (losses.py:64-67): 1e-6 relative on
+    the value, 3e-6 on the gradients (an upstream factor of 0.25 included)."""
+    g = golden('kld')
+    mean, lv = dev(g['kld_%s_mean' % tag]).requires_grad_(), dev(g['kld_%s_lv' % tag]).requires_grad_()
+    loss = mg.losses.KLD_standard_normal(mean, lv)
+    assert loss.dim() == 0 and loss.dtype == torch.float32
+    want = float(g['kld_%s_loss' % tag])
+    assert abs(loss.item() - want) <= 1e-6 * abs(want)
+    (0.25 * loss).backward()
+    np.testing.assert_allclose(mean.grad.cpu().numpy(), g['kld_%s_grad_mean' % tag], rtol=3e-6, atol=1e-9)
+    np.testing.assert_allclose(lv.grad.cpu().numpy(), g['kld_%s_grad_lv' % tag], rtol=3e-6, atol=1e-9)
+
+
+def test_kld_standard_normal_large_and_deterministic(mg):
+    rng = np.random.default_rng(4)
+    m, lv = rng.standard_normal((1000, 257)).astype(np.float32), (0.3 * rng.standard_normal((1000, 257))).astype(np.float32)
+    md, lvd = dev(m).requires_grad_(), dev(lv).requires_grad_()
+    loss = mg.losses.KLD_standard_normal(md, lvd)
+    want, want_gm, want_glv = O.kld_standard_normal(m, lv)
+    assert abs(loss.item() - want) <= 1e-6 * abs(want)
+    assert mg.losses.KLD_standard_normal(md, lvd).item() == loss.item()
+    loss.backward()
+    np.testing.assert_allclose(md.grad.cpu().numpy(), want_gm, rtol=3e-6, atol=1e-12)
+    np.testing.assert_allclose(lvd.grad.cpu().numpy(), want_glv, rtol=3e-6, atol=1e-10)
+
+
 def test_both_voiced_mask_golden(mg, golden):
     """utils.both_voiced_mask against outputs of the reference (utils.py:169-172): NaN and -0. included, dtype argument kept."""
     g = golden('voiced_mask')

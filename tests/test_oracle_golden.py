@@ -63,6 +63,15 @@ def test_sequence_mask(golden):
     assert np.array_equal(O.sequence_mask(seq_len, 4), g['mask_len4_u8'])
 
 
+@pytest.mark.parametrize('tag', ['2d', '3d', 'row'])
+def test_kld_standard_normal(golden, tag):
+    g = golden('kld')
+    loss, grad_mean, grad_lv = O.kld_standard_normal(g['kld_%s_mean' % tag], g['kld_%s_lv' % tag])
+    np.testing.assert_allclose(loss, g['kld_%s_loss' % tag], rtol=REL)
+    np.testing.assert_allclose(0.25 * grad_mean, g['kld_%s_grad_mean' % tag], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(0.25 * grad_lv, g['kld_%s_grad_lv' % tag], rtol=1e-5, atol=1e-8)
+
+
 def test_both_voiced_mask(golden):
     g = golden('voiced_mask')
     a, b, c = g['voiced_a'], g['voiced_b'], g['voiced_c']
