@@ -69,6 +69,8 @@ __device__ __forceinline__ float elem_bwd(float a, float b) {
   } else if constexpr (KIND == MG_RED_ABSDIFF) {
     const float d = __fsub_rn(a, b);
     return d > 0.f ? 1.f : (d < 0.f ? -1.f : 0.f);
+  } else if constexpr (KIND == MG_RED_SUM) {   // the masked mean of a caller-supplied per-element loss (sequence_loss, losses.py:9-47)
+    return 1.f;
   } else {  // MG_RED_BCE: ATen binary_cross_entropy_backward, (p - y) / max((1 - p) * p, 1e-12)
     return __fdiv_rn(__fsub_rn(a, b), fmaxf(__fmul_rn(__fsub_rn(1.f, a), a), 1e-12f));
   }
@@ -375,7 +377,7 @@ __device__ __forceinline__ void run_float_term(const mg_term& tm, int b, int64_t
     run_per_frame<KIND>(a, tm.a_st, bb, tm.b_st, tm.m, tm.m_st, tm.m_dtype, tm.flags, b * tm.m_sb + r0 * tm.m_st, n_valid, D, sum, cnt);
     return;
   }
-  constexpr bool CAN_GRAD = KIND == MG_RED_SQDIFF || KIND == MG_RED_ABSDIFF || KIND == MG_RED_BCE;
+  constexpr bool CAN_GRAD = KIND == MG_RED_SQDIFF || KIND == MG_RED_ABSDIFF || KIND == MG_RED_BCE || KIND == MG_RED_SUM;
   const bool contiguous = tm.a_st == D && (!kind_has_b(KIND) || tm.b_st == D);
   // a wide slice of a row-major tensor: both operands with the same row stride and the same position inside a 16-byte line
   const bool wide_slice = !contiguous && n_valid > 0 && D >= 4 && 2 * static_cast<int64_t>(D) >= tm.a_st && tm.a_st <= 4 * kRedThreads &&
@@ -511,7 +513,7 @@ extern "C" int mg_masked_reduce(const mg_term* terms, int n_terms, const int64_t
     }
     MG_REQUIRE(!kind_has_b(tm.kind) || tm.b != nullptr || T == 0, "mg_masked_reduce: term %d needs a second operand", i);
     if (tm.grad != nullptr) {
-      MG_REQUIRE(tm.kind == MG_RED_SQDIFF || tm.kind == MG_RED_ABSDIFF || tm.kind == MG_RED_BCE || tm.kind == MG_RED_CE,
+      MG_REQUIRE(tm.kind == MG_RED_SQDIFF || tm.kind == MG_RED_ABSDIFF || tm.kind == MG_RED_BCE || tm.kind == MG_RED_CE || tm.kind == MG_RED_SUM,
                  "mg_masked_reduce: term %d: kind %d has no gradient", i, tm.kind);
       MG_REQUIRE(tm.m == nullptr, "mg_masked_reduce: term %d: weighted terms have no gradient", i);
     }

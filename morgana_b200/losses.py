@@ -5,7 +5,20 @@
 that supports ``.backward()``.  ``l1`` is the same wrapper around the absolute error; ``ce`` takes logits and class
 indices (``morgana/losses.py:59-61``); ``KLD_standard_normal`` is the unmasked latent-space term (``morgana/losses.py:64-67``).
 """
+import functools
+
 from morgana_b200 import ops
+
+
+def sequence_loss(loss_fn):
+    r"""Sequence-loss wrapper of the reference (``morgana/losses.py:9-47``): adds the optional ``seq_len`` argument that masks
+    padded frames.  ``loss_fn(predictions, targets)`` is the caller's own per-element loss (any differentiable torch code
+    returning ``(batch_size, seq_len, feat_dim)``); the masking, the per-utterance normalisation by the number of valid frames
+    and the mean over batch items and feature dimensions are one kernel launch (forward) and one (backward)."""
+    @functools.wraps(loss_fn)
+    def wrapped_loss(predictions, targets, seq_len=None):
+        return ops.masked_loss(loss_fn(predictions, targets), None, seq_len, 'mean')
+    return wrapped_loss
 
 
 def mse(predictions, targets, seq_len=None):

@@ -492,7 +492,7 @@ def masked_objective(pred, target, seq_len, cols, slots, grad=None, grad_scale_d
                                       ws.numel(), _stream()), 'mg_masked_objective_f32')
 
 
-_LOSS_KINDS = {'mse': _lib.RED_SQDIFF, 'l1': _lib.RED_ABSDIFF, 'bce': _lib.RED_BCE, 'ce': _lib.RED_CE}
+_LOSS_KINDS = {'mse': _lib.RED_SQDIFF, 'l1': _lib.RED_ABSDIFF, 'bce': _lib.RED_BCE, 'ce': _lib.RED_CE, 'mean': _lib.RED_SUM}
 
 
 class _MaskedLossFn(torch.autograd.Function):
@@ -532,6 +532,16 @@ class _MaskedLossFn(torch.autograd.Function):
 def masked_loss(predictions, targets, seq_len=None, kind='mse'):
     """``mean_{b,d} [ sum_{t < n_b} l(p, y) / n_b ]`` as a 0-dim float32 tensor with autograd."""
     _require_cuda(predictions, 'predictions')
+    if kind == 'mean':     # the masked mean of a per-element loss the caller computed (losses.sequence_loss around a custom loss_fn)
+        if targets is not None:
+            raise TypeError("kind 'mean' takes the per-element loss alone")
+        if predictions.dtype != torch.float32 or predictions.dim() != 3:
+            raise TypeError('sequence_loss needs a float32 (batch_size, seq_len, feat_dim) per-element loss, got {} {}'
+                            .format(predictions.dtype, tuple(predictions.shape)))
+        if predictions.shape[0] == 0 or predictions.shape[2] == 0:
+            return torch.full((), float('nan'), dtype=torch.float32, device=predictions.device)
+        seq_len = _seq_len_arg(seq_len, predictions.shape[0], predictions.device)
+        return _MaskedLossFn.apply(predictions, None, seq_len, _LOSS_KINDS[kind])
     _require_cuda(targets, 'targets')
     if kind == 'ce':
         if predictions.dtype != torch.float32 or predictions.dim() != 3 or targets.dtype != torch.int64 or \

@@ -37,7 +37,7 @@ def patch(morgana=None):
             _swap(morgana.utils, name, getattr(_utils, name))
     _swap(morgana.losses, 'mse', _losses.mse)
     _swap(morgana.losses, 'bce', _losses.bce)
-    for name in ('ce', 'KLD_standard_normal'):
+    for name in ('ce', 'KLD_standard_normal', 'sequence_loss'):
         if hasattr(morgana.losses, name):
             _swap(morgana.losses, name, getattr(_losses, name))
     for name in ('normalise_mvn', 'denormalise_mvn', 'normalise_minmax', 'denormalise_minmax'):

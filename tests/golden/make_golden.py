@@ -134,6 +134,30 @@ def kld_cases():
     return out
 
 
+def sequence_loss_cases():
+    """losses.sequence_loss (reference losses.py:9-47) around a loss the reference does not ship: smooth-L1 per element."""
+    import torch.nn.functional as F
+
+    @losses.sequence_loss
+    def huber(predictions, targets):
+        return F.smooth_l1_loss(predictions, targets, reduction='none')
+
+    g = gen(79)
+    out = {}
+    p = (2. * torch.randn(6, 29, 7, generator=g)).requires_grad_()
+    t = torch.randn(6, 29, 7, generator=g)
+    n = torch.tensor([29, 1, 17, 5, 29, 11])
+    out['seqloss_p'], out['seqloss_t'], out['seqloss_n'] = p.detach().numpy(), t.numpy(), n.numpy()
+    loss = huber(p, t, seq_len=n)
+    (3. * loss).backward()
+    out['seqloss_masked'], out['seqloss_masked_grad'] = loss.detach().numpy(), p.grad.numpy().copy()
+    p.grad = None
+    loss = huber(p, t)
+    loss.backward()
+    out['seqloss_full'], out['seqloss_full_grad'] = loss.detach().numpy(), p.grad.numpy().copy()
+    return out
+
+
 def normaliser_cases():
     out = {}
     g = gen(100)
@@ -436,7 +460,7 @@ def signature_cases():
     names = {
         'utils': ['upsample_to_repetitions', 'sequence_mask', 'batched_masked_select', 'get_segment_ends', 'split_to_segments',
                   'both_voiced_mask'],
-        'losses': ['mse', 'bce', 'ce', 'KLD_standard_normal'],
+        'losses': ['mse', 'bce', 'ce', 'KLD_standard_normal', 'sequence_loss'],
         'data': ['normalise_mvn', 'denormalise_mvn', 'normalise_minmax', 'denormalise_minmax'],
         'viz.synthesis': ['MLPG'],
     }
@@ -481,7 +505,7 @@ def main():
                 json.dump(signature_cases(), f, indent=1, sort_keys=True)
             print('signatures.json written')
             return
-        arrays = {'voiced_mask': voiced_mask_cases, 'kld': kld_cases}[name]()
+        arrays = {'voiced_mask': voiced_mask_cases, 'kld': kld_cases, 'sequence_loss': sequence_loss_cases}[name]()
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
         print('%-14s %4d arrays' % (name, len(arrays)))
         return
@@ -494,6 +518,7 @@ def main():
         'sequence_mask': sequence_mask_cases(),
         'voiced_mask': voiced_mask_cases(),
         'kld': kld_cases(),
+        'sequence_loss': sequence_loss_cases(),
         'normalise': normaliser_cases(),
         'losses': loss_cases(),
         'metrics': metric_cases(),

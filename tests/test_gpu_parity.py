@@ -654,6 +654,28 @@ def test_fused_objective_matches_drop_in_composition(mg):
         assert rel_err(got.result(), float(want.result())) <= REL
 
 
+def test_sequence_loss_wrapper_golden(mg, golden):
+    """losses.sequence_loss around a caller-defined per-element loss (smooth-L1, which the reference does not ship) against
+    the reference's wrapper (losses.py:9-47): the loss_fn is the caller's torch code, masking + normalisation + mean are ours."""
+    g = golden('sequence_loss')
+
+    @mg.losses.sequence_loss
+    def huber(predictions, targets):
+        return torch.nn.functional.smooth_l1_loss(predictions, targets, reduction='none')
+
+    assert huber.__name__ == 'huber'
+    p, t, n = dev(g['seqloss_p']).requires_grad_(), dev(g['seqloss_t']), dev(g['seqloss_n'])
+    loss = huber(p, t, seq_len=n)
+    assert abs(loss.item() - float(g['seqloss_masked'])) <= 1e-6 * abs(float(g['seqloss_masked']))
+    (3. * loss).backward()
+    np.testing.assert_allclose(p.grad.cpu().numpy(), g['seqloss_masked_grad'], rtol=3e-6, atol=1e-10)
+    p.grad = None
+    loss = huber(p, t)
+    assert abs(loss.item() - float(g['seqloss_full'])) <= 1e-6 * abs(float(g['seqloss_full']))
+    loss.backward()
+    np.testing.assert_allclose(p.grad.cpu().numpy(), g['seqloss_full_grad'], rtol=3e-6, atol=1e-10)
+
+
 @pytest.mark.parametrize('tag', ['2d', '3d', 'row'])
 def test_kld_standard_normal_golden(mg, golden, tag):
     """losses.KLD_standard_normal against outputs and autograd gradients of the reference (losses.py:64-67): 1e-6 relative on
