@@ -32,7 +32,7 @@ def patch(morgana=None):
         return morgana
     _swap(morgana.utils, 'upsample_to_repetitions', _utils.upsample_to_repetitions)
     _swap(morgana.utils, 'ExponentialMovingAverage', _utils.ExponentialMovingAverage)
-    for name in ('batched_masked_select', 'get_segment_ends', 'split_to_segments', 'both_voiced_mask'):
+    for name in ('batched_masked_select', 'get_segment_ends', 'split_to_segments', 'both_voiced_mask', 'detach_batched_seqs'):
         if hasattr(morgana.utils, name):
             _swap(morgana.utils, name, getattr(_utils, name))
     _swap(morgana.losses, 'mse', _losses.mse)

@@ -99,6 +99,42 @@ def upsample_packed_to_repetitions(packed_feature, packed_repeats, n_items, norm
                                return_lengths=return_lengths)
 
 
+def detach_batched_seqs(*sequence_features, seq_len=None, squeeze=True):
+    r"""Converts :class:`torch.Tensor` to `np.ndarray`: moves data to the host, detaches gradients and removes padding
+    (``morgana/utils.py:66-102``; called on the outputs of ``predict`` by ``models/RNN_SPSS.py:149`` and ``viz/io.py:47``).
+
+    Same return structure as the reference -- per feature a list of ``(seq_len_b, feat_dim)`` arrays (squeezed when
+    ``squeeze``), or the whole padded array without ``seq_len`` -- but a CUDA feature is packed on the device first
+    (``mg_pack_rows``): only the valid rows cross PCIe, in one copy, and the per-utterance arrays are views of that buffer.
+    """
+    import numpy as np
+    lengths = seq_len
+    if isinstance(lengths, torch.Tensor):
+        lengths = lengths.detach().cpu().numpy()
+    detached = []
+    for feature in sequence_features:
+        on_device = isinstance(feature, torch.Tensor) and feature.is_cuda
+        if on_device and lengths is not None and feature.dim() > 2 and feature.shape[0] == len(lengths) and \
+                all(0 <= int(n) for n in lengths):
+            batch_size, max_len = feature.shape[0], feature.shape[1]
+            rows = feature.detach().reshape(batch_size, max_len, -1)
+            clipped = np.minimum(np.asarray(lengths, dtype=np.int64), max_len)
+            packed = ops.pack_rows(rows, torch.as_tensor(clipped, device=feature.device)).cpu().numpy()
+            packed = packed.reshape((packed.shape[0],) + tuple(feature.shape[2:]))
+            stops = np.cumsum(clipped)
+            items = [packed[stop - n:stop] for stop, n in zip(stops, clipped)]
+            feature = [item.squeeze() if squeeze else item for item in items]
+        else:
+            if isinstance(feature, torch.Tensor):
+                feature = feature.cpu().detach().numpy()
+            if lengths is not None and feature[0].ndim > 1:
+                feature = [item[:n].squeeze() if squeeze else item[:n] for item, n in zip(feature, lengths)]
+        detached.append(feature)
+    if len(detached) == 1:
+        return detached[0]
+    return detached
+
+
 def batched_masked_select(sequence_feature, seq_len):
     r"""Feature vectors of all batch items that lie inside their sequence, as one ``(sum(seq_len), feat_dim)`` tensor
     (morgana/utils.py:147-166).  One scan + one row-copy kernel instead of mask / nonzero / advanced indexing."""

@@ -158,6 +158,22 @@ def sequence_loss_cases():
     return out
 
 
+def detach_cases():
+    """utils.detach_batched_seqs (reference utils.py:66-102): padding removed per utterance, squeezed or not."""
+    g = gen(80)
+    out = {}
+    x = torch.randn(5, 13, 4, generator=g)
+    y = torch.randn(5, 13, 1, generator=g)
+    n = torch.tensor([13, 1, 0, 7, 9])
+    out['detach_x'], out['detach_y'], out['detach_n'] = x.numpy(), y.numpy(), n.numpy()
+    xs, ys = utils.detach_batched_seqs(x, y, seq_len=n)
+    raw = utils.detach_batched_seqs(y, seq_len=n, squeeze=False)
+    for b in range(5):
+        out['detach_x_%d' % b], out['detach_y_%d' % b], out['detach_y_raw_%d' % b] = xs[b], ys[b], raw[b]
+    out['detach_full'] = utils.detach_batched_seqs(x)
+    return out
+
+
 def normaliser_cases():
     out = {}
     g = gen(100)
@@ -459,7 +475,7 @@ def signature_cases():
     from morgana.viz import synthesis
     names = {
         'utils': ['upsample_to_repetitions', 'sequence_mask', 'batched_masked_select', 'get_segment_ends', 'split_to_segments',
-                  'both_voiced_mask'],
+                  'both_voiced_mask', 'detach_batched_seqs'],
         'losses': ['mse', 'bce', 'ce', 'KLD_standard_normal', 'sequence_loss'],
         'data': ['normalise_mvn', 'denormalise_mvn', 'normalise_minmax', 'denormalise_minmax'],
         'viz.synthesis': ['MLPG'],
@@ -505,7 +521,7 @@ def main():
                 json.dump(signature_cases(), f, indent=1, sort_keys=True)
             print('signatures.json written')
             return
-        arrays = {'voiced_mask': voiced_mask_cases, 'kld': kld_cases, 'sequence_loss': sequence_loss_cases}[name]()
+        arrays = {'voiced_mask': voiced_mask_cases, 'kld': kld_cases, 'sequence_loss': sequence_loss_cases, 'detach': detach_cases}[name]()
         np.savez_compressed(os.path.join(HERE, name + '.npz'), **arrays)
         print('%-14s %4d arrays' % (name, len(arrays)))
         return
@@ -519,6 +535,7 @@ def main():
         'voiced_mask': voiced_mask_cases(),
         'kld': kld_cases(),
         'sequence_loss': sequence_loss_cases(),
+        'detach': detach_cases(),
         'normalise': normaliser_cases(),
         'losses': loss_cases(),
         'metrics': metric_cases(),

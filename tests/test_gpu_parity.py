@@ -704,6 +704,21 @@ def test_kld_standard_normal_large_and_deterministic(mg):
     np.testing.assert_allclose(lvd.grad.cpu().numpy(), want_glv, rtol=3e-6, atol=1e-10)
 
 
+def test_detach_batched_seqs_golden(mg, golden):
+    """utils.detach_batched_seqs on CUDA tensors (packed on the device, one copy of the valid rows) against the lists the
+    reference returns (utils.py:66-102): shapes after squeeze included (length-1 and length-0 utterances)."""
+    g = golden('detach')
+    x, y, n = dev(g['detach_x']).requires_grad_(), dev(g['detach_y']), dev(g['detach_n'])
+    xs, ys = mg.utils.detach_batched_seqs(x, y, seq_len=n)
+    raw = mg.utils.detach_batched_seqs(y, seq_len=g['detach_n'], squeeze=False)
+    assert len(xs) == len(ys) == len(raw) == 5
+    for b in range(5):
+        for got, want in ((xs[b], g['detach_x_%d' % b]), (ys[b], g['detach_y_%d' % b]), (raw[b], g['detach_y_raw_%d' % b])):
+            assert isinstance(got, np.ndarray) and got.shape == want.shape and np.array_equal(got, want), b
+    full = mg.utils.detach_batched_seqs(x)
+    assert isinstance(full, np.ndarray) and np.array_equal(full, g['detach_full'])
+
+
 def test_both_voiced_mask_golden(mg, golden):
     """utils.both_voiced_mask against outputs of the reference (utils.py:169-172): NaN and -0. included, dtype argument kept."""
     g = golden('voiced_mask')
