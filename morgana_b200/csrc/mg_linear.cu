@@ -449,8 +449,7 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
   if (pair) {
     // persistent: one CTA per SM, launched as 2-CTA clusters (a pair shares a TPC)
     const int64_t n_pairs = n_tiles_total < sms / 2 ? n_tiles_total : sms / 2;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(static_cast<unsigned>(2 * n_pairs));
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = kGemmSmem;

@@ -160,7 +160,6 @@ bias_grad_finish_kernel(const double* __restrict__ partial, int n_ctas, int64_t 
 // K7w: weight gradient
 // ------------------------------------------------------------------------------------------------------------------
 constexpr int kWgTileN = 128;             // output rows (out_features) of one accumulator = TMEM lanes
-constexpr int kWgMaxTileK = 256;          // output columns (in_features) of one accumulator = N of the MMA
 constexpr int kWgFrames = 128;            // frames per shared-memory stage (8 MMAs of 16 per barrier round trip; 64: 0.231 vs 0.214 ms at 512 x 600); MG_WGRAD_FRAMES=64
 constexpr int kWgAtom = 64;               // features per TMA box / swizzle atom (128 bytes of bf16)
 constexpr int kWgMaxStages = 6;
@@ -504,8 +503,7 @@ extern "C" int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, i
   }
   const unsigned units = static_cast<unsigned>(plan.splits * plan.n_tiles * plan.k_tiles);
   if (plan.pair) {
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
+    cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(2 * units);
     cfg.blockDim = dim3(kWgThreads);
     cfg.dynamicSmemBytes = kWgSmem;
