@@ -6,6 +6,7 @@ elementwise work; 1e-6 relative for reductions (the reference reduces in fp32, t
 """
 import numpy as np
 import pytest
+import torch
 
 from oracle import np_oracle as O
 
@@ -344,3 +345,20 @@ def test_segment_ops_bit_exact(golden):
     assert np.array_equal(O.get_segment_ends(xi, li), g['seg_int_ends'])
     assert np.array_equal(O.split_to_segments(xi, li), g['seg_int_split'])
     assert np.array_equal(O.batched_masked_select(xi, np.array([9, 1, 4])), g['seg_int_select'])
+
+
+def test_linear_backward_oracle_against_autograd():
+    """The K7 backward checkers (sigmoid_grad, linear_wgrad) against torch autograd of nn.Linear + nn.Sigmoid on the CPU -- what
+    the reference's training step runs (README.rst:65-73, experiment_builder.py:470-479)."""
+    torch.manual_seed(3)
+    layer = torch.nn.Linear(37, 11)
+    x = torch.randn(53, 37)
+    pre = layer(x)
+    y = torch.sigmoid(pre)
+    upstream = torch.randn_like(y)
+    grad_pre, = torch.autograd.grad(y, pre, upstream, retain_graph=True)
+    got = O.sigmoid_grad(upstream.numpy(), y.detach().numpy())
+    assert got.dtype == np.float32 and np.array_equal(got, grad_pre.numpy())          # ATen: grad * (1 - y) * y, same rounding order
+    y.backward(upstream)
+    np.testing.assert_allclose(O.linear_wgrad(grad_pre.numpy(), x.numpy()), layer.weight.grad.numpy(), rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(grad_pre.numpy().astype(np.float64).sum(0), layer.bias.grad.numpy(), rtol=1e-5, atol=1e-5)
