@@ -235,3 +235,16 @@ def test_torch_ops_are_registered_for_cuda_only(mg):
         torch.ops.morgana_b200.upsample_norm(x, torch.ones(2, 3, dtype=torch.long), None, None, 'none', -1)
     with pytest.raises(NotImplementedError):
         torch.ops.morgana_b200.masked_loss(x, x, None, 'mse')
+
+
+def test_detach_batched_seqs_host_inputs_match_golden(mg, golden):
+    """utils.detach_batched_seqs moves data to the host and strips padding -- no arithmetic: tensors that already live on the
+    host (and NumPy inputs) go through the same slicing as the reference (utils.py:66-102)."""
+    g = golden('detach')
+    x, y, n = torch.from_numpy(g['detach_x']).requires_grad_(), g['detach_y'], torch.from_numpy(g['detach_n'])
+    xs, ys = mg.utils.detach_batched_seqs(x, y, seq_len=n)
+    raw = mg.utils.detach_batched_seqs(torch.from_numpy(y), seq_len=g['detach_n'], squeeze=False)
+    for b in range(5):
+        for got, want in ((xs[b], g['detach_x_%d' % b]), (ys[b], g['detach_y_%d' % b]), (raw[b], g['detach_y_raw_%d' % b])):
+            assert got.shape == want.shape and np.array_equal(got, want)
+    assert np.array_equal(mg.utils.detach_batched_seqs(x), g['detach_full'])
