@@ -326,6 +326,9 @@ int mg_act_grad_bf16(const void* grad_y, int grad_is_bf16, int64_t ldg, const vo
                      void* out, int64_t ld_out, float* bias_grad, int64_t M, int N, void* workspace, int64_t workspace_bytes,
                      mg_stream_t stream);
 int64_t mg_linear_wgrad_workspace_bytes(int64_t M, int N, int K);
+/* host-only: the launch plan of mg_linear_wgrad_bf16 (tile_k, n_tiles, k_tiles, splits, blocks_per_split, n_fblocks, tile_rows,
+ * pair) for the shapes of nn.Linear's weight gradient (README.rst:65-73); used by the CPU tests to check the plan's invariants */
+int mg_linear_wgrad_plan(int64_t M, int N, int K, int64_t* out8);
 int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, int64_t ldx, float* grad_w, int64_t ldw, int64_t M, int N,
                          int K, void* workspace, int64_t workspace_bytes, mg_stream_t stream);
 

@@ -95,6 +95,7 @@ PROTOTYPES = {
     'mg_act_grad_bf16': (c_int, [c_void_p, c_int, c_i64, c_void_p, c_int, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_int,
                                  c_void_p, c_i64, c_void_p]),
     'mg_linear_wgrad_workspace_bytes': (c_i64, [c_i64, c_int, c_int]),
+    'mg_linear_wgrad_plan': (c_int, [c_i64, c_int, c_int, ctypes.POINTER(c_i64)]),
     'mg_linear_wgrad_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_int, c_void_p, c_i64,
                                      c_void_p]),
     'mg_kld_workspace_bytes': (c_i64, [c_i64]),

@@ -458,6 +458,16 @@ extern "C" int64_t mg_linear_wgrad_workspace_bytes(int64_t M, int N, int K) {
   return plan_wgrad(M, N, K).partial_elems * static_cast<int64_t>(sizeof(float));
 }
 
+// Host-only: the launch plan of mg_linear_wgrad_bf16 as 8 integers (tile_k, n_tiles, k_tiles, splits, blocks_per_split, n_fblocks,
+// tile_rows, pair) -- lets the CPU test-suite check its invariants (every frame slice non-empty, workspace size) over many shapes.
+extern "C" int mg_linear_wgrad_plan(int64_t M, int N, int K, int64_t* out8) {
+  MG_REQUIRE(M >= 1 && N >= 1 && K >= 1 && out8 != nullptr, "mg_linear_wgrad_plan: bad argument");
+  const WgradPlan p = plan_wgrad(M, N, K);
+  out8[0] = p.tile_k; out8[1] = p.n_tiles; out8[2] = p.k_tiles; out8[3] = p.splits; out8[4] = p.blocks_per_split;
+  out8[5] = p.n_fblocks; out8[6] = p.tile_rows; out8[7] = p.pair ? 1 : 0;
+  return MG_OK;
+}
+
 extern "C" int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, int64_t ldx, float* grad_w, int64_t ldw,
                                     int64_t M, int N, int K, void* workspace, int64_t workspace_bytes, mg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);

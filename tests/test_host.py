@@ -248,3 +248,30 @@ def test_detach_batched_seqs_host_inputs_match_golden(mg, golden):
         for got, want in ((xs[b], g['detach_x_%d' % b]), (ys[b], g['detach_y_%d' % b]), (raw[b], g['detach_y_raw_%d' % b])):
             assert got.shape == want.shape and np.array_equal(got, want)
     assert np.array_equal(mg.utils.detach_batched_seqs(x), g['detach_full'])
+
+
+def test_wgrad_plan_invariants(mg):
+    """The frame-split plan of the tcgen05 weight gradient, over many shapes, on the host: every slice of frames is
+    non-empty (an empty slice would leave a CTA waiting for an accumulator that never completes), the slices cover every
+    frame block exactly once, pairs only where the x tile splits into whole 64-column atoms, and the workspace matches."""
+    import ctypes
+    from morgana_b200 import _lib
+    rng = np.random.default_rng(0)
+    shapes = [(1, 1, 1), (63, 1, 32), (64, 3, 8), (65, 187, 256), (348928, 512, 600), (348928, 128, 512), (30000, 32, 128),
+              (2 ** 31 - 200, 2048, 4096), (129, 2048, 64), (10 ** 6, 199, 609), (128 * 148, 256, 512), (128 * 148 + 1, 130, 130)]
+    shapes += [(int(rng.integers(1, 400000)), int(rng.integers(1, 2049)), int(rng.integers(1, 2049))) for _ in range(300)]
+    out = (ctypes.c_int64 * 8)()
+    for M, N, K in shapes:
+        assert _lib.lib.mg_linear_wgrad_plan(M, N, K, out) == 0
+        tile_k, n_tiles, k_tiles, splits, per_split, n_fblocks, tile_rows, pair = list(out)
+        frames = 128
+        assert n_fblocks == (M + frames - 1) // frames
+        assert tile_k in (64, 128, 192, 256) and tile_rows == (256 if pair else 128)
+        assert n_tiles * tile_rows >= N > (n_tiles - 1) * tile_rows and k_tiles * tile_k >= K > (k_tiles - 1) * tile_k
+        assert splits >= 1 and per_split >= 1
+        assert splits * per_split >= n_fblocks > (splits - 1) * per_split, (M, N, K)          # covered, and the last slice is not empty
+        ctas = splits * n_tiles * k_tiles * (2 if pair else 1)
+        assert ctas <= max(148, n_tiles * k_tiles * (2 if pair else 1)), (M, N, K)             # one wave when the tiles allow it
+        if pair:
+            assert N > 128 and tile_k % 128 == 0
+        assert _lib.lib.mg_linear_wgrad_workspace_bytes(M, N, K) == 4 * splits * n_tiles * tile_rows * k_tiles * tile_k
