@@ -170,3 +170,35 @@ def test_ema_and_segments(seed):
         tl = torch.from_numpy(lens)[:, :, None]
         assert np.array_equal(O.get_segment_ends(x, lens), ref_utils.get_segment_ends(torch.from_numpy(x), tl).numpy())
         assert np.array_equal(O.split_to_segments(x, lens), ref_utils.split_to_segments(torch.from_numpy(x), tl).numpy())
+
+
+@pytest.mark.parametrize('kind', ['mvn', 'minmax'])
+def test_normaliser_classes_numpy_path(kind, tmp_path):
+    """The drop-in normaliser classes on NumPy inputs (what DataLoader workers call, data.py:119-127) against the reference's
+    classes loaded from the same JSON files: same file names, same parameters, bit-identical results, deltas included."""
+    import json
+    mg_data = pytest.importorskip('morgana_b200.data')
+    rng = np.random.default_rng(7)
+    D = 9
+    if kind == 'mvn':
+        params = {'mean': rng.standard_normal(D).tolist(), 'std_dev': (np.abs(rng.standard_normal(D)) + 0.1).tolist()}
+        ref_cls, our_cls = ref_data.MeanVarianceNormaliser, mg_data.MeanVarianceNormaliser
+    else:
+        lo = rng.standard_normal(D)
+        hi = lo + np.abs(rng.standard_normal(D))
+        hi[2] = lo[2]
+        params = {'mmin': lo.tolist(), 'mmax': hi.tolist()}
+        ref_cls, our_cls = ref_data.MinMaxNormaliser, mg_data.MinMaxNormaliser
+    (tmp_path / 'norm').mkdir()
+    for name in ('lab', 'lab_deltas'):
+        with open(tmp_path / 'norm' / ('%s_%s.json' % (name, kind)), 'w') as f:
+            json.dump(params if name == 'lab' else {k: [v * 0.5 + 0.25 for v in vals] for k, vals in params.items()}, f)
+    ref_norm, our_norm = ref_cls('lab', use_deltas=True), our_cls('lab', use_deltas=True)
+    ref_norm.load_params('norm', data_root=str(tmp_path))
+    our_norm.load_params('norm', data_root=str(tmp_path))
+    x = rng.standard_normal((23, D)).astype(np.float32)
+    for deltas in (False, True):
+        want = ref_norm.normalise(x, deltas=deltas)
+        got = our_norm.normalise(x, deltas=deltas)
+        assert isinstance(got, np.ndarray) and got.dtype == want.dtype and np.array_equal(got, want)
+        assert np.array_equal(our_norm.denormalise(x, deltas=deltas), ref_norm.denormalise(x, deltas=deltas))
