@@ -120,9 +120,10 @@ int mg_upsample_norm_bwd_f32(const float* grad_out, const int32_t* ends, const f
  * packed     (sum_b len_b, row_bytes) bytes: utterance 0's rows, then utterance 1's, ...
  * ends       (B,) int32 inclusive scan of the lengths (mg_dur_scan over the lengths viewed as one (1, B) row).
  * out        (B, T, row_bytes): rows t < len_b copied, rows t >= len_b zero.  Utterances longer than T are truncated.
+ * total_rows rows held by `packed`: lengths that sum past it are truncated there (nothing is read beyond the buffer).
  */
 int mg_pad_collate(const void* packed, const int32_t* ends, void* out, int B, int64_t row_bytes, int64_t T,
-                   mg_stream_t stream);
+                   int64_t total_rows, mg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Sibling segment operations ("next" row 4): the same scan drives three more dtype-agnostic row movers.  Strides in BYTES.
@@ -140,6 +141,12 @@ int mg_segment_ends(const void* x, int64_t x_stride_b_bytes, int64_t x_stride_t_
                     int B, int S, int64_t T, int64_t row_bytes, mg_stream_t stream);
 int mg_split_to_segments(const void* x, int64_t x_stride_b_bytes, int64_t x_stride_t_bytes, const int32_t* seg_ends, void* out,
                          int B, int S, int64_t L, int64_t T, int64_t row_bytes, mg_stream_t stream);
+/* Backward of mg_segment_ends (L == 0; grad_out (B, S, row_bytes)) and of mg_split_to_segments (L > 0; grad_out
+ * (B, S, L, row_bytes)): what autograd's index_put_ does for the reference's advanced indexing (utils.py:281, 328).  Every
+ * frame row receives at most one output row, so this is a gather into the contiguous grad_x (B, T, row_bytes); rows no output
+ * row came from are zero.  (mg_pack_rows' backward is mg_pad_collate.) */
+int mg_segments_bwd(const void* grad_out, const int32_t* seg_ends, void* grad_x, int B, int S, int64_t L, int64_t T,
+                    int64_t row_bytes, mg_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K3  standalone normalise / denormalise -- replaces data.normalise_mvn, denormalise_mvn, normalise_minmax,

@@ -74,10 +74,11 @@ PROTOTYPES = {
                                   c_void_p]),
     'mg_upsample_norm_bwd_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_i64, c_int, c_void_p, c_int, c_int,
                                          c_int, c_i64, c_void_p]),
-    'mg_pad_collate': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_void_p]),
+    'mg_pad_collate': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_i64, c_i64, c_i64, c_void_p]),
     'mg_pack_rows': (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_int, c_i64, c_i64, c_void_p]),
     'mg_segment_ends': (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_void_p]),
     'mg_split_to_segments': (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p]),
+    'mg_segments_bwd': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_i64, c_i64, c_i64, c_void_p]),
     'mg_normalise_f32': (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_i64, c_int, c_i64, c_void_p]),
     'mg_masked_reduce_workspace_bytes': (c_i64, [c_int, c_int, c_i64]),
     'mg_masked_reduce': (c_int, [ctypes.POINTER(Term), c_int, c_void_p, c_int, c_i64, c_void_p, c_i64, c_void_p]),

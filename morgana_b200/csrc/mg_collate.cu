@@ -41,10 +41,11 @@ __device__ __forceinline__ void zero_span(unsigned char* dst, int64_t bytes) {
 // ends: inclusive scan of the lengths (int32, from mg_dur_scan on a (1, B) view).  vec: 16 / 4 / 1 bytes.
 __global__ void __launch_bounds__(kCollateThreads)
 pad_collate_kernel(const unsigned char* __restrict__ packed, const int32_t* __restrict__ ends, unsigned char* __restrict__ out,
-                   int64_t row_bytes, int64_t T, int rows_per_cta, int vec) {
+                   int64_t row_bytes, int64_t T, int64_t total_rows, int rows_per_cta, int vec) {
   const int b = blockIdx.y;
-  const int64_t begin = b > 0 ? static_cast<int64_t>(__ldg(ends + b - 1)) : 0;
-  const int64_t n_b = min(static_cast<int64_t>(__ldg(ends + b)) - begin, T);
+  // lengths that sum past the packed rows (unchecked on the no-sync path) are truncated, never read out of bounds
+  const int64_t begin = min(b > 0 ? static_cast<int64_t>(__ldg(ends + b - 1)) : 0, total_rows);
+  const int64_t n_b = min(min(static_cast<int64_t>(__ldg(ends + b)), total_rows) - begin, T);
   const int64_t r0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
   const int64_t r1 = min(r0 + rows_per_cta, T);
   const int64_t valid_end = min(r1, n_b);
@@ -70,9 +71,9 @@ pad_collate_kernel(const unsigned char* __restrict__ packed, const int32_t* __re
 }  // namespace
 
 extern "C" int mg_pad_collate(const void* packed, const int32_t* ends, void* out, int B, int64_t row_bytes, int64_t T,
-                              mg_stream_t stream_) {
+                              int64_t total_rows, mg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  MG_REQUIRE(B >= 0 && row_bytes >= 0 && T >= 0, "mg_pad_collate: negative shape");
+  MG_REQUIRE(B >= 0 && row_bytes >= 0 && T >= 0 && total_rows >= 0, "mg_pad_collate: negative shape");
   MG_REQUIRE(B <= 65535, "mg_pad_collate: B=%d exceeds 65535 utterances per call", B);
   if (B == 0 || T == 0 || row_bytes == 0) return MG_OK;
   MG_REQUIRE(ends != nullptr && out != nullptr && packed != nullptr, "mg_pad_collate: NULL buffer");
@@ -87,7 +88,7 @@ extern "C" int mg_pad_collate(const void* packed, const int32_t* ends, void* out
   dim3 grid(static_cast<unsigned>((T + rows - 1) / rows), static_cast<unsigned>(B));
   pad_collate_kernel<<<grid, kCollateThreads, 0, stream>>>(static_cast<const unsigned char*>(packed), ends,
                                                            static_cast<unsigned char*>(out), row_bytes, T,
-                                                           static_cast<int>(rows), vec);
+                                                           total_rows, static_cast<int>(rows), vec);
   MG_LAUNCH_OK();
   return MG_OK;
 }

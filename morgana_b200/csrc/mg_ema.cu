@@ -91,11 +91,13 @@ extern "C" int mg_ema_update_f32(float* const* shadow, const float* const* param
   MG_REQUIRE(n_tensors >= 0, "mg_ema_update_f32: negative tensor count");
   if (n_tensors == 0) return MG_OK;
   MG_REQUIRE(shadow != nullptr && param != nullptr && numel != nullptr, "mg_ema_update_f32: NULL table");
-  for (int first = 0; first < n_tensors; first += kEmaMaxTensors) {
+  int next = 0;     // running index: empty tensors are skipped without using up a slot of the launch
+  while (next < n_tensors) {
     EmaParams prm;
     memset(&prm, 0, sizeof(prm));
     int count = 0, chunks = 0;
-    for (int i = first; i < n_tensors && count < kEmaMaxTensors; ++i) {
+    int i = next;
+    for (; i < n_tensors && count < kEmaMaxTensors; ++i) {
       MG_REQUIRE(numel[i] >= 0, "mg_ema_update_f32: tensor %d has negative numel", i);
       if (numel[i] == 0) continue;
       MG_REQUIRE(shadow[i] != nullptr && param[i] != nullptr, "mg_ema_update_f32: tensor %d is NULL", i);
@@ -109,6 +111,7 @@ extern "C" int mg_ema_update_f32(float* const* shadow, const float* const* param
       chunks += static_cast<int>(c);
       ++count;
     }
+    next = i;
     if (count == 0) continue;
     prm.chunk_begin[count] = chunks;
     prm.n_tensors = count;

@@ -85,6 +85,40 @@ split_segments_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t
   else zero_row(dst, row_bytes, vec, lane);
 }
 
+// Backward of the two segment gathers: every frame row (b, t) belongs to at most one output row, so the gradient is a gather
+// too -- no atomics, no accumulation order.  Warp per (b, t): binary search of the segment whose interval holds t, then
+//   ENDS  (L == 0): grad_x[b, t] = grad_out[b, s]     if t is the segment's last frame, else 0
+//   SPLIT (L  > 0): grad_x[b, t] = grad_out[b, s, j]  with j = t - begin_s, if j < L, else 0 (rows cut off by a short L)
+// Rows past the last segment get zeros (the reference's padder row swallows nothing from them either).
+__global__ void __launch_bounds__(kSegWarps * 32)
+segments_bwd_kernel(const unsigned char* __restrict__ grad_out, const int32_t* __restrict__ seg_ends,
+                    unsigned char* __restrict__ grad_x, int B, int S, int64_t L, int64_t T, int64_t row_bytes, int vec) {
+  const int lane = threadIdx.x & 31;
+  const int64_t w = static_cast<int64_t>(blockIdx.x) * kSegWarps + (threadIdx.x >> 5);
+  if (w >= static_cast<int64_t>(B) * T) return;
+  const int b = static_cast<int>(w / T);
+  const int64_t t = w - static_cast<int64_t>(b) * T;
+  const int32_t* e = seg_ends + static_cast<int64_t>(b) * S;
+  int lo = 0, hi = S;                      // first s with e[s] > t
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (static_cast<int64_t>(__ldg(e + mid)) > t) hi = mid; else lo = mid + 1;
+  }
+  unsigned char* dst = grad_x + w * row_bytes;
+  if (lo < S) {
+    const int64_t end = __ldg(e + lo);
+    const int64_t begin = lo > 0 ? static_cast<int64_t>(__ldg(e + lo - 1)) : 0;
+    const int64_t bs = static_cast<int64_t>(b) * S + lo;
+    if (L == 0) {
+      if (t == end - 1) { copy_row(grad_out + bs * row_bytes, dst, row_bytes, vec, lane); return; }
+    } else if (t - begin < L) {
+      copy_row(grad_out + (bs * L + (t - begin)) * row_bytes, dst, row_bytes, vec, lane);
+      return;
+    }
+  }
+  zero_row(dst, row_bytes, vec, lane);
+}
+
 int pick_vec(const void* x, int64_t x_sb, int64_t x_st, const void* out, int64_t row_bytes) {
   auto ok = [&](int64_t a) { return row_bytes % a == 0 && mg_aligned(x, a) && mg_aligned(out, a) && x_sb % a == 0 && x_st % a == 0; };
   return ok(16) ? 16 : (ok(4) ? 4 : 1);
@@ -132,6 +166,21 @@ extern "C" int mg_split_to_segments(const void* x, int64_t x_stride_b_bytes, int
   split_segments_kernel<<<static_cast<unsigned>((warps + kSegWarps - 1) / kSegWarps), kSegWarps * 32, 0, stream>>>(
       static_cast<const unsigned char*>(x), x_stride_b_bytes, x_stride_t_bytes, seg_ends, static_cast<unsigned char*>(out), B, S, L, T,
       row_bytes, pick_vec(x, x_stride_b_bytes, x_stride_t_bytes, out, row_bytes));
+  MG_LAUNCH_OK();
+  return MG_OK;
+}
+
+extern "C" int mg_segments_bwd(const void* grad_out, const int32_t* seg_ends, void* grad_x, int B, int S, int64_t L, int64_t T,
+                               int64_t row_bytes, mg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MG_REQUIRE(B >= 0 && S >= 0 && L >= 0 && T >= 0 && row_bytes >= 0, "mg_segments_bwd: negative shape");
+  if (B == 0 || T == 0 || row_bytes == 0) return MG_OK;
+  MG_REQUIRE(grad_x != nullptr && (S == 0 || (seg_ends != nullptr && grad_out != nullptr)), "mg_segments_bwd: NULL buffer");
+  const int64_t warps = static_cast<int64_t>(B) * T;
+  MG_REQUIRE(warps / kSegWarps < (int64_t(1) << 31), "mg_segments_bwd: too many rows");
+  segments_bwd_kernel<<<static_cast<unsigned>((warps + kSegWarps - 1) / kSegWarps), kSegWarps * 32, 0, stream>>>(
+      static_cast<const unsigned char*>(grad_out), seg_ends, static_cast<unsigned char*>(grad_x), B, S, L, T, row_bytes,
+      pick_vec(grad_out, 16, 16, grad_x, row_bytes));
   MG_LAUNCH_OK();
   return MG_OK;
 }

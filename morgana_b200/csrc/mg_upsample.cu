@@ -310,8 +310,9 @@ upsample_bwd_kernel(const float* __restrict__ grad_out, const int32_t* __restric
   if (w >= n_items_total) return;
   const int b = static_cast<int>(w / P), p = static_cast<int>(w % P);
   const int32_t* e = ends + static_cast<int64_t>(b) * P;
-  const int64_t start = p > 0 ? static_cast<int64_t>(__ldg(e + p - 1)) : 0;
-  const int64_t stop = static_cast<int64_t>(__ldg(e + p));
+  // clamped to the rows grad_out has: with a caller-supplied max_len < n_b the forward truncated the utterance, so do we
+  const int64_t start = min(p > 0 ? static_cast<int64_t>(__ldg(e + p - 1)) : 0, T);
+  const int64_t stop = min(static_cast<int64_t>(__ldg(e + p)), T);
   const Vec* g = reinterpret_cast<const Vec*>(grad_out) + static_cast<int64_t>(b) * T * nvec;
   Vec* gx = reinterpret_cast<Vec*>(grad_x) + w * nvec;
   const float* q0 = p0 + static_cast<int64_t>(b) * p_sb;
@@ -365,8 +366,9 @@ upsample_bwd_rows_kernel(const float* __restrict__ grad_out, const int32_t* __re
   if (w >= n_items_total) return;
   const int b = static_cast<int>(w / P), p = static_cast<int>(w % P);
   const int32_t* e = ends + static_cast<int64_t>(b) * P;
-  const int64_t start = p > 0 ? static_cast<int64_t>(__ldg(e + p - 1)) : 0;
-  const int64_t stop = static_cast<int64_t>(__ldg(e + p));
+  // clamped to the rows grad_out has: with a caller-supplied max_len < n_b the forward truncated the utterance, so do we
+  const int64_t start = min(p > 0 ? static_cast<int64_t>(__ldg(e + p - 1)) : 0, T);
+  const int64_t stop = min(static_cast<int64_t>(__ldg(e + p)), T);
   const float4* g = reinterpret_cast<const float4*>(grad_out) + static_cast<int64_t>(b) * T * nvec;
   float4 acc[NS];
 #pragma unroll

@@ -262,8 +262,8 @@ def pad_collate(packed, lengths, max_len=None):
     D = packed.shape[1]
     out = torch.empty((B, int(max_len), D), dtype=packed.dtype, device=packed.device)
     with _device_of(packed):
-        check(lib.mg_pad_collate(_ptr(packed), _ptr(ends), _ptr(out), B, D * packed.element_size(), int(max_len), _stream()),
-              'mg_pad_collate')
+        check(lib.mg_pad_collate(_ptr(packed), _ptr(ends), _ptr(out), B, D * packed.element_size(), int(max_len), packed.shape[0],
+                                 _stream()), 'mg_pad_collate')
     return out
 
 
@@ -685,11 +685,13 @@ def cast_pad_bf16(x, k_padded=None):
 _ACTS = {None: _lib.ACT_NONE, 'none': _lib.ACT_NONE, 'sigmoid': _lib.ACT_SIGMOID}
 
 
-def linear_bf16(x, weight, bias=None, act=None, out_dtype=torch.float32):
+def linear_bf16(x, weight, bias=None, act=None, out_dtype=torch.float32, in_features=None):
     """K7: ``act(x @ weight.T + bias)`` on the tcgen05 tensor cores.  bf16 operands, fp32 accumulation.
 
     x : (M, K) bfloat16, row stride a multiple of 8 (fp32 input is converted with :func:`cast_pad_bf16`).
     weight : (N, K) bfloat16 (``nn.Linear.weight`` layout), bias : (N,) float32 or None.
+    in_features : the true K when the operands carry padding columns; by default both operands must have the same width up
+    to the padding to a multiple of 8 (a real mismatch raises, as ``nn.Linear`` does).
     """
     _require_cuda(x, 'x')
     _require_cuda(weight, 'weight')
@@ -702,7 +704,15 @@ def linear_bf16(x, weight, bias=None, act=None, out_dtype=torch.float32):
     if x.dtype != torch.bfloat16 or weight.dtype != torch.bfloat16:
         raise TypeError('linear_bf16 takes bfloat16 (or float32, converted) operands')
     M, N = x.shape[0], weight.shape[0]
-    K = min(x.shape[1], weight.shape[1])   # a padded operand carries zeros beyond the true K
+    if in_features is None:
+        if (x.shape[1] + 7) // 8 != (weight.shape[1] + 7) // 8:
+            raise RuntimeError('mat1 and mat2 shapes cannot be multiplied ({}x{} and {}x{})'
+                               .format(M, x.shape[1], weight.shape[1], N))
+        K = min(x.shape[1], weight.shape[1])   # a padded operand carries zeros beyond the true K
+    else:
+        K = int(in_features)
+        if not 0 <= K <= min(x.shape[1], weight.shape[1]):
+            raise ValueError('in_features={} exceeds the operands ({} and {} columns)'.format(K, x.shape[1], weight.shape[1]))
     for name, t in (('x', x), ('weight', weight)):
         if t.stride(1) != 1 or t.stride(0) % 8 != 0 or t.data_ptr() % 16 != 0:
             raise ValueError('{}: rows must be contiguous, 16-byte aligned, with a stride that is a multiple of 8'.format(name))
@@ -841,9 +851,40 @@ def _rows3(x, what):
     return x, x.stride(0) * es, x.stride(1) * es, x.shape[2] * es
 
 
-def pack_rows(x, seq_len):
-    """``(B, T, D)`` + lengths -> ``(sum(min(len, T)), D)``: the rows inside every utterance, back to back."""
+def _pack_rows_launch(x, ends, total):
     x, sb, st, row_bytes = _rows3(x, 'sequence_feature')
+    B, T, D = x.shape
+    out = torch.empty((total, D), dtype=x.dtype, device=x.device)
+    with _device_of(x):
+        check(lib.mg_pack_rows(_ptr(x), sb, st, _ptr(ends), _ptr(out), B, T, row_bytes, _stream()), 'mg_pack_rows')
+    return out
+
+
+class _PackRowsFn(torch.autograd.Function):
+    """Backward = the on-device collate: packed gradient rows back into a zero-padded (B, T, D) batch."""
+    @staticmethod
+    def forward(ctx, x, ends, total):
+        ctx.save_for_backward(ends)
+        ctx.shape = tuple(x.shape)
+        return _pack_rows_launch(x, ends, total)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (ends,) = ctx.saved_tensors
+        B, T, D = ctx.shape
+        grad = grad.contiguous()
+        grad_x = torch.empty((B, T, D), dtype=grad.dtype, device=grad.device)
+        with _device_of(grad):
+            check(lib.mg_pad_collate(_ptr(grad), _ptr(ends), _ptr(grad_x), B, D * grad.element_size(), T, grad.shape[0],
+                                     _stream()), 'mg_pad_collate')
+        return grad_x, None, None
+
+
+def pack_rows(x, seq_len):
+    """``(B, T, D)`` + lengths -> ``(sum(min(len, T)), D)``: the rows inside every utterance, back to back.  Differentiable."""
+    _require_cuda(x, 'sequence_feature')
+    if x.dim() != 3:
+        raise ValueError('sequence_feature must have shape (batch_size, max_seq_len, feat_dim)')
     B, T, D = x.shape
     if not isinstance(seq_len, torch.Tensor):
         seq_len = torch.as_tensor(seq_len, device=x.device)
@@ -851,10 +892,9 @@ def pack_rows(x, seq_len):
     lengths = seq_len.reshape(B).to(torch.int64).clamp(0, T)
     ends, _, summary = dur_scan(lengths.reshape(1, B))
     total = int(summary[2].item())                       # the output size is data dependent: one 8-byte read, as the reference's nonzero()
-    out = torch.empty((total, D), dtype=x.dtype, device=x.device)
-    with _device_of(x):
-        check(lib.mg_pack_rows(_ptr(x), sb, st, _ptr(ends), _ptr(out), B, T, row_bytes, _stream()), 'mg_pack_rows')
-    return out
+    if x.requires_grad and torch.is_grad_enabled():
+        return _PackRowsFn.apply(x, ends, total)
+    return _pack_rows_launch(x, ends, total)
 
 
 def _segment_scan(segment_lens, batch_size):
@@ -863,31 +903,88 @@ def _segment_scan(segment_lens, batch_size):
     return lens, ends, summary
 
 
-def segment_ends(x, segment_lens):
-    """``out[b, s] = x[b, cumsum(lens)[b, s] - 1]``, zero for empty segments."""
+def _segments_bwd(grad, ends, shape, L):
+    B, T, D = shape
+    S = ends.shape[1]
+    grad = grad.contiguous()
+    grad_x = torch.empty((B, T, D), dtype=grad.dtype, device=grad.device)
+    with _device_of(grad):
+        check(lib.mg_segments_bwd(_ptr(grad), _ptr(ends), _ptr(grad_x), B, S, L, T, D * grad.element_size(), _stream()),
+              'mg_segments_bwd')
+    return grad_x
+
+
+def _segment_ends_launch(x, ends):
     x, sb, st, row_bytes = _rows3(x, 'sequence_feature')
     B, T, D = x.shape
-    lens, ends, _ = _segment_scan(segment_lens, B)
-    S = lens.shape[1]
+    S = ends.shape[1]
     out = torch.empty((B, S, D), dtype=x.dtype, device=x.device)
     with _device_of(x):
         check(lib.mg_segment_ends(_ptr(x), sb, st, _ptr(ends), _ptr(out), B, S, T, row_bytes, _stream()), 'mg_segment_ends')
     return out
 
 
-def split_to_segments(x, segment_lens, max_segment_len=None):
-    """``out[b, s, j] = x[b, begin_s + j]`` for ``j < len_s`` else zero; ``(B, S, longest segment, D)``."""
+class _SegmentEndsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ends):
+        ctx.save_for_backward(ends)
+        ctx.shape = tuple(x.shape)
+        return _segment_ends_launch(x, ends)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (ends,) = ctx.saved_tensors
+        return _segments_bwd(grad, ends, ctx.shape, 0), None
+
+
+def segment_ends(x, segment_lens):
+    """``out[b, s] = x[b, cumsum(lens)[b, s] - 1]``, zero for empty segments.  Differentiable (clockwork RNNs train through it)."""
+    _require_cuda(x, 'sequence_feature')
+    if x.dim() != 3:
+        raise ValueError('sequence_feature must have shape (batch_size, max_seq_len, feat_dim)')
+    _, ends, _ = _segment_scan(segment_lens, x.shape[0])
+    if x.requires_grad and torch.is_grad_enabled():
+        return _SegmentEndsFn.apply(x, ends)
+    return _segment_ends_launch(x, ends)
+
+
+def _split_launch(x, ends, L):
     x, sb, st, row_bytes = _rows3(x, 'sequence_feature')
     B, T, D = x.shape
-    lens, ends, summary = _segment_scan(segment_lens, B)
-    S = lens.shape[1]
-    if max_segment_len is None:
-        if int(summary[1].item()):
-            raise ValueError('segment_lens may not contain negative values.')
-        max_segment_len = int(lens.max().item()) if lens.numel() else 0     # the reference syncs here too (utils.py:256)
-    L = int(max_segment_len)
+    S = ends.shape[1]
     out = torch.empty((B, S, L, D), dtype=x.dtype, device=x.device)
     with _device_of(x):
         check(lib.mg_split_to_segments(_ptr(x), sb, st, _ptr(ends), _ptr(out), B, S, L, T, row_bytes, _stream()),
               'mg_split_to_segments')
     return out
+
+
+class _SplitToSegmentsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, ends, L):
+        ctx.save_for_backward(ends)
+        ctx.shape, ctx.L = tuple(x.shape), L
+        return _split_launch(x, ends, L)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (ends,) = ctx.saved_tensors
+        if ctx.L == 0:
+            return torch.zeros(ctx.shape, dtype=grad.dtype, device=grad.device), None, None
+        return _segments_bwd(grad, ends, ctx.shape, ctx.L), None, None
+
+
+def split_to_segments(x, segment_lens, max_segment_len=None):
+    """``out[b, s, j] = x[b, begin_s + j]`` for ``j < len_s`` else zero; ``(B, S, longest segment, D)``.  Differentiable."""
+    _require_cuda(x, 'sequence_feature')
+    if x.dim() != 3:
+        raise ValueError('sequence_feature must have shape (batch_size, max_seq_len, feat_dim)')
+    lens, ends, summary = _segment_scan(segment_lens, x.shape[0])
+    if max_segment_len is None:
+        if int(summary[1].item()):
+            raise ValueError('segment_lens may not contain negative values.')
+        max_segment_len = int(lens.max().item()) if lens.numel() else 0     # the reference syncs here too (utils.py:256)
+    L = int(max_segment_len)
+    if x.requires_grad and torch.is_grad_enabled():
+        return _SplitToSegmentsFn.apply(x, ends, L)
+    return _split_launch(x, ends, L)
