@@ -64,13 +64,20 @@ def mg():
     return morgana_b200
 
 
-def _voiced_initial_state(model):
-    """Random initial weights predict "unvoiced" almost everywhere; widen the V/UV logit so LF0_RMSE_Hz has frames to count."""
+def _voiced_initial_state(model, features):
+    """Random initial weights predict one V/UV class for every frame; centre and widen the V/UV logit on these features (one
+    CPU forward pass of the unmodified model) so that LF0_RMSE_Hz has voiced frames to count and unvoiced ones to skip."""
     state = {k: v.clone() for k, v in model.state_dict().items()}
     linear_indices = [int(m.group(1)) for m in (re.match(r'^layers\.(\d+)\.weight$', k) for k in state) if m]
-    w = state['layers.%d.weight' % max(linear_indices)]                 # the output layer: columns lf0 | vuv | mcep | bap
+    last = max(linear_indices)                                             # the output layer: columns lf0 | vuv | mcep | bap
+    w, b = state['layers.%d.weight' % last], state['layers.%d.bias' % last]
     if w.shape[0] > 3:
+        with torch.no_grad(), H.cpu_lengths():
+            prob = model.predict(features)['vuv']
+        valid = torch.arange(prob.shape[1])[None, :] < features['n_frames'][:, None]
+        logit = torch.logit(prob[:, :, 0][valid].double())
         w[3] *= 40.
+        b[3] = 40. * (b[3] - float(logit.median()))
     return state
 
 
@@ -80,7 +87,7 @@ def _run_three_arms(morgana, mg, module_name, class_name, features, params, **mo
     unpatched = ref_loader.load_model_module_as(module_name, 'ref_models_unpatched_' + module_name)
     cls = getattr(unpatched, class_name)
     cpu_model = H.build_model(morgana, cls, params, 'cpu', **model_kwargs)
-    state = _voiced_initial_state(cpu_model)
+    state = _voiced_initial_state(cpu_model, features)
     cpu_model.load_state_dict(state)
     arms = {'oracle': H.forward_backward(cpu_model, features)}
     cuda_features = H.to_device(features, 'cuda')
@@ -182,7 +189,7 @@ def test_experiment_builder_train_epoch_with_ema_on_the_kernels(morgana, mg):
     batches = [H.make_features(batch_size=4, seed=100 + i, params=params) for i in range(3)]
     unpatched = ref_loader.load_model_module_as('RNN_SPSS', 'ref_models_unpatched_train')
     seed_model = H.build_model(morgana, unpatched.LSTMAcousticModel, params, 'cpu', output_dims=H.OUTPUT_DIMS_187, num_layers=1)
-    state = _voiced_initial_state(seed_model)
+    state = _voiced_initial_state(seed_model, batches[0])
     cpu = _train(morgana, unpatched, params, 'cpu', state, batches, 0.999)
     stock = _train(morgana, unpatched, params, 'cuda', state, batches, 0.999)
     mg.patch(morgana)
