@@ -15,7 +15,7 @@ LIB_DIR = os.path.join(PKG_DIR, 'lib')
 LIB_PATH = os.path.join(LIB_DIR, 'libmorgana_b200.so')
 INCLUDE = os.path.join(REPO_ROOT, 'include')
 
-SOURCES = ['mg_core.cu', 'mg_scan.cu', 'mg_upsample.cu', 'mg_collate.cu', 'mg_normalise.cu', 'mg_reduce.cu', 'mg_objective.cu', 'mg_ema.cu',
+SOURCES = ['mg_core.cu', 'mg_scan.cu', 'mg_upsample.cu', 'mg_collate.cu', 'mg_normalise.cu', 'mg_reduce.cu', 'mg_objective.cu', 'mg_objective_stream.cu', 'mg_ema.cu',
            'mg_linear.cu', 'mg_linear_bwd.cu', 'mg_mlpg.cu', 'mg_segments.cu', 'mg_kld.cu']
 
 NVCC_FLAGS = [

@@ -1,0 +1,795 @@
+// K4b, persistent row-stream form -- the whole-row masked objective (models/RNN_SPSS.py:120-139: 3 x losses.mse + losses.bce
+// with the gradient, and the four streaming metrics; morgana/losses.py:29-56, morgana/metrics.py:383-394, 597-694) for
+// contiguous (B, T, D <= 224) float32 tensors whose bases are 16-byte aligned.  Same results contract as mg_objective.cu.
+//
+// Why a second form.  The chunk-per-CTA kernel spends ~20 us of a 150 us launch in per-CTA work that does not scale with
+// the bytes (column-program set-up, barrier init, special-column phase, slot sums, two ticket levels per 131-row chunk) and
+// keeps only one 12 KB stage per CTA in flight while it computes (profiles/r1b_summary.md, r1d_summary.md).  Here:
+//
+//   * The (B*T, D) row space is cut into STAGES of 8 rows (8*D floats = 32*D bytes: 16-byte aligned for every D, and a
+//     whole number of rows, so thread t always sees column t).  One persistent CTA per half SM owns a contiguous range of
+//     stages chosen on the device so that every CTA moves the same number of bytes (cost 3 per valid row: two reads + one
+//     gradient write; 1 per padding row: the zero gradient).
+//   * Warp roles.  A producer lane keeps a ring of stages in flight with cp.async.bulk global->shared (TMA engine, SASS
+//     UBLKCP) on "full" mbarriers and refills a slot as soon as the consumer warps have arrived on its "empty" mbarrier -- no
+//     CTA-wide barrier inside the stream, the bytes in flight live in shared memory (ring x 12 KB per CTA).  Padding-only
+//     stages cost it one bulk store from a zero tile and are never loaded.  ceil(D/32) consumer warps own one column per
+//     thread: 16 shared-memory loads in flight, squared error into an fp32 partial per stage (row order), one fp64 add per
+//     stage, gradient straight from registers.  Runs of fully valid stages of one utterance are a tight loop without any
+//     per-stage classification.
+//   * "Special" columns (BCE, exp, equality, per-frame root, voiced weighting: 3 of 187, ~100 instructions per element) would
+//     make the warp that owns them a straggler.  Instead consumer warp w adopts special column w: as each stage passes, eight
+//     of its lanes park that column's operands (and the mask / group columns they depend on, same row of the stage) in
+//     registers; after four stages the warp holds 32 rows, lane = row, and evaluates them on one code path.  (A first version
+//     with a dedicated warp evaluating 8 rows x 3 columns per stage ran at 2.2 us per stage -- a dependent chain of ~500
+//     instructions in one warp -- and was slower than the kernel it replaces; profiles/r2b_summary.md.)
+//   * Accumulators are carried across stages AND utterances in registers: per thread (sum, sum / n_b) of its loss slot and the
+//     sum of its metric slot, flushed into the weighted form only when the utterance changes.  One CTA-level reduction at the
+//     end of the kernel, one ticket, and the last CTA adds the per-CTA partials in index order.
+//
+// Determinism: the stage -> CTA assignment is a pure function of (B, T, seq_len, grid), every sum has a fixed order, no
+// floating-point atomics.
+#include <stdlib.h>
+#include <string.h>
+
+#include "mg_objective_common.cuh"
+
+namespace {
+
+using namespace mgobj;
+
+constexpr int kRows = 8;            // rows per stage
+constexpr int kMaxRing = 16;
+constexpr int kMaxB = 1024;         // utterance lengths and the cost prefix live in shared memory
+constexpr int kSpPerWarp = 1;       // special columns a consumer warp evaluates in batches of 32 rows
+constexpr int kMaxSp = 16;          // batched special columns per CTA (any further one is evaluated by its own thread)
+constexpr int kMaxWarps = 8;        // 7 consumer warps (D <= 224) + producer: 256 threads, 128 registers at two CTAs per SM
+constexpr int kMaxCtas = 1024;      // bounds the per-CTA partials in the workspace
+
+struct StreamParams {
+  MgFinishSlot slots[MG_MAX_TERMS];
+  const float* pred;
+  const float* target;
+  float* grad;
+  const float* grad_scale_dev;
+  const mg_column* cols;
+  const int64_t* seq_len;
+  unsigned int* ticket;
+  double2* partials;     // [grid][n_slots][2]: (sum, sum / n_b), (weighted count, -)
+  int64_t T;
+  int D, B, n_slots, ring, n_consumer_warps;
+  int cost_valid, cost_pad;   // relative cost of a valid / padding row in the stage -> CTA partition
+  int debug;   // tuning experiments only (MG_OBJ_DEBUG): 1 consumers skip the arithmetic, 2 no special columns, 4 no zero stores,
+               // 8 per-CTA %globaltimer stamps (entry, range known, first stage ready, stream done, partials written) -> `stamps`
+  unsigned long long* stamps;
+};
+
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mg_smem_addr(bar)) : "memory");
+}
+
+// Walks the stages of a CTA's range; every role keeps its own copy and sees the same sequence.
+struct StageCursor {
+  int64_t stage, stage_end;   // current stage and end of the CTA's range
+  int64_t total_rows;
+  int64_t T;
+  int b;                      // utterance of the stage's first row
+  int64_t t0;                 // that row's index inside the utterance
+  __device__ __forceinline__ void init(int64_t s_lo, int64_t s_hi, int64_t T_, int64_t total_rows_) {
+    stage = s_lo; stage_end = s_hi; T = T_; total_rows = total_rows_;
+    const int64_t r = s_lo * kRows;
+    b = static_cast<int>(r / T_);
+    t0 = r - static_cast<int64_t>(b) * T_;
+  }
+  __device__ __forceinline__ bool done() const { return stage >= stage_end; }
+  __device__ __forceinline__ void next() {
+    ++stage;
+    t0 += kRows;
+    while (t0 >= T) { t0 -= T; ++b; }
+  }
+  __device__ __forceinline__ void advance(int64_t n) {
+    stage += n;
+    t0 += n * kRows;
+    while (t0 >= T) { t0 -= T; ++b; }
+  }
+  // consecutive FULL stages (8 valid rows of utterance b) from here, inside the CTA's range
+  __device__ __forceinline__ int64_t full_run(const int* s_nb) const {
+    const int64_t n_b = s_nb[b];
+    if (t0 + kRows > n_b) return 0;
+    const int64_t run = (n_b - t0) / kRows, cap = stage_end - stage;
+    return run < cap ? run : cap;
+  }
+  // consecutive PAD stages (8 padding rows of utterance b) from here, inside the CTA's range
+  __device__ __forceinline__ int64_t pad_run(const int* s_nb) const {
+    if (t0 < s_nb[b] || t0 + kRows > T) return 0;
+    const int64_t run = (T - t0) / kRows, cap = stage_end - stage;
+    return run < cap ? run : cap;
+  }
+  // rows of this stage that exist (8 except for the last stage of the tensor)
+  __device__ __forceinline__ int rows() const {
+    const int64_t left = total_rows - stage * kRows;
+    return left < kRows ? static_cast<int>(left) : kRows;
+  }
+};
+
+enum StageKind { STAGE_FULL = 0, STAGE_MIXED = 1, STAGE_PAD = 2, STAGE_TAIL = 3 };
+
+// FULL: 8 valid rows of one utterance.  PAD: 8 padding rows (no load; zero gradient).  TAIL: the tensor's last, short stage
+// (its byte count need not be a multiple of 16: read from global memory).  MIXED: anything else that has 8 rows.
+__device__ __forceinline__ int classify(const StageCursor& c, const int* s_nb, int B) {
+  if (c.rows() < kRows) return STAGE_TAIL;
+  const int64_t n_b = s_nb[c.b];
+  if (c.t0 + kRows <= c.T) {
+    if (c.t0 + kRows <= n_b) return STAGE_FULL;
+    if (c.t0 >= n_b) return STAGE_PAD;
+    return STAGE_MIXED;
+  }
+  // the stage runs into the next utterance(s): padding only if every row is padding
+  int b = c.b;
+  int64_t t = c.t0;
+  for (int u = 0; u < kRows; ++u) {
+    if (t < s_nb[b]) return STAGE_MIXED;
+    if (++t >= c.T) { t = 0; ++b; }
+  }
+  return STAGE_PAD;
+}
+
+// One element of a special column from values held in registers.  `root_acc`: squared error summed over the column's
+// ROOT_SQDIFF group (only read when the column leads a group of more than one column).
+template <bool GRAD>
+__device__ __forceinline__ void special_value(const mg_column& sc, float pv, float yv, float mask_v, float root_acc, float* g,
+                                              float w_row, double& l_acc, double& m_acc, double& n_acc) {
+  const bool has_mask = sc.mask_col != MG_COL_NONE;
+  mg_column prog = sc;
+  prog.width = 1;
+  if (sc.metric_kind == MG_RED_ROOT_SQDIFF && sc.width > 1) {
+    float root = sqrtf(root_acc);                     // feature-axis sum of the group (metrics.py:661), then the root (:662)
+    if (has_mask) {
+      const float voiced = mask_v > 0.5f ? 1.f : 0.f;
+      root = __fmul_rn(root, voiced);
+      n_acc += static_cast<double>(voiced);
+    }
+    m_acc += static_cast<double>(root);
+    prog.metric_kind = MG_COL_NONE;   // the loss part of the column (if any) still goes through general_one
+  }
+  general_one<GRAD>(prog, pv, yv, mask_v, has_mask, nullptr, nullptr, g, w_row, l_acc, m_acc, n_acc);
+}
+
+__device__ __forceinline__ float root_group_acc(const mg_column& sc, int k, const float* row_p, const float* row_y) {
+  const float d0 = __fsub_rn(row_y[k], row_p[k]);
+  float acc = __fmul_rn(d0, d0);
+  for (int j = 1; j < sc.width; ++j) {
+    const float dj = __fsub_rn(row_y[k + j], row_p[k + j]);
+    acc = __fadd_rn(acc, __fmul_rn(dj, dj));
+  }
+  return acc;
+}
+
+template <bool GRAD>
+__global__ void __launch_bounds__(kMaxWarps * 32, 2)
+objective_stream_kernel(const __grid_constant__ StreamParams prm) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];   // [ring x (pred stage | target stage)] [zero tile]
+  __shared__ __align__(8) uint64_t s_full[kMaxRing], s_empty[kMaxRing];
+  __shared__ mg_column s_cols[256];
+  __shared__ int s_nb[kMaxB];
+  __shared__ int s_pref[kMaxB + 1];          // exclusive prefix of the per-utterance cost
+  __shared__ int s_sp_col[kMaxSp];
+  __shared__ int s_n_sp, s_has_empty;
+  __shared__ int64_t s_range[2];
+  __shared__ long long s_wvalid[kMaxWarps];
+  __shared__ int s_wsum[kMaxWarps];
+
+  __shared__ double s_slot[MG_MAX_TERMS][3];
+  __shared__ bool s_is_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int D = prm.D, B = prm.B, ring = prm.ring, n_cw = prm.n_consumer_warps;
+  const int producer_warp = n_cw;
+  const int64_t T = prm.T;
+  const int64_t total_rows = static_cast<int64_t>(B) * T;
+  const int stage_elems = kRows * D;
+  const uint32_t stage_bytes = static_cast<uint32_t>(stage_elems) * 4u;
+  float* s_ring = reinterpret_cast<float*>(smem_raw);
+  float* s_zero = s_ring + static_cast<size_t>(ring) * 2 * stage_elems;
+  const int kCostValid = prm.cost_valid, kCostPad = GRAD ? prm.cost_pad : 0;
+
+  const bool stamp = (prm.debug & 8) != 0;
+  if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 0] = global_ns();
+  // ---- prologue: column programs, utterance lengths, cost prefix, this CTA's stage range -----------------------------------
+  for (int k = tid; k < D; k += blockDim.x) s_cols[k] = prm.cols[k];
+  for (int b = tid; b < B; b += blockDim.x) s_nb[b] = static_cast<int>(mg_valid_frames(prm.seq_len, b, T));
+  if (GRAD) for (int i = tid; i < stage_elems; i += blockDim.x) s_zero[i] = 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < ring; ++i) { mg_mbar_init(&s_full[i], 1); mg_mbar_init(&s_empty[i], static_cast<uint32_t>(n_cw)); }
+    mg_mbar_fence_init();
+  }
+  __syncthreads();
+  if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 8] = global_ns();
+  {
+    // exclusive prefix of the per-utterance cost, by the whole CTA: a shuffle scan per warp, warp totals through shared memory
+    const int nt = blockDim.x, n_warps = nt >> 5;
+    int carry = 0, empty = 0;
+    long long valid = 0;
+    for (int base = 0; base < B; base += nt) {
+      const int b = base + tid;
+      const int n = b < B ? s_nb[b] : 0;
+      const int cost = b < B ? kCostValid * n + kCostPad * (static_cast<int>(T) - n) : 0;
+      int incl = cost;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(MG_FULL_MASK, incl, o);
+        if (lane >= o) incl += v;
+      }
+      if (lane == 31) s_wsum[warp] = incl;
+      empty |= (b < B && n == 0) ? 1 : 0;
+      valid += n;
+      __syncthreads();
+      int before = 0, total = 0;
+      for (int w = 0; w < n_warps; ++w) { const int v = s_wsum[w]; total += v; if (w < warp) before += v; }
+      if (b < B) s_pref[b] = carry + before + incl - cost;
+      carry += total;
+      __syncthreads();
+    }
+    empty = __syncthreads_or(empty);
+    valid = mg_warp_sum(valid);
+    if (lane == 0) s_wvalid[warp] = valid;
+    if (tid == 0) { s_pref[B] = carry; s_has_empty = empty; }
+  }
+  if (warp == producer_warp) {
+    // special columns in column order; the first kSpPerWarp * n_cw of them are evaluated in batches (below), any further one
+    // by the thread that owns the column
+    int n_sp = 0;
+    for (int c0 = 0; c0 < D; c0 += 32) {
+      const int k = c0 + lane;
+      const bool special = k < D && !column_is_simple(s_cols[k]);
+      const unsigned bits = __ballot_sync(MG_FULL_MASK, special);
+      if (special) {
+        const int idx = n_sp + __popc(bits & ((1u << lane) - 1));
+        if (idx < kMaxSp) s_sp_col[idx] = k;
+      }
+      n_sp += __popc(bits);
+    }
+    const int cap = kSpPerWarp * n_cw < kMaxSp ? kSpPerWarp * n_cw : kMaxSp;
+    if (lane == 0) s_n_sp = n_sp < cap ? n_sp : cap;
+  }
+  if (GRAD) mg_fence_proxy_async_smem();   // the zero tile is read by the bulk-copy engine
+  __syncthreads();
+  if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 9] = global_ns();
+  if (tid == 0 || tid == 32) {
+    // cost position -> row (valid rows first inside an utterance), rounded up to a stage; the same function at both ends of
+    // every CTA's range, so the ranges tile the stages exactly.  Two threads, one end each.
+    const int e = tid >> 5;
+    const unsigned total_cost = static_cast<unsigned>(s_pref[B]);
+    const int64_t n_stages = (total_rows + kRows - 1) / kRows;
+    const unsigned c = blockIdx.x + e;
+    int64_t stage;
+    if (c >= gridDim.x) stage = n_stages;
+    else if (c == 0) stage = 0;
+    else {
+      // floor(total_cost * c / grid) up to the rounding of one double division: any monotone function of c works
+      const unsigned x = static_cast<unsigned>(static_cast<double>(total_cost) * static_cast<double>(c) / static_cast<double>(gridDim.x));
+      int lo = 0, hi = B;                      // last b with pref[b] <= x
+      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (static_cast<unsigned>(s_pref[mid]) <= x) lo = mid; else hi = mid; }
+      const unsigned y = x - static_cast<unsigned>(s_pref[lo]), n = static_cast<unsigned>(s_nb[lo]);
+      const unsigned pad_div = kCostPad > 0 ? static_cast<unsigned>(kCostPad) : 1u;
+      unsigned r_in = y < static_cast<unsigned>(kCostValid) * n ? y / static_cast<unsigned>(kCostValid)
+                                                                : (kCostPad > 0 ? n + (y - static_cast<unsigned>(kCostValid) * n) / pad_div
+                                                                                : static_cast<unsigned>(T));
+      if (r_in > static_cast<unsigned>(T)) r_in = static_cast<unsigned>(T);
+      stage = (static_cast<int64_t>(lo) * T + r_in + kRows - 1) / kRows;
+      if (stage > n_stages) stage = n_stages;
+    }
+    s_range[e] = stage;
+  }
+  __syncthreads();
+  const int64_t s_lo = s_range[0], s_hi = s_range[1];
+  if (stamp && tid == 0) { prm.stamps[blockIdx.x * 16 + 1] = global_ns(); prm.stamps[blockIdx.x * 16 + 5] = static_cast<unsigned long long>(s_hi - s_lo); }
+  const int n_sp = s_n_sp;
+  double scale = 1.;
+  if (GRAD && prm.grad_scale_dev != nullptr) scale = static_cast<double>(__ldg(prm.grad_scale_dev));
+  const double scale_over_b = scale / static_cast<double>(B);
+
+  // what each thread brings to the CTA reduction at the end: (slot, sum, weighted sum, count) contributions of its own column
+  // [0, 1] and of the special columns its warp evaluates [2 ..]
+  constexpr int kOut = 2 + 2 * kSpPerWarp;
+  int out_slot[kOut];
+  double out_sum[kOut], out_w[kOut], out_n[kOut];
+#pragma unroll
+  for (int e = 0; e < kOut; ++e) { out_slot[e] = -1; out_sum[e] = out_w[e] = out_n[e] = 0.; }
+
+  if (warp == producer_warp) {
+    // ---- producer: bulk loads into the ring, zero gradients of padding-only stages ----------------------------------------
+    if (lane == 0) {
+      StageCursor cur;
+      cur.init(s_lo, s_hi, T, total_rows);
+      const uint64_t policy = mg_policy_evict_first();
+      int slot = 0;
+      uint32_t phase = 1;       // parity to wait for on the slot's "empty" barrier; the first pass over the ring does not wait
+      bool first_pass = true;
+      auto load_stage = [&](int64_t stage) {
+        if (!first_pass) mg_mbar_wait(&s_empty[slot], phase);
+        const int64_t off = stage * stage_elems;
+        float* dst = s_ring + static_cast<size_t>(slot) * 2 * stage_elems;
+        mg_mbar_expect_tx(&s_full[slot], 2 * stage_bytes);
+        mg_bulk_load(dst, prm.pred + off, stage_bytes, &s_full[slot]);
+        mg_bulk_load(dst + stage_elems, prm.target + off, stage_bytes, &s_full[slot]);
+        if (++slot == ring) { slot = 0; phase ^= 1u; first_pass = false; }
+      };
+      while (!cur.done()) {
+        int64_t run = cur.full_run(s_nb);
+        if (run > 0) {                                   // a run of fully valid stages of one utterance
+          for (int64_t i = 0; i < run; ++i) load_stage(cur.stage + i);
+          cur.advance(run);
+          continue;
+        }
+        run = cur.pad_run(s_nb);
+        if (run > 0) {                                   // a run of padding-only stages: zero gradient, nothing to load
+          if (GRAD && !(prm.debug & 4)) {
+            for (int64_t i = 0; i < run; ++i) {
+              mg_bulk_store_hint(prm.grad + (cur.stage + i) * stage_elems, mg_smem_addr(s_zero), stage_bytes, policy);
+              mg_bulk_commit();
+            }
+          }
+          cur.advance(run);
+          continue;
+        }
+        const int kind = classify(cur, s_nb, B);         // boundary stages
+        if (kind == STAGE_PAD) {
+          if (GRAD && !(prm.debug & 4)) { mg_bulk_store_hint(prm.grad + cur.stage * stage_elems, mg_smem_addr(s_zero), stage_bytes, policy); mg_bulk_commit(); }
+        } else if (kind != STAGE_TAIL) {
+          load_stage(cur.stage);
+        }
+        cur.next();
+      }
+      if (GRAD) mg_bulk_wait_read<0>();   // the zero tile has been read by every bulk store (their writes complete asynchronously)
+    }
+  } else {
+    // ---- consumers: thread t owns column t; warp w also evaluates special columns w, w + n_cw, ... in batches of 32 rows ----
+    const bool active = tid < D;
+    const mg_column col = active ? s_cols[tid] : s_cols[0];
+    const bool simple = active && column_is_simple(col);
+    bool served = false;      // special column evaluated in batches (the first kSpPerWarp * n_cw of them)
+    for (int i = 0; i < n_sp; ++i) served = served || s_sp_col[i] == tid;
+    const bool own_special = active && !simple && !served;   // any further special column: its own thread evaluates it
+    const bool use_loss = (simple || own_special) && col.loss_kind != MG_COL_NONE;
+    const bool use_metric = (simple || own_special) && col.metric_kind != MG_COL_NONE;
+    const bool loss_sq = col.loss_kind == MG_RED_SQDIFF, metric_sq = col.metric_kind == MG_RED_SQDIFF;
+    const bool hot = simple && use_loss && loss_sq && (metric_sq || !use_metric);
+    int b_cur = -1;
+    double n_cur = 1.;
+    float w_row = 0.f, w2 = 0.f;
+    double cur_l = 0., cur_m = 0., cur_n = 0., sum_l = 0., wsum_l = 0., sum_m = 0., sum_n = 0.;
+    auto enter = [&](int b) {   // the utterance changes: fold the finished one into the weighted sums
+      if (b == b_cur) return;
+      sum_l += cur_l; wsum_l += cur_l / n_cur; sum_m += cur_m; sum_n += cur_n;
+      cur_l = cur_m = cur_n = 0.;
+      b_cur = b;
+      n_cur = b >= 0 ? static_cast<double>(s_nb[b]) : 1.;
+      w_row = use_loss ? static_cast<float>(static_cast<double>(col.loss_weight) * (scale_over_b / n_cur)) : 0.f;
+      w2 = __fmul_rn(2.f, w_row);
+    };
+    // rows of a stage one at a time, from shared or global memory (mixed / tail stages and non-squared programs)
+    auto slow_rows = [&](const float* sp, const float* sy, float* g, const StageCursor& cur, int n_rows) {
+      int b = cur.b;
+      int64_t t = cur.t0;
+      for (int u = 0; u < n_rows; ++u) {
+        const bool valid = t < s_nb[b];
+        if (valid && own_special) {
+          enter(b);
+          const float* row_p = sp + u * D - tid;
+          const float* row_y = sy + u * D - tid;
+          const float root = (col.metric_kind == MG_RED_ROOT_SQDIFF && col.width > 1) ? root_group_acc(col, tid, row_p, row_y) : 0.f;
+          special_value<GRAD>(col, row_p[tid], row_y[tid], col.mask_col != MG_COL_NONE ? row_p[col.mask_col] : 1.f, root,
+                              GRAD ? g + u * D : nullptr, w_row, cur_l, cur_m, cur_n);
+        } else if (valid && simple) {
+          enter(b);
+          const float d = __fsub_rn(sp[u * D], sy[u * D]);
+          const float sq = __fmul_rn(d, d), ab = fabsf(d);
+          if (use_loss) cur_l += static_cast<double>(loss_sq ? sq : ab);
+          if (use_metric) cur_m += static_cast<double>(metric_sq ? sq : ab);
+          if (GRAD) __stcs(g + u * D, __fmul_rn(simple_slope(loss_sq, d), w_row));
+        } else if (GRAD && !valid) {
+          __stcs(g + u * D, 0.f);      // padding rows, every column (special ones included)
+        }
+        if (++t >= T) { t = 0; ++b; }
+      }
+    };
+
+    // -- special columns of this warp: operands of 32 rows (four stages) are parked in registers, lane = row, then every
+    // column is evaluated by the whole warp on one code path (~100 instructions per element: BCE, exp, root ...) ------------
+    int n_my = 0;
+    int my_k[kSpPerWarp];
+    mg_column my_sc[kSpPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSpPerWarp; ++j) {
+      const int q = warp + j * n_cw;
+      my_k[j] = 0;
+      my_sc[j] = s_cols[0];
+      if (q < n_sp && !(prm.debug & 2)) { my_k[j] = s_sp_col[q]; my_sc[j] = s_cols[my_k[j]]; n_my = j + 1; }
+    }
+    float b_pv[kSpPerWarp], b_yv[kSpPerWarp], b_mv[kSpPerWarp], b_root[kSpPerWarp];
+    int b_utt = -1;               // utterance of this lane's parked row, -1: nothing parked
+    int64_t b_off = 0;            // float offset of that row in the tensors
+    double sp_sum_l[kSpPerWarp], sp_w_l[kSpPerWarp], sp_sum_m[kSpPerWarp], sp_sum_n[kSpPerWarp];
+#pragma unroll
+    for (int j = 0; j < kSpPerWarp; ++j) { sp_sum_l[j] = sp_w_l[j] = sp_sum_m[j] = sp_sum_n[j] = 0.; b_pv[j] = b_yv[j] = b_mv[j] = b_root[j] = 0.f; }
+    int batch_pos = 0;
+    auto park = [&](const float* stage_p, const float* stage_y, const StageCursor& cur, int64_t off, int kind) {
+      // lanes [8 * batch_pos, 8 * batch_pos + 8) take the stage's rows
+      const int u = lane & 7;
+      if ((lane >> 3) == batch_pos) {
+        int b = cur.b;
+        int64_t t = cur.t0 + u;
+        if (kind != STAGE_FULL) while (t >= T && b < B - 1) { t -= T; ++b; }
+        const bool valid = kind == STAGE_FULL || (u < cur.rows() && t < T && t < s_nb[b]);
+        b_utt = valid ? b : -1;
+        b_off = off + static_cast<int64_t>(u) * D;
+        if (valid) {
+          const float* row_p = stage_p + u * D;
+          const float* row_y = stage_y + u * D;
+#pragma unroll
+          for (int j = 0; j < kSpPerWarp; ++j) {
+            if (j < n_my) {
+              const mg_column& sc = my_sc[j];
+              b_pv[j] = row_p[my_k[j]];
+              b_yv[j] = row_y[my_k[j]];
+              b_mv[j] = sc.mask_col != MG_COL_NONE ? row_p[sc.mask_col] : 1.f;
+              b_root[j] = (sc.metric_kind == MG_RED_ROOT_SQDIFF && sc.width > 1) ? root_group_acc(sc, my_k[j], row_p, row_y) : 0.f;
+            }
+          }
+        }
+      }
+      ++batch_pos;
+    };
+    auto evaluate = [&]() {
+      if (b_utt >= 0) {
+        const double n_b = static_cast<double>(s_nb[b_utt]);
+#pragma unroll
+        for (int j = 0; j < kSpPerWarp; ++j) {
+          if (j < n_my) {   // warp-uniform
+            const mg_column& sc = my_sc[j];
+            const float w = static_cast<float>(static_cast<double>(sc.loss_weight) * (scale_over_b / n_b));
+            double l = 0., m = 0., n = 0.;
+            special_value<GRAD>(sc, b_pv[j], b_yv[j], b_mv[j], b_root[j], GRAD ? prm.grad + b_off + my_k[j] : nullptr, w, l, m, n);
+            sp_sum_l[j] += l; sp_w_l[j] += l / n_b; sp_sum_m[j] += m; sp_sum_n[j] += n;
+          }
+        }
+      }
+      b_utt = -1;
+      batch_pos = 0;
+    };
+
+    // one fully valid stage of utterance cur.b in ring slot `slot` (the hot path)
+    const bool generic_lane = active && !hot && !served;    // absolute-error programs, metric-only columns, a 7th special column ...
+    auto full_stage = [&](const float* stage_p, int64_t off, const StageCursor& cur) {
+      if (hot && !(prm.debug & 1)) {
+        const float* sp = stage_p + tid;
+        const float* sy = sp + stage_elems;
+        float pv[kRows], yv[kRows];
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) { pv[u] = sp[u * D]; yv[u] = sy[u * D]; }    // 16 loads in flight, then the arithmetic
+        float part = 0.f;     // 8 rows in fp32, row order, then one fp64 add
+        float* g = GRAD ? prm.grad + off + tid : nullptr;
+#pragma unroll
+        for (int u = 0; u < kRows; ++u) {
+          const float d = __fsub_rn(pv[u], yv[u]);
+          part = __fadd_rn(part, __fmul_rn(d, d));
+          if (GRAD) __stcs(g + u * D, __fmul_rn(d, w2));
+        }
+        cur_l += static_cast<double>(part);
+        if (use_metric) cur_m += static_cast<double>(part);
+      } else if (generic_lane && !(prm.debug & 1)) {
+        slow_rows(stage_p + tid, stage_p + stage_elems + tid, GRAD ? prm.grad + off + tid : nullptr, cur, kRows);
+      }
+    };
+
+    StageCursor cur;
+    cur.init(s_lo, s_hi, T, total_rows);
+    int slot = 0;
+    uint32_t phase = 0;
+    int n_loaded = 0;    // stages that went through the ring (debug stamps)
+    while (!cur.done()) {
+      int64_t run = cur.full_run(s_nb);
+      if (run > 0) {
+        n_loaded += static_cast<int>(run);
+        enter(cur.b);
+        for (int64_t i = 0; i < run; ++i) {
+          const int64_t off = cur.stage * stage_elems;
+          mg_mbar_wait(&s_full[slot], phase);
+          if (stamp && tid == 0 && prm.stamps[blockIdx.x * 16 + 2] == 0) prm.stamps[blockIdx.x * 16 + 2] = global_ns();
+          const float* stage_p = s_ring + static_cast<size_t>(slot) * 2 * stage_elems;
+          full_stage(stage_p, off, cur);
+          if (n_my > 0) park(stage_p, stage_p + stage_elems, cur, off, STAGE_FULL);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&s_empty[slot]);   // the stage's operands are in registers: the slot may be refilled
+          if (++slot == ring) { slot = 0; phase ^= 1u; }
+          if (batch_pos == 4) evaluate();
+          cur.stage += 1;
+          cur.t0 += kRows;
+        }
+        cur.advance(0);
+        continue;
+      }
+      run = cur.pad_run(s_nb);
+      if (run > 0) { cur.advance(run); continue; }
+      const int kind = classify(cur, s_nb, B);
+      if (kind == STAGE_PAD) { cur.next(); continue; }
+      const int64_t off = cur.stage * stage_elems;
+      float* g = GRAD ? prm.grad + off + tid : nullptr;
+      if (kind == STAGE_TAIL) {
+        if (active) slow_rows(prm.pred + off + tid, prm.target + off + tid, g, cur, cur.rows());
+        if (n_my > 0) { park(prm.pred + off, prm.target + off, cur, off, kind); if (batch_pos == 4) evaluate(); }
+        cur.next();
+        continue;
+      }
+      ++n_loaded;
+      mg_mbar_wait(&s_full[slot], phase);
+      const float* stage_p = s_ring + static_cast<size_t>(slot) * 2 * stage_elems;
+      if (active && !(prm.debug & 1)) {
+        if ((hot || served) && T >= kRows) {
+          // a boundary stage is at most: valid rows of utterance b | padding | valid rows of utterance b + 1 | padding
+          const int rows_a = static_cast<int>(min(static_cast<int64_t>(kRows), T - cur.t0));
+          const int valid_a = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(rows_a), s_nb[cur.b] - cur.t0)));
+          const int valid_b = rows_a < kRows ? min(kRows - rows_a, s_nb[cur.b + 1]) : 0;
+          const float* sp = stage_p + tid;
+          const float* sy = sp + stage_elems;
+          auto valid_rows = [&](int u0, int u1, int b) {
+            if (u1 <= u0 || !hot) return;
+            enter(b);
+            float part = 0.f;
+            for (int u = u0; u < u1; ++u) {
+              const float d = __fsub_rn(sp[u * D], sy[u * D]);
+              part = __fadd_rn(part, __fmul_rn(d, d));
+              if (GRAD) __stcs(g + u * D, __fmul_rn(d, w2));
+            }
+            cur_l += static_cast<double>(part);
+            if (use_metric) cur_m += static_cast<double>(part);
+          };
+          valid_rows(0, valid_a, cur.b);
+          valid_rows(rows_a, rows_a + valid_b, cur.b + 1);
+          if (GRAD) {
+            for (int u = valid_a; u < rows_a; ++u) __stcs(g + u * D, 0.f);
+            for (int u = rows_a + valid_b; u < kRows; ++u) __stcs(g + u * D, 0.f);
+          }
+        } else {
+          slow_rows(stage_p + tid, stage_p + stage_elems + tid, g, cur, kRows);
+        }
+      }
+      if (n_my > 0) park(stage_p, stage_p + stage_elems, cur, off, kind);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_empty[slot]);
+      if (++slot == ring) { slot = 0; phase ^= 1u; }
+      if (batch_pos == 4) evaluate();
+      cur.next();
+    }
+    if (stamp && tid == 0) { prm.stamps[blockIdx.x * 16 + 3] = global_ns(); prm.stamps[blockIdx.x * 16 + 7] = static_cast<unsigned long long>(n_loaded); }
+    if (n_my > 0) evaluate();
+    enter(-2);   // fold the last utterance (b = -2 never matches)
+    if (use_loss) { out_slot[0] = col.loss_slot; out_sum[0] = sum_l; out_w[0] = wsum_l; }
+    if (use_metric) { out_slot[1] = col.metric_slot; out_sum[1] = sum_m; out_n[1] = sum_n; }
+#pragma unroll
+    for (int j = 0; j < kSpPerWarp; ++j) {
+      if (j < n_my) {
+        if (my_sc[j].loss_kind != MG_COL_NONE) { out_slot[2 + 2 * j] = my_sc[j].loss_slot; out_sum[2 + 2 * j] = sp_sum_l[j]; out_w[2 + 2 * j] = sp_w_l[j]; }
+        if (my_sc[j].metric_kind != MG_COL_NONE) { out_slot[3 + 2 * j] = my_sc[j].metric_slot; out_sum[3 + 2 * j] = sp_sum_m[j]; out_n[3 + 2 * j] = sp_sum_n[j]; }
+      }
+    }
+  }
+
+  // ---- one CTA-level reduction: contributions parked in shared memory, warp s sums slot s over them in index order with a
+  // fixed shuffle tree.  (Folding inside each warp with ballots + fp64 shuffles first was 3.7 us slower per launch.) ---------
+  {
+  __syncthreads();   // every role is done with the ring: it becomes the scratch of the reduction
+  const int n_entries = kOut * blockDim.x;
+  double* s_v = reinterpret_cast<double*>(smem_raw);           // [3][n_entries]
+  signed char* s_s = reinterpret_cast<signed char*>(s_v + 3 * n_entries);
+#pragma unroll
+  for (int e = 0; e < kOut; ++e) {
+    const int i = e * blockDim.x + tid;
+    s_v[i] = out_sum[e];
+    s_v[n_entries + i] = out_w[e];
+    s_v[2 * n_entries + i] = out_n[e];
+    s_s[i] = static_cast<signed char>(out_slot[e]);
+  }
+  __syncthreads();
+  const int n_warps = blockDim.x >> 5;
+  for (int slot = warp; slot < prm.n_slots; slot += n_warps) {
+    double a = 0., w = 0., n = 0.;
+    for (int i = lane; i < n_entries; i += 32) {
+      if (s_s[i] == slot) { a += s_v[i]; w += s_v[n_entries + i]; n += s_v[2 * n_entries + i]; }
+    }
+    a = mg_warp_sum(a); w = mg_warp_sum(w); n = mg_warp_sum(n);
+    if (lane == 0) { s_slot[slot][0] = a; s_slot[slot][1] = w; s_slot[slot][2] = n; }
+  }
+  __syncthreads();
+  }
+
+  // ---- ticket: the last CTA adds the per-CTA partials in index order and writes the result records.  The producer warp
+  // publishes: its threads have no gradient stores in flight, so their release fence does not wait for the CTA's stream of
+  // stores to drain (a fence in a consumer thread does). ------------------------------------------------------------------
+  if (warp == producer_warp) {
+    if (lane < prm.n_slots) {
+      double2* out = prm.partials + (static_cast<int64_t>(blockIdx.x) * prm.n_slots + lane) * 2;
+      out[0] = make_double2(s_slot[lane][0], s_slot[lane][1]);
+      out[1] = make_double2(s_slot[lane][2], 0.);
+      __threadfence();
+    }
+    __syncwarp();
+    if (lane == 0) {
+      if (stamp) prm.stamps[blockIdx.x * 16 + 4] = global_ns();
+      const bool last = atomicAdd(prm.ticket, 1u) == gridDim.x - 1;
+      if (last) __threadfence();     // acquire: the other threads read after the barrier below, through L2 (__ldcg)
+      s_is_last = last;
+    }
+  }
+  __syncthreads();
+  if (!s_is_last) return;
+  if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 10] = global_ns();
+  mg_term_result old;
+  memset(&old, 0, sizeof(old));
+  if (tid < prm.n_slots && prm.slots[tid].accumulate) old = *prm.slots[tid].result;   // in flight under the loads below
+  {
+    // partials [cta][slot]: `per` threads per slot, thread i of a slot takes CTAs i, i + per, ... (index order per thread, twelve
+    // records in flight); then the slot's threads are summed in thread order with a fixed shuffle tree
+    double* s_v = reinterpret_cast<double*>(smem_raw);           // [n_slots][3][per]
+    const int per = blockDim.x / prm.n_slots;                     // >= 18 (n_slots <= 12, >= 224 threads)
+    const int slot = tid / per, idx = tid - slot * per;
+    if (slot < prm.n_slots) {
+      double a = 0., w = 0., n = 0.;
+      for (unsigned c0 = idx; c0 < gridDim.x; c0 += 12 * per) {
+        double2 v0[12], v1[12];
+#pragma unroll
+        for (int j = 0; j < 12; ++j) {
+          const unsigned c = c0 + j * per;
+          if (c < gridDim.x) {
+            const double2* in = prm.partials + (static_cast<int64_t>(c) * prm.n_slots + slot) * 2;
+            v0[j] = __ldcg(in);
+            v1[j] = __ldcg(in + 1);
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 12; ++j)
+          if (c0 + j * per < gridDim.x) { a += v0[j].x; w += v0[j].y; n += v1[j].x; }
+      }
+      s_v[(slot * 3 + 0) * per + idx] = a;
+      s_v[(slot * 3 + 1) * per + idx] = w;
+      s_v[(slot * 3 + 2) * per + idx] = n;
+    }
+    __syncthreads();
+    if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 11] = global_ns();
+    const int n_warps = blockDim.x >> 5;
+    for (int sl = warp; sl < prm.n_slots; sl += n_warps) {
+      double a = 0., w = 0., n = 0.;
+      for (int i = lane; i < per; i += 32) {
+        a += s_v[(sl * 3 + 0) * per + i];
+        w += s_v[(sl * 3 + 1) * per + i];
+        n += s_v[(sl * 3 + 2) * per + i];
+      }
+      a = mg_warp_sum(a); w = mg_warp_sum(w); n = mg_warp_sum(n);
+      if (lane == 0) { s_slot[sl][0] = a; s_slot[sl][1] = w; s_slot[sl][2] = n; }
+    }
+  }
+  __syncthreads();
+  if (tid < prm.n_slots) {
+    const MgFinishSlot& sl = prm.slots[tid];
+    double s = s_slot[tid][0], c;
+    double l = s_slot[tid][1] / (static_cast<double>(B) * static_cast<double>(sl.D));   // torch.mean over (B, D), losses.py:42
+    if (s_has_empty) l = __longlong_as_double(0x7ff8000000000000LL);   // an empty utterance contributes 0 / 0 (losses.py:39)
+    if (sl.weighted) c = s_slot[tid][2];
+    else if (prm.seq_len != nullptr) { long long v = 0; for (int w2 = 0; w2 < (blockDim.x >> 5); ++w2) v += s_wvalid[w2]; c = static_cast<double>(v); }                          // frames (metrics.py:393-394)
+    else c = static_cast<double>(B) * static_cast<double>(T) * (sl.per_frame ? 1. : static_cast<double>(sl.D));   // numel (:390)
+    if (sl.accumulate) {
+      s += old.sum;
+      c += old.count;
+    }
+    mg_term_result res;
+    res.sum = s;
+    res.count = c;
+    res.loss = l;
+    res.isum = static_cast<int64_t>(s);
+    res.sum_f32 = static_cast<float>(s);
+    res.count_f32 = static_cast<float>(c);
+    res.loss_f32 = static_cast<float>(l);
+    res.weighted_loss_f32 = 0.f;
+    *sl.result = res;
+    s_slot[tid][0] = sl.in_total ? static_cast<double>(sl.weight) * l : 0.;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    double weighted_total = 0.;
+    for (int t = 0; t < prm.n_slots; ++t) weighted_total += s_slot[t][0];
+    prm.slots[0].result->weighted_loss_f32 = static_cast<float>(weighted_total);
+    *prm.ticket = 0u;   // leave the workspace clean for the next launch
+    if (stamp) prm.stamps[blockIdx.x * 16 + 6] = global_ns();
+  }
+}
+
+int env_int(const char* name, int fallback) {
+  const char* e = getenv(name);
+  return (e && *e) ? atoi(e) : fallback;
+}
+
+}  // namespace
+
+int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
+  static const int enabled = env_int("MG_OBJECTIVE_STREAM", 1);
+  if (!enabled) return MG_STREAM_NOT_APPLICABLE;
+  const int D = a.D, B = a.B;
+  const int64_t T = a.T;
+  // preconditions: contiguous (B, T, D) tensors on 16-byte aligned bases, D <= 224, B <= 1024
+  if (D > (kMaxWarps - 1) * 32 || B > kMaxB || T < 1 || static_cast<int64_t>(B) * T * 3 >= (int64_t(1) << 31)) return MG_STREAM_NOT_APPLICABLE;
+  if (a.p_st != D || a.t_st != D || a.p_sb != T * D || a.t_sb != T * D) return MG_STREAM_NOT_APPLICABLE;
+  if (!mg_aligned(a.pred, 16) || !mg_aligned(a.target, 16)) return MG_STREAM_NOT_APPLICABLE;
+  if (a.grad != nullptr && (a.g_st != D || a.g_sb != T * D || !mg_aligned(a.grad, 16))) return MG_STREAM_NOT_APPLICABLE;
+  if (static_cast<int64_t>(B) * T < 4 * kRows) return MG_STREAM_NOT_APPLICABLE;
+
+  const int sms = mg_cached_sm_count();
+  const int ctas_per_sm = env_int("MG_OBJ_CTAS_PER_SM", 2);
+  const int n_cw = (D + 31) / 32;
+  const int threads = (n_cw + 1) * 32;
+  const size_t stage_pair = static_cast<size_t>(2) * kRows * D * sizeof(float);
+  const size_t zero_bytes = a.grad != nullptr ? static_cast<size_t>(kRows) * D * sizeof(float) : 0;
+  size_t reduce_bytes = static_cast<size_t>(2 + 2 * kSpPerWarp) * threads * (3 * sizeof(double) + 1) + 64;
+  const size_t finish_bytes = static_cast<size_t>(a.n_slots) * 3 * threads * sizeof(double);   // scratch of the last CTA
+  if (reduce_bytes < finish_bytes) reduce_bytes = finish_bytes;
+  // shared memory per CTA: 227 KB per SM minus ~13 KB of static arrays and 1 KB of reserve per CTA
+  const size_t budget = (static_cast<size_t>(227) * 1024) / ctas_per_sm - 14 * 1024;
+  int ring = env_int("MG_OBJ_RING", 0);
+  // measured at config 2 (D = 187, two CTAs per SM): ring 2 / 3 / 4 / 5 / 6 / 8 -> 0.140 / 0.124 / 0.123 / 0.132 / 0.136 / 0.138 ms:
+  // four 12 KB stages per CTA cover the latency; a deeper ring only takes shared memory away from L1
+  if (ring <= 0) {
+    ring = budget > zero_bytes ? static_cast<int>((budget - zero_bytes) / stage_pair) : 0;
+    if (ring > 4) ring = 4;
+  }
+  if (ring > kMaxRing) ring = kMaxRing;
+  if (ring < 2) return MG_STREAM_NOT_APPLICABLE;
+  size_t smem = static_cast<size_t>(ring) * stage_pair + zero_bytes;
+  if (smem < reduce_bytes) smem = reduce_bytes;
+
+  const int64_t n_stages = (static_cast<int64_t>(B) * T + kRows - 1) / kRows;
+  int64_t grid = static_cast<int64_t>(sms) * ctas_per_sm;
+  if (grid > n_stages / 4) grid = n_stages / 4 > 0 ? n_stages / 4 : 1;     // tiny batches: at least four stages per CTA
+  if (grid > kMaxCtas) grid = kMaxCtas;
+  const int64_t need = kMgTicketBytes + grid * a.n_slots * static_cast<int64_t>(2 * sizeof(double2));
+  if (a.workspace_bytes < need) return MG_STREAM_NOT_APPLICABLE;
+
+  // special columns: the stream serves at most kMaxSp of them, each with its dependencies inside the row
+  // (checked on the device-side table by the caller's contract: mask_col / group columns are < D)
+  StreamParams prm;
+  memset(&prm, 0, sizeof(prm));
+  for (int i = 0; i < a.n_slots; ++i) {
+    MgFinishSlot& sl = prm.slots[i];
+    sl.result = a.slots[i].result;
+    sl.D = a.slots[i].D;
+    sl.per_frame = a.slots[i].per_frame;
+    sl.weighted = a.slots[i].weighted;
+    sl.accumulate = a.slots[i].accumulate;
+    sl.in_total = a.slots[i].in_total;
+    sl.weight = a.slots[i].weight;
+  }
+  prm.pred = a.pred; prm.target = a.target; prm.grad = a.grad; prm.grad_scale_dev = a.grad_scale_dev;
+  prm.cols = a.cols; prm.seq_len = a.seq_len;
+  unsigned char* base = static_cast<unsigned char*>(a.workspace);
+  prm.ticket = reinterpret_cast<unsigned int*>(base);
+  prm.partials = reinterpret_cast<double2*>(base + kMgTicketBytes);
+  prm.T = T; prm.D = D; prm.B = B; prm.n_slots = a.n_slots; prm.ring = ring; prm.n_consumer_warps = n_cw;
+  prm.debug = env_int("MG_OBJ_DEBUG", 0);
+  prm.stamps = reinterpret_cast<unsigned long long*>(base + kMgTicketBytes + 512 * 1024);
+  if ((prm.debug & 8) && a.workspace_bytes < kMgTicketBytes + 512 * 1024 + grid * 128) prm.debug &= ~8;
+  prm.cost_valid = env_int("MG_OBJ_COST_VALID", a.grad != nullptr ? 6 : 2);
+  prm.cost_pad = env_int("MG_OBJ_COST_PAD", 1);
+
+  if (smem > 200 * 1024) return MG_STREAM_NOT_APPLICABLE;
+  if (a.grad != nullptr) MG_CUDA_OK(cudaFuncSetAttribute(objective_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  else MG_CUDA_OK(cudaFuncSetAttribute(objective_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  if (a.grad != nullptr) objective_stream_kernel<true><<<static_cast<unsigned>(grid), threads, smem, stream>>>(prm);
+  else objective_stream_kernel<false><<<static_cast<unsigned>(grid), threads, smem, stream>>>(prm);
+  MG_LAUNCH_OK();
+  return MG_OK;
+}

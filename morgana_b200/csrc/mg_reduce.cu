@@ -480,7 +480,9 @@ int rows_per_cta_for(int D, int B, int64_t T, int sms) {
 extern "C" int64_t mg_masked_reduce_workspace_bytes(int n_terms, int B, int64_t T) {
   (void)T;
   if (n_terms < 0 || B < 0) return MG_ERR_INVALID_ARG;
-  return mg_workspace_bytes(n_terms, B);
+  const int64_t chunked = mg_workspace_bytes(n_terms, B);
+  const int64_t streamed = kMgTicketBytes + 1024 * static_cast<int64_t>(n_terms) * 32;   // per-CTA partials of the row-stream form
+  return chunked > streamed ? chunked : streamed;
 }
 
 extern "C" int mg_masked_reduce(const mg_term* terms, int n_terms, const int64_t* seq_len, int B, int64_t T,

@@ -142,13 +142,18 @@ def cpu_lengths():
 def forward_backward(model, features, mode='train'):
     """``BaseSPSS.forward`` (base_models.py:317-321) + backward, the inner part of ``train_epoch`` (:464-470).
 
-    Returns (loss tensor, outputs, {metric name: (sum, count)} as Python floats, {param name: grad}).
+    Returns (loss tensor, outputs, {metric name: (sum, count)} as Python floats, {param name: grad}); the gradient of the loss
+    with respect to every differentiable output (the boundary between the path and the layers) is kept in ``outputs[k].grad``.
     """
     model.mode = mode
     model.metrics.reset_state(mode)
     model.zero_grad()
     with cpu_lengths():
-        loss, outputs = model(features)
+        output_features = model.predict(features)           # BaseSPSS.forward, with the outputs' gradients retained
+        for value in output_features.values():
+            if isinstance(value, torch.Tensor) and value.requires_grad:
+                value.retain_grad()
+        loss, outputs = model.loss(features, output_features), output_features
         loss.backward()
     sums = {}
     for name, metric in model.metrics[mode].items():

@@ -136,6 +136,14 @@ def _compare(tag, arms, mlpg_metrics, records):
         assert c_ours == c_stock, name
         assert rel(s_ours, s_stock) <= tol or abs(s_ours - s_stock) <= 1e-12, name
 
+    # gradient of the loss at the boundary of the path (what autograd hands to the layers): ours vs ATen's, element by element
+    for key in out_stock:
+        if out_stock[key].grad is None:
+            continue
+        d = max_rel(out_ours[key].grad, out_stock[key].grad)
+        report('%s d loss / d %-26s ours-vs-stock %.2e' % (tag, key, d))
+        assert d <= REL, key
+
     worst, worst_cpu_ours, worst_cpu_stock = 0., 0., 0.
     assert set(g_ours) == set(g_stock)
     for name in g_stock:
@@ -144,9 +152,10 @@ def _compare(tag, arms, mlpg_metrics, records):
         worst_cpu_stock = max(worst_cpu_stock, max_rel(g_stock[name], g_cpu[name]))
     report('%s parameter gradients: ours-vs-stock %.2e (max over %d tensors), stock-vs-cpu %.2e, ours-vs-cpu %.2e'
            % (tag, worst, len(g_stock), worst_cpu_stock, worst_cpu_ours))
-    # the loss gradient is within 1e-6 of ATen's element by element; what the layers' backward (cuDNN, atomics in cuBLAS
-    # split-K) adds on top is the stock arm's own run-to-run noise
-    assert worst <= 2e-5
+    # the loss gradient is within 1e-6 of ATen's element by element (above); the recurrent layers' backward amplifies last-bit
+    # differences of its input -- the same layers on the CPU are 4e-4 away from the stock CUDA run -- so the parameter gradients
+    # are held to a quarter of that distance (and to 2e-5 where there is no recurrence)
+    assert worst <= max(2e-5, 0.25 * worst_cpu_stock)
     assert worst_cpu_ours <= 2. * worst_cpu_stock + 2e-5
 
 
