@@ -4,20 +4,25 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
 One "step" = one pass of the hot path over one synthetic batch of configs[1] (256 utterances x ~60 phones, durations
-U{1..30}, 600-dim labels; SURVEY.md section 8d, seed 1234):
+U{1..30}, 600-dim labels; SURVEY.md section 8d, seed 1234), through the package's public API:
 
-    K1 duration scan -> K2 fused min-max normalise + phone->frame expansion to (B, T, 600)
-    -> K4/K5 one-launch masked objective on the batch's (B, T, 187) prediction/target pair: 3 x mse + bce with the
-       gradient w.r.t. the prediction, plus the four streaming metrics of models/RNN_SPSS.py:124-129.
+    utils.upsample_to_repetitions(lab, dur, normaliser=minmax)  = K1 duration scan + K2 fused normalise + expansion -> (B, T, 600)
+    fused.AcousticObjective(pred, target, n_frames)             = K4b: 3 x mse + bce of models/RNN_SPSS.py:131-139 with the
+                                                                  gradient, and its four streaming metrics (:124-129)
 
-`value` is whole-job valid frames/s with inputs resident in HBM (CUDA events, max over ranks); `e2e` is the same metric
-through the public Python API from pinned HOST buffers with the host<->device copies inside the timed region;
-`roofline` describes the dominant kernel (K2) from CUDA events around its launches inside the timed region
-(`roofline_k4b`: the same for the step's other kernel);
-`cpu_baseline` / `--impl reference` time the reference's own op chain (oracle/aten_chain.py) on the host cores.
+`value`   whole-job valid frames/s with the inputs resident in HBM (CUDA events on the launching stream, max over ranks).
+`e2e`     the same metric through the same API from pinned HOST buffers, host<->device copies inside the timed region.
+`roofline` the kernel with the largest share of the step, from CUDA events around its launches inside the timed region
+          (`ops.KernelProbe`); the step's other kernel is reported the same way beside it.
+`cpu_baseline` / `--impl reference`: the UNMODIFIED reference (ZackHodari/morgana, mirrored into oracle/_ref by
+          oracle/make_ref.py) on the box's host cores, same 256 utterances; that arm never imports the product package.
+`other_configs` (N = 1): the remaining BASELINE.json configurations and the stock-ATen path on the same GPU, each timed with its
+          own CUDA events inside this run.  `training` (every N): BASELINE.json configs[4], data-parallel training of the README
+          F0 MLP with the flat-bucket gradient all-reduce.
 Prints exactly one JSON line on rank 0.
 """
 import argparse
+import importlib.util
 import json
 import os
 import statistics
@@ -33,19 +38,27 @@ if ROOT not in sys.path:
 METRIC = 'valid frames/sec through normalise->upsample->masked-loss path'
 UNIT = 'frames/s'
 N_ROTATING_BATCHES = 3        # distinct input batches cycled between steps (each step's working set is ~1.9 GB >> L2)
-CPU_SAMPLE_UTTS = 64          # utterances per CPU-baseline pass (a quarter of the batch)
 
 
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=2000)
+    ap.add_argument('--steps', type=int, default=400)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--batch-size', type=int, default=256)
     ap.add_argument('--e2e-steps', type=int, default=0, help='steps of the host-buffer loop (0: min(steps, 30))')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true', help='skip other_configs and the training section')
     return ap.parse_args()
+
+
+def load_by_path(name, *relative):
+    """Import a source file without importing the package around it (the reference arm must not load the product)."""
+    spec = importlib.util.spec_from_file_location(name, os.path.join(ROOT, *relative))
+    module = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(module)
+    return module
 
 
 def peaks():
@@ -65,7 +78,7 @@ class ClockSampler(object):
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
 
-    def __init__(self, gpu_index, period_ms=100):
+    def __init__(self, gpu_index, period_ms=50):
         self.samples = []
         self.proc = None
         try:
@@ -116,21 +129,66 @@ class ClockSampler(object):
 
 
 # ----------------------------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the reference's op chain on the host cores
+# reference arm / CPU baseline: the unmodified reference on the host cores
 # ----------------------------------------------------------------------------------------------------------------------
-def cpu_pass(sample):
-    """One pass of the path as the reference executes it (oracle/aten_chain.py), on CPU tensors."""
-    from oracle import aten_chain as ref
-    norm_lab = ref.normalise_minmax_chain(sample['lab'], sample['mmin'], sample['mmax'])
-    frames = ref.upsample_chain(norm_lab, sample['dur'])
-    loss, grad, increments = ref.acoustic_loss_and_metrics(sample['pred'], sample['target'], sample['voiced'],
-                                                           sample['n_frames'])
-    return frames, loss, grad, increments
+WORLD_LAYOUT = ((0, 3), (3, 4), (4, 184), (184, 187))     # lf0 | vuv | mcep | bap after torch.split (models/RNN_SPSS.py:86-88)
 
 
-def make_cpu_sample(batch_size, n_utts):
+class ReferencePath(object):
+    """One pass of the path as the reference executes it, with the reference's own functions (CPU or CUDA tensors):
+    ``data.normalise_minmax`` (data.py:579-584) -> ``utils.upsample_to_repetitions`` (utils.py:175-228) -> the body of
+    ``LSTMAcousticModel.loss`` (models/RNN_SPSS.py:120-139): four metric accumulations, 3 x ``losses.mse`` + ``losses.bce``,
+    ``/ 4``, and ``backward()`` for the gradient w.r.t. the prediction."""
+    def __init__(self):
+        from oracle import ref_loader
+        self.available = ref_loader.available()
+        self.kind = 'reference' if self.available else 'port'
+        if self.available:
+            self.morgana = ref_loader.import_reference()
+            self.where = os.path.relpath(ref_loader.reference_root(), ROOT) if ref_loader.reference_root().startswith(ROOT) \
+                else ref_loader.reference_root()
+            m = self.morgana.metrics
+            self.metrics = {'LF0_RMSE_Hz': m.LF0Distortion(), 'VUV_accuracy': m.Mean(), 'MCEP_distortion': m.MelCepDistortion(),
+                            'BAP_distortion': m.Distortion()}
+            for metric in self.metrics.values():
+                metric.reset_state()
+        else:    # the mirror did not travel: the restatement of the same op chain (oracle/aten_chain.py)
+            from oracle import aten_chain
+            self.port, self.where = aten_chain, 'oracle/aten_chain.py'
+
+    def upsample(self, lab, dur, mmin, mmax):
+        if not self.available:
+            return self.port.upsample_chain(self.port.normalise_minmax_chain(lab, mmin, mmax), dur)
+        return self.morgana.utils.upsample_to_repetitions(self.morgana.data.normalise_minmax(lab, mmin, mmax), dur)
+
+    def objective(self, pred, target, n_frames, voiced_target):
+        import torch
+        if not self.available:
+            return self.port.acoustic_loss_and_metrics(pred, target, voiced_target, n_frames)[:2]
+        losses, (lf0, vuv, mcep, bap) = self.morgana.losses, WORLD_LAYOUT
+        pred = pred.detach().requires_grad_()
+        vuv_pred = pred[..., vuv[0]:vuv[1]] > 0.5
+        with torch.no_grad():
+            self.metrics['LF0_RMSE_Hz'].accumulate(target[..., 0:1], pred[..., 0:1], vuv_pred.clone(), n_frames)
+            self.metrics['VUV_accuracy'].accumulate((voiced_target == vuv_pred).type(torch.float), n_frames)
+            self.metrics['MCEP_distortion'].accumulate(target[..., 4:64], pred[..., 4:64], n_frames)
+            self.metrics['BAP_distortion'].accumulate(target[..., 184:185], pred[..., 184:185], n_frames)
+        loss = 0.
+        for a, b in (lf0, mcep, bap):
+            loss += losses.mse(pred[..., a:b], target[..., a:b], n_frames)
+        loss += losses.bce(pred[..., vuv[0]:vuv[1]], target[..., vuv[0]:vuv[1]], n_frames)
+        loss = loss / 4.
+        loss.backward()
+        return loss.detach(), pred.grad
+
+    def step(self, sample):
+        frames = self.upsample(sample['lab'], sample['dur'], sample['mmin'], sample['mmax'])
+        loss, grad = self.objective(sample['pred'], sample['target'], sample['n_frames'], sample['voiced'])
+        return frames, loss, grad
+
+
+def make_cpu_sample(workloads, batch_size, n_utts):
     import torch
-    from morgana_b200 import workloads
     ling = workloads.linguistic_batch(batch_size=batch_size, seed=1234)
     ac = workloads.acoustic_batch(ling['n_frames'], seed=1234)
     n = min(n_utts, batch_size)
@@ -142,14 +200,14 @@ def make_cpu_sample(batch_size, n_utts):
     return sample, int(sample['n_frames'].sum())
 
 
-def time_cpu(sample, steps, warmup):
+def time_cpu(path, sample, steps, warmup):
     import torch
     for _ in range(warmup):
-        cpu_pass(sample)
+        path.step(sample)
     times = []
     for _ in range(steps):
         t0 = time.perf_counter()
-        cpu_pass(sample)
+        path.step(sample)
         times.append(time.perf_counter() - t0)
     return times, torch.get_num_threads()
 
@@ -166,31 +224,38 @@ def cpu_model_name():
 
 
 def run_reference(args, rank, world):
+    """`--impl reference`: rank 0 alone times the reference on the host cores; nothing of the product package is imported."""
     if rank != 0:
         return
     import torch
-    # Bounded sample: calibrate on 16 utterances, then size each step so that warm-up + K steps take about two minutes.
-    probe, probe_frames = make_cpu_sample(args.batch_size, 16)
-    cpu_pass(probe)
+    workloads = load_by_path('_mg_workloads', 'morgana_b200', 'workloads.py')     # the file, not the package
+    path = ReferencePath()
+    # The whole batch of the GPU arm (256 utterances) per step; shrink only if K + W passes would not end within ~2.5 minutes.
+    probe, _ = make_cpu_sample(workloads, args.batch_size, 32)
+    path.step(probe)
     t0 = time.perf_counter()
-    cpu_pass(probe)
-    per_utt = (time.perf_counter() - t0) / 16
-    budget_s = 120.0
+    path.step(probe)
+    per_utt = (time.perf_counter() - t0) / 32
+    budget_s = 150.0
     n_utts = int(budget_s / max(args.steps + args.warmup, 1) / max(per_utt, 1e-6))
-    n_utts = max(4, min(CPU_SAMPLE_UTTS, n_utts, args.batch_size))
-    sample, frames = make_cpu_sample(args.batch_size, n_utts)
-    times, threads = time_cpu(sample, args.steps, args.warmup)
+    n_utts = max(8, min(args.batch_size, n_utts))
+    sample, frames = make_cpu_sample(workloads, args.batch_size, n_utts)
+    times, threads = time_cpu(path, sample, args.steps, args.warmup)
     total = sum(times)
     value = frames * len(times) / total
+    assert 'morgana_b200' not in sys.modules, 'the reference arm imported the product package'
     line = {
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times), 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args, note='each step = the first %d utterances of the batch on the host CPU' % n_utts),
-        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                         'sample': '%d of %d utterances (%d valid frames) per step; reference op chain restated in '
-                                   'oracle/aten_chain.py (the Python reference cannot travel to the GPU box); %s, torch %s'
-                                   % (n_utts, args.batch_size, frames, cpu_model_name(), torch.__version__)},
+        'config': workload_config(args, note=None if n_utts == args.batch_size else
+                                  'each step = the first %d utterances of the batch (time budget)' % n_utts),
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': threads, 'kind': path.kind,
+                         'sample': '%d of %d utterances (%d valid frames) per step; %s, imported from %s, on %s, torch %s'
+                                   % (n_utts, args.batch_size, frames,
+                                      'the unmodified reference functions (data.normalise_minmax, utils.upsample_to_repetitions, '
+                                      'losses.mse / bce + backward, metrics.*.accumulate)' if path.available else
+                                      'restatement of the reference op chain', path.where, cpu_model_name(), torch.__version__)},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -201,7 +266,7 @@ def workload_config(args, note=None):
     cfg = {'workload': 'configs[1]: upsample_to_repetitions + minmax normalise, %d utts x ~60 phones, dur U{1..30}, '
                        '600-dim labels -> masked loss + metrics on 187-dim WORLD targets of the same batch' % args.batch_size,
            'batch_utterances_per_gpu': args.batch_size, 'label_dim': 600, 'target_dim': 187, 'seed': 1234,
-           'l2': 'inputs larger than L2: each step streams ~1.9 GB (837 MB output alone) and rotates over %d input batches'
+           'l2': 'inputs larger than L2: each step streams ~1.5 GB (837 MB output alone) and rotates over %d input batches'
                  % N_ROTATING_BATCHES,
            'parallelism': 'utterance-sharded, one process per GPU'}
     if note:
@@ -226,6 +291,7 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     sampler = ClockSampler(local_rank) if rank == 0 else None
+    windows = []
 
     # ---- inputs: each rank owns its own shard of utterances (different seeds), resident in HBM -------------------
     host_batches, dev_batches = [], []
@@ -252,46 +318,18 @@ def run_ours(args, rank, world, local_rank):
     normaliser = ('minmax', mmin, mmax)
     objective = AcousticObjective()
     stream = torch.cuda.current_stream()
+    # one row of four 48-byte loss records per step: K4b writes step i's losses into row i, nothing is accumulated or copied
+    # per step; the rows and the four running metric records cross the ranks in ONE all-reduce when the epoch ends, as the
+    # reference only needs epoch sums (experiment_builder.py:499-501)
+    loss_log = ops.new_result_records(4 * max(args.steps, 1), dev).reshape(max(args.steps, 1), 4, -1)
+    scratch_records = ops.new_result_records(4, dev)
 
-    def step(batch, time_k2=None, time_k4b=None):
-        # K1 + K2 (max_len: the padded length is known on the host, as features['n_frames'] is in the reference pipeline)
-        if time_k2 is not None:
-            ends, n_frames, _ = ops.dur_scan(batch['dur'])   # keep K1 outside the bracket: the events time K2 alone
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            B, P, D = batch['lab'].shape
-            out = torch.empty((B, batch['T'], D), dtype=torch.float32, device=dev)
-            e0.record(stream)
-            ops.check(ops.lib.mg_upsample_norm_f32(batch['lab'].data_ptr(), batch['lab'].stride(0), batch['lab'].stride(1),
-                                                   ends.data_ptr(), mmin.data_ptr(), mmax.data_ptr(), 0, 2, out.data_ptr(),
-                                                   B, P, D, batch['T'], 0, stream.cuda_stream), 'mg_upsample_norm_f32')
-            e1.record(stream)
-            time_k2.append((e0, e1))
-        else:
-            out, n_frames = mg.utils.upsample_to_repetitions(batch['lab'], batch['dur'], normaliser=normaliser,
-                                                             max_len=batch['T'], return_lengths=True)
-        if time_k4b is not None:   # K4b (+ the 2 us fill of its result records) between its own pair of events
-            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            o0.record(stream)
-            loss, grad = objective(batch['pred'], batch['target'], n_frames)
-            o1.record(stream)
-            time_k4b.append((o0, o1))
-        else:
-            loss, grad = objective(batch['pred'], batch['target'], n_frames)
+    def step(batch, loss_records):
+        # max_len: the padded length is known on the host, as features['n_frames'] is in the reference pipeline
+        out, n_frames = mg.utils.upsample_to_repetitions(batch['lab'], batch['dur'], normaliser=normaliser,
+                                                         max_len=batch['T'], return_lengths=True)
+        loss, grad = objective(batch['pred'], batch['target'], n_frames, loss_records=loss_records)
         return out, loss, grad
-
-    pending = []
-
-    def exchange():
-        """The path's one collective: SUM of the packed loss / metric-sum records over ranks (NCCL over NVLink).  It is
-        issued asynchronously -- the records are copied first, the all-reduce runs on NCCL's stream while the next step's
-        kernels run on ours -- and joined one step later (and before the timed region closes)."""
-        if world > 1:
-            join()
-            pending.append(dp.allreduce_records(objective.last_loss_records, objective._records, async_op=True))
-
-    def join():
-        while pending:
-            pending.pop().result()
 
     def barrier():
         if world > 1:
@@ -300,15 +338,16 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- warm-up ---------------------------------------------------------------------------------------------------
     for i in range(max(args.warmup, 3)):
-        step(dev_batches[i % N_ROTATING_BATCHES])
-        exchange()
+        step(dev_batches[i % N_ROTATING_BATCHES], scratch_records)
+    if world > 1:
+        dp.allreduce_records(scratch_records)          # NCCL communicator set-up outside the timed region
     barrier()
 
     # ---- timed region: exactly K steps, device-resident inputs ---------------------------------------------------------
-    # A pair of event records costs ~3 us of the stream's time: K2 is bracketed on every 4th step and K4b on every 8th of a
-    # long run (every step of a short one) -- the averages are still taken live, inside the timed region.
-    k2_events, k4b_events, k2_steps, k4b_steps = [], [], [], []
-    k2_every, k4b_every = (4, 8) if args.steps >= 64 else (1, 1)
+    # A pair of event records costs ~3 us of the stream's time, so the probe brackets K2 on steps 0, 4, 8, ... and K4b on steps
+    # 2, 6, 10, ...; the averages are still taken live, inside the timed region, on the launching stream.
+    k2_probe, k4b_probe = ops.KernelProbe('K2'), ops.KernelProbe('K4b')
+    k2_steps, k4b_steps = [], []
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     frames_done = 0
     barrier()
@@ -316,144 +355,194 @@ def run_ours(args, rank, world, local_rank):
     start.record(stream)
     for i in range(args.steps):
         batch = dev_batches[i % N_ROTATING_BATCHES]
-        time_k2, time_k4b = i % k2_every == 0, i % k4b_every == 0
-        if time_k2:
+        if i % 4 == 0:
             k2_steps.append(i)
-        if time_k4b:
+            with k2_probe:
+                step(batch, loss_log[i])
+        elif i % 4 == 2:
             k4b_steps.append(i)
-        step(batch, time_k2=k2_events if time_k2 else None, time_k4b=k4b_events if time_k4b else None)
-        exchange()
+            with k4b_probe:
+                step(batch, loss_log[i])
+        else:
+            step(batch, loss_log[i])
         frames_done += batch['frames']
-    join()
+    # the path's one collective: SUM of the epoch's loss records and metric records over the ranks (NCCL over NVLink)
+    epoch_records = dp.allreduce_records(loss_log.reshape(-1, loss_log.shape[-1]), objective._records) if world > 1 else None
     stop.record(stream)
     barrier()
     wall1 = time.time()
+    windows.append((wall0, wall1))
     elapsed_ms = start.elapsed_time(stop)
+    del epoch_records
 
-    k2_ms = [a.elapsed_time(b) for a, b in k2_events]
-    k2_avg_ms = sum(k2_ms) / len(k2_ms)
-    k2_bytes = []
-    for i in k2_steps:
-        hb = host_batches[i % N_ROTATING_BATCHES]
-        k2_bytes.append(4 * 600 * (args.batch_size * hb['T'] + hb['n_phones']) + 4 * args.batch_size * hb['P'] + 8 * 600)
-    k2_avg_bytes = sum(k2_bytes) / len(k2_bytes)
-    k4b_avg_ms = sum(a.elapsed_time(b) for a, b in k4b_events) / len(k4b_events)
-    k4b_avg_bytes = sum(4 * 187 * (2 * host_batches[i % N_ROTATING_BATCHES]['frames'] +
-                                   args.batch_size * host_batches[i % N_ROTATING_BATCHES]['T'])
-                        for i in k4b_steps) / len(k4b_steps)   # valid rows of pred + target read, the whole gradient written
+    def kernel_line(name, probe, steps_timed, bytes_of):
+        ms = probe.ms(name)
+        avg_ms = sum(ms) / len(ms)
+        avg_bytes = sum(bytes_of(host_batches[i % N_ROTATING_BATCHES]) for i in steps_timed) / len(steps_timed)
+        return avg_ms, avg_bytes, len(ms)
+
+    k2_ms, k2_bytes, k2_n = kernel_line('K2', k2_probe, k2_steps, lambda hb: 4 * 600 * (args.batch_size * hb['T'] + hb['n_phones']) +
+                                        4 * args.batch_size * hb['P'] + 8 * 600)
+    # valid rows of pred + target read, the whole gradient written
+    k4b_ms, k4b_bytes, k4b_n = kernel_line('K4b', k4b_probe, k4b_steps or k2_steps, lambda hb: 4 * 187 * (2 * hb['frames'] + args.batch_size * hb['T'])) \
+        if k4b_steps else (float('nan'), 0., 0)
 
     # ---- end-to-end: the public API from pinned host buffers, copies inside the timed region ------------------------
     e2e_steps = args.e2e_steps or min(args.steps, 30)
-    e2e_keys = ('lab_packed', 'dur_packed', 'pred_packed', 'target_packed', 'phone_counts', 'frame_counts')
-    h2d = sum(host_batches[0][k].numel() * host_batches[0][k].element_size() for k in e2e_keys)
-    d2h = 8 * ops.RESULT_BYTES
-
     copy_stream = torch.cuda.Stream(device=dev)
 
-    def upload(hb):
-        """Host -> device on the copy stream: only valid rows cross PCIe (packed wire format)."""
-        with torch.cuda.stream(copy_stream):
-            up = {k: hb[k].to(dev, non_blocking=True) for k in e2e_keys}
-            done = torch.cuda.Event()
-            done.record(copy_stream)
-        return up, done
+    def run_e2e(keys, label):
+        """Every step's inputs are uploaded inside the loop (one cudaMemcpyAsync per buffer, on a copy stream); the upload of
+        step i + 1 overlaps the kernels of step i; the step's result records are read back to the host every step."""
+        h2d = sum(host_batches[0][k].numel() * host_batches[0][k].element_size() for k in keys)
 
-    def e2e_compute(hb, up, done):
-        # The zero padding of collate_fn (reference data.py:184-193) is produced on the device.  Lengths are host-side
-        # knowledge (features['n_frames']), so nothing synchronises until the result records are read back.
-        stream.wait_event(done)
-        for t in up.values():
-            t.record_stream(stream)
-        pred = mg.data.pad_collate(up['pred_packed'], up['frame_counts'], max_len=hb['T'])
-        target = mg.data.pad_collate(up['target_packed'], up['frame_counts'], max_len=hb['T'])
-        # the items are consumed as they arrive (packed): no phone padding is built or read
-        out, n_frames = mg.utils.upsample_packed_to_repetitions(up['lab_packed'], up['dur_packed'], up['phone_counts'],
-                                                                normaliser=normaliser, max_len=hb['T'], max_items=hb['P'],
-                                                                return_lengths=True)
-        loss, grad = objective(pred, target, n_frames)
-        if world > 1:     # the step's result is read back right away, so this exchange is joined at once
-            return dp.allreduce_records(objective.last_loss_records, objective._records).cpu()
-        return torch.cat([objective.last_loss_records, objective._records]).cpu()   # device -> host read of the result
+        def upload(hb):
+            with torch.cuda.stream(copy_stream):
+                up = {k: hb[k].to(dev, non_blocking=True) for k in keys}
+                done = torch.cuda.Event()
+                done.record(copy_stream)
+            return up, done
 
-    def e2e_loop(n_steps):
-        """Every step's inputs are uploaded inside the loop; the upload of step i + 1 overlaps the kernels of step i."""
-        frames = 0
-        pending = upload(host_batches[0])
-        for i in range(n_steps):
-            hb = host_batches[i % N_ROTATING_BATCHES]
-            up, done = pending
-            if i + 1 < n_steps:
-                pending = upload(host_batches[(i + 1) % N_ROTATING_BATCHES])
-            e2e_compute(hb, up, done)
-            frames += hb['frames']
-        return frames
+        def compute(hb, db, up, done):
+            # The zero padding of collate_fn (reference data.py:184-193) is produced on the device.  Lengths are host-side
+            # knowledge (features['n_frames']), so nothing synchronises until the result records are read back.
+            stream.wait_event(done)
+            for t in up.values():
+                t.record_stream(stream)
+            if 'pred_packed' in up:
+                pred = mg.data.pad_collate(up['pred_packed'], up['frame_counts'], max_len=hb['T'])
+            else:
+                pred = db['pred']            # produced on the device by the model in the real pipeline (RNN_SPSS.py:83)
+            target = mg.data.pad_collate(up['target_packed'], up['frame_counts'], max_len=hb['T'])
+            # the items are consumed as they arrive (packed): no phone padding is built or read
+            out, n_frames = mg.utils.upsample_packed_to_repetitions(up['lab_packed'], up['dur_packed'], up['phone_counts'],
+                                                                    normaliser=normaliser, max_len=hb['T'], max_items=hb['P'],
+                                                                    return_lengths=True)
+            loss, grad = objective(pred, target, n_frames)
+            if world > 1:     # the step's result is read back right away, so this exchange is joined at once
+                return dp.allreduce_records(objective.last_loss_records, objective._records).cpu()
+            return torch.cat([objective.last_loss_records, objective._records]).cpu()   # device -> host read of the result
 
-    e2e_loop(3)
-    barrier()
-    e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ewall0 = time.time()
-    e_start.record(stream)
-    copy_stream.wait_event(e_start)          # the first upload belongs to the timed region
-    e2e_frames = e2e_loop(e2e_steps)
-    e_stop.record(stream)
-    barrier()
-    ewall1 = time.time()
-    e2e_ms = e_start.elapsed_time(e_stop)
+        def loop(n_steps):
+            frames = 0
+            pending = upload(host_batches[0])
+            for i in range(n_steps):
+                hb, db = host_batches[i % N_ROTATING_BATCHES], dev_batches[i % N_ROTATING_BATCHES]
+                up, done = pending
+                if i + 1 < n_steps:
+                    pending = upload(host_batches[(i + 1) % N_ROTATING_BATCHES])
+                compute(hb, db, up, done)
+                frames += hb['frames']
+            return frames
+
+        loop(3)
+        barrier()
+        e_start, e_stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.time()
+        e_start.record(stream)
+        copy_stream.wait_event(e_start)          # the first upload belongs to the timed region
+        frames = loop(e2e_steps)
+        e_stop.record(stream)
+        barrier()
+        windows.append((w0, time.time()))
+        return {'ms': e_start.elapsed_time(e_stop), 'frames': frames, 'h2d': h2d, 'label': label}
+
+    all_keys = ('lab_packed', 'dur_packed', 'pred_packed', 'target_packed', 'phone_counts', 'frame_counts')
+    e2e_full = run_e2e(all_keys, 'lab + dur + target + pred from the host')
+    # `pred` is produced on the device by the model in the real pipeline; the host-side inputs of the path are lab / dur /
+    # target / lengths -- reported beside the headline number, which keeps everything on the wire
+    e2e_inputs = run_e2e(tuple(k for k in all_keys if k != 'pred_packed'), 'lab + dur + target from the host, pred resident')
+    d2h = 8 * ops.RESULT_BYTES
 
     # ---- max over ranks -------------------------------------------------------------------------------------------
-    stats = torch.tensor([elapsed_ms, e2e_ms, float(frames_done), float(e2e_frames)], dtype=torch.float64, device=dev)
+    stats = torch.tensor([elapsed_ms, e2e_full['ms'], e2e_inputs['ms'], float(frames_done), float(e2e_full['frames']),
+                          float(e2e_inputs['frames'])], dtype=torch.float64, device=dev)
     if world > 1:
-        times = stats[:2].clone()
+        times = stats[:3].clone()
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
-        counts = stats[2:].clone()
+        counts = stats[3:].clone()
         dist.all_reduce(counts, op=dist.ReduceOp.SUM)
-        elapsed_ms, e2e_ms = times.tolist()
-        frames_done, e2e_frames = counts.tolist()
+        stats = torch.cat([times, counts])
+    elapsed_ms, e2e_ms, e2e_in_ms, frames_done, e2e_frames, e2e_in_frames = stats.tolist()
+
+    pk, pk_src = peaks()
+    sections = None
+    extras = {}
+    if not args.no_extras:
+        sections = load_by_path('_mg_bench_sections', 'scripts', 'bench_sections.py')
+        t0 = time.time()
+        extras['training'] = sections.training_section(rank, world, dev, pk)
+        windows.append((t0, time.time()))
+        if world == 1:
+            t0 = time.time()
+            extras['other_configs'] = sections.other_configs(dev, pk, ReferencePath())
+            windows.append((t0, time.time()))
     if sampler is not None:
         sampler.stop()
     if rank != 0:
         if world > 1:
+            dist.barrier()
             dist.destroy_process_group()
         return
 
-    pk, pk_src = peaks()
-    achieved = k2_avg_bytes / (k2_avg_ms * 1e-3) / 1e9
-    traffic, traffic_src = None, None
-    traffic_path = os.path.join(ROOT, 'profiles', 'k2_traffic.json')
-    if os.path.exists(traffic_path):       # DRAM bytes of one K2 launch from the committed `ncu --set full` capture
-        with open(traffic_path) as f:
-            t = json.load(f)
-        traffic, traffic_src = t['dram_bytes_read'] + t['dram_bytes_write'], t['source']
+    step_ms = elapsed_ms / args.steps
+    traffic, traffic_src = {}, {}
+    for name, fname in (('K2', 'k2_traffic.json'), ('K4b', 'k4b_traffic.json')):
+        path = os.path.join(ROOT, 'profiles', fname)
+        if os.path.exists(path):       # DRAM bytes of one launch from the committed `ncu --set full` capture
+            with open(path) as f:
+                t = json.load(f)
+            traffic[name], traffic_src[name] = t['dram_bytes_read'] + t['dram_bytes_write'], t['source']
+
+    def roofline(name, kernel, ms, nbytes, n):
+        achieved = nbytes / (ms * 1e-3) / 1e9
+        return {'bound': 'hbm', 'kernel': kernel, 'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
+                'frac': achieved / pk['hbm_gbs'], 'frac_of_8000_nominal': achieved / 8000.0, 'traffic': traffic.get(name),
+                'traffic_source': traffic_src.get(name), 'peak_source': pk_src, 'algorithmic_bytes_per_launch': nbytes,
+                'avg_launch_ms': ms, 'launches_timed': n, 'share_of_step': ms / step_ms}
+
+    lines = {'K2': roofline('K2', 'upsample_bulk_kernel<MINMAX> (K2, fused normalise + expansion)', k2_ms, k2_bytes, k2_n)}
+    if k4b_n:
+        lines['K4b'] = roofline('K4b', 'objective_stream_kernel<GRAD> (K4b: 3 x mse + bce + gradient + 4 metrics)', k4b_ms, k4b_bytes, k4b_n)
+    dominant = max(lines, key=lambda k: lines[k]['share_of_step'])
+    step_bytes = k2_bytes + (k4b_bytes if k4b_n else 0.)
     line = {
         'metric': METRIC, 'value': frames_done / (elapsed_ms * 1e-3), 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-        'warmup': max(args.warmup, 3), 'ms_per_step': elapsed_ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'warmup': max(args.warmup, 3), 'ms_per_step': step_ms, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic', 'config': workload_config(args),
-        'clocks': sampler.summary([(wall0, wall1), (ewall0, ewall1)]),
-        'e2e': {'value': e2e_frames / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
+        'clocks': sampler.summary(windows),
+        'e2e': {'value': e2e_frames / (e2e_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': e2e_full['h2d'], 'd2h_bytes_per_step': d2h,
                 'steps': e2e_steps, 'ms_per_step': e2e_ms / e2e_steps,
-                'api': 'utils.upsample_packed_to_repetitions(packed lab, packed dur, n_phones, normaliser=..., max_len=T) | data.pad_collate(packed pred / target) -> fused.AcousticObjective, from pinned host tensors'},
+                'h2d_gb_per_s_per_gpu': e2e_full['h2d'] / (e2e_ms / e2e_steps * 1e-3) / 1e9,
+                'wire': e2e_full['label'],
+                'api': 'utils.upsample_packed_to_repetitions(packed lab, packed dur, n_phones, normaliser=..., max_len=T) | '
+                       'data.pad_collate(packed pred / target) -> fused.AcousticObjective, from pinned host tensors',
+                'inputs_only': {'value': e2e_in_frames / (e2e_in_ms * 1e-3), 'unit': UNIT, 'h2d_bytes_per_step': e2e_inputs['h2d'],
+                                'ms_per_step': e2e_in_ms / e2e_steps, 'wire': e2e_inputs['label']}},
         'gpu_launches': 3 * args.steps, 'e2e_gpu_launches_per_step': 8,
-        'roofline': {'bound': 'hbm', 'kernel': 'upsample_bulk_kernel<MINMAX> (K2, fused normalise + expansion)',
-                     'achieved': achieved, 'peak': pk['hbm_gbs'], 'unit': 'GB/s', 'frac': achieved / pk['hbm_gbs'],
-                     'frac_of_8000_nominal': achieved / 8000.0, 'traffic': traffic, 'traffic_source': traffic_src, 'peak_source': pk_src,
-                     'algorithmic_bytes_per_launch': k2_avg_bytes, 'avg_launch_ms': k2_avg_ms, 'launches_timed': len(k2_ms),
-                     'share_of_step': k2_avg_ms / (elapsed_ms / args.steps)},
-        # the step's other kernel, for the record (same method: CUDA events on the launching stream, algorithmic bytes)
-        'roofline_k4b': {'bound': 'hbm', 'kernel': 'masked_objective_kernel<GRAD> (K4b: 3 x mse + bce + gradient + 4 metrics)',
-                         'achieved': k4b_avg_bytes / (k4b_avg_ms * 1e-3) / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s',
-                         'frac': k4b_avg_bytes / (k4b_avg_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
-                         'algorithmic_bytes_per_launch': k4b_avg_bytes, 'avg_launch_ms': k4b_avg_ms, 'launches_timed': len(k4b_events),
-                         'share_of_step': k4b_avg_ms / (elapsed_ms / args.steps)},
+        'step': {'algorithmic_bytes': step_bytes, 'achieved_gb_per_s': step_bytes / (step_ms * 1e-3) / 1e9,
+                 'frac_of_measured_hbm_peak': step_bytes / (step_ms * 1e-3) / 1e9 / pk['hbm_gbs'],
+                 'frac_of_8000_nominal': step_bytes / (step_ms * 1e-3) / 1e9 / 8000.0,
+                 'kernels': 'K1 dur_scan + K2 + K4b per step, through utils.upsample_to_repetitions and fused.AcousticObjective; '
+                            'one all-reduce of the loss / metric records per epoch (N > 1)'},
+        'roofline': lines[dominant],
     }
+    for name, entry in lines.items():
+        if name != dominant:
+            line['roofline_' + name.lower()] = entry
+    line.update(extras)
     if world == 1 and not args.no_cpu_baseline:
-        sample, frames = make_cpu_sample(args.batch_size, CPU_SAMPLE_UTTS)
-        times, threads = time_cpu(sample, steps=8, warmup=1)
-        line['cpu_baseline'] = {'value': frames / min(times), 'unit': UNIT, 'cores': threads, 'kind': 'port',
-                                'sample': '%d of %d utterances (%d valid frames), best of %d passes of the reference op '
-                                          'chain (oracle/aten_chain.py) on %s' % (CPU_SAMPLE_UTTS, args.batch_size, frames,
-                                                                                 len(times), cpu_model_name())}
+        path = ReferencePath()
+        sample, frames = make_cpu_sample(workloads, args.batch_size, args.batch_size)
+        times, threads = time_cpu(path, sample, steps=5, warmup=1)
+        line['cpu_baseline'] = {'value': frames / min(times), 'unit': UNIT, 'cores': threads, 'kind': path.kind,
+                                'sample': 'all %d utterances (%d valid frames), best of %d passes of %s (imported from %s) on %s'
+                                          % (args.batch_size, frames, len(times),
+                                             'the unmodified reference functions' if path.available else 'the restated op chain',
+                                             path.where, cpu_model_name())}
     emit(line)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 

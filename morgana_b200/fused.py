@@ -69,12 +69,13 @@ class AcousticObjective(object):
         self._slot_dims = [w_lf0, w_mcep, w_bap, w_vuv, 1, 1, self.mcep_static - 1, 1]
         return ops.column_table(cols, device)
 
-    def __call__(self, pred, target, n_frames, want_grad=True, grad_scale_dev=None):
+    def __call__(self, pred, target, n_frames, want_grad=True, grad_scale_dev=None, loss_records=None):
         """-> ``(loss, grad)``: the 0-dim total loss and d loss / d pred (``None`` unless `want_grad`).
 
         ``pred`` / ``target``: (B, T, total_dim) float32; the vuv column of ``pred`` is a probability and of ``target`` is
         0/1.  ``n_frames``: (B,) lengths.  Metric state is updated in place (see ``self.metrics``).
-        One launch of the whole-row kernel (K4b); ``last_loss_records`` holds the four per-term losses.
+        One launch of the whole-row kernel (K4b); ``last_loss_records`` holds the four per-term losses (written into
+        ``loss_records``, a (4, 48) uint8 device block, when the caller keeps a per-step log of them).
         """
         ops._require_cuda(pred, 'pred')
         ops._require_cuda(target, 'target')
@@ -97,7 +98,8 @@ class AcousticObjective(object):
                 sl.weighted = int(i == 4)
                 if i >= 4:
                     sl.result = self._records[i - 4].data_ptr()
-        loss_records = ops.new_output_records(4, pred.device)
+        if loss_records is None:
+            loss_records = ops.new_output_records(4, pred.device)
         for i in range(4):
             self._slots[i].result = loss_records[i].data_ptr()
         grad = torch.empty((B, T, D), dtype=torch.float32, device=pred.device) if want_grad else None

@@ -48,6 +48,48 @@ def _ptr(tensor):
     return tensor.data_ptr() if tensor is not None else None
 
 
+class KernelProbe(object):
+    """CUDA events around named kernel launches made through the public ops, on the stream they are launched on.
+
+        with ops.KernelProbe('K2', 'K4b') as probe:      # measurement only: a pair of event records costs ~3 us of the stream
+            out = utils.upsample_to_repetitions(...)
+        torch.cuda.synchronize()
+        probe.ms('K2')                                   # list of launch durations in ms
+
+    Names: ``K1`` (duration scan), ``K2`` (normalise + expansion), ``K4b`` (whole-row objective).  Without an active probe the
+    ops record nothing.
+    """
+    active = None
+
+    def __init__(self, *names):
+        self.names = frozenset(names)
+        self.events = dict((name, []) for name in names)
+        self._open = {}
+
+    def __enter__(self):
+        self._previous, KernelProbe.active = KernelProbe.active, self
+        return self
+
+    def __exit__(self, *exc):
+        KernelProbe.active = self._previous
+
+    def begin(self, name):
+        if name in self.names:
+            event = torch.cuda.Event(enable_timing=True)
+            event.record(torch.cuda.current_stream())
+            self._open[name] = event
+
+    def end(self, name):
+        start = self._open.pop(name, None)
+        if start is not None:
+            stop = torch.cuda.Event(enable_timing=True)
+            stop.record(torch.cuda.current_stream())
+            self.events[name].append((start, stop))
+
+    def ms(self, name):
+        return [a.elapsed_time(b) for a, b in self.events[name]]
+
+
 # ----------------------------------------------------------------------------------------------------------------------
 # K1 + K2: duration scan and fused normalise + expansion
 # ----------------------------------------------------------------------------------------------------------------------
@@ -140,10 +182,15 @@ def _upsample_forward(x, repeats, norm, max_len, path, out_dtype=None):
                                                    _ptr(out), B, P, D, T, _stream()), 'mg_upsample_norm_f32_bf16out')
         return out, ends, n_frames, (mode, p0, p1, p_sb)
     out = torch.empty((B, T, D), dtype=x.dtype, device=x.device)
+    probe = KernelProbe.active
     with _device_of(x):
         if x.dtype == torch.float32:
+            if probe is not None:
+                probe.begin('K2')
             check(lib.mg_upsample_norm_f32(_ptr(x), x.stride(0), x.stride(1), _ptr(ends), _ptr(p0), _ptr(p1), p_sb, mode,
                                            _ptr(out), B, P, D, T, _PATHS[path], _stream()), 'mg_upsample_norm_f32')
+            if probe is not None:
+                probe.end('K2')
         else:
             if mode != _lib.NORM_NONE:
                 raise TypeError('fused normalisation needs float32 features, got {}'.format(x.dtype))
@@ -487,9 +534,14 @@ def masked_objective(pred, target, seq_len, cols, slots, grad=None, grad_scale_d
     n_slots = len(slots)
     ws = _workspace(pred.device, n_slots, B, T)
     g_sb, g_st = (grad.stride(0), grad.stride(1)) if grad is not None else (0, 0)
+    probe = KernelProbe.active
+    if probe is not None:
+        probe.begin('K4b')
     check(lib.mg_masked_objective_f32(_ptr(pred), p_sb, p_st, _ptr(target), t_sb, t_st, _ptr(grad), g_sb, g_st,
                                       _ptr(grad_scale_dev), _ptr(cols), D, slots, n_slots, _ptr(seq_len), B, T, _ptr(ws),
                                       ws.numel(), _stream()), 'mg_masked_objective_f32')
+    if probe is not None:
+        probe.end('K4b')
 
 
 _LOSS_KINDS = {'mse': _lib.RED_SQDIFF, 'l1': _lib.RED_ABSDIFF, 'bce': _lib.RED_BCE, 'ce': _lib.RED_CE, 'mean': _lib.RED_SUM}
@@ -639,6 +691,21 @@ def ema_update(pairs, one_minus_decay, plan=None):
             raise NotImplementedError('EMA needs contiguous parameters (the update is in place on their storage)')
     plan = (plan or EmaPlan()).update(pairs)
     with _device_of(pairs[0][0]):
+        check(lib.mg_ema_update_f32(plan.shadow, plan.param, plan.numel, plan.n, ctypes.c_float(one_minus_decay),
+                                    _stream()), 'mg_ema_update_f32')
+
+
+def ema_update_tensors(shadows, params, one_minus_decay, plan):
+    """:func:`ema_update` for a fixed list of tensors that is updated every step: the checks and the pointer tables are redone
+    only when a storage moved (the per-step cost is one ``data_ptr()`` per tensor and the launch)."""
+    key = tuple(t.data_ptr() for t in params) + tuple(t.data_ptr() for t in shadows)
+    if getattr(plan, 'fast_key', None) != key or plan.n != len(params):
+        ema_update([(s, p.detach()) for s, p in zip(shadows, params)], one_minus_decay, plan=plan)
+        plan.fast_key = key
+        return
+    if not params:
+        return
+    with _device_of(shadows[0]):
         check(lib.mg_ema_update_f32(plan.shadow, plan.param, plan.numel, plan.n, ctypes.c_float(one_minus_decay),
                                     _stream()), 'mg_ema_update_f32')
 

@@ -71,6 +71,7 @@ class ExponentialMovingAverage(object):
             if param.requires_grad:
                 self.shadow[name] = param.data
         self._plan = ops.EmaPlan()
+        self._pairing = None      # (other_model, its parameters that have a shadow, their shadows)
 
     def _update_param(self, name, x):
         """One tensor: ``shadow -= (1 - decay) * (shadow - x)``."""
@@ -80,9 +81,11 @@ class ExponentialMovingAverage(object):
     def update_params(self, other_model):
         """All tensors of ``other_model`` that have a shadow, in one launch per 64 tensors."""
         assert other_model is not self.model
-        pairs = [(self.shadow[name], param.data) for name, param in other_model.named_parameters()
-                 if name in self.shadow]
-        ops.ema_update(pairs, 1.0 - self.decay, plan=self._plan)
+        pairing = self._pairing
+        if pairing is None or pairing[0] is not other_model:
+            named = [(name, param) for name, param in other_model.named_parameters() if name in self.shadow]
+            pairing = self._pairing = (other_model, [param for _, param in named], [self.shadow[name] for name, _ in named])
+        ops.ema_update_tensors(pairing[2], pairing[1], 1.0 - self.decay, self._plan)
 
 
 def upsample_packed_to_repetitions(packed_feature, packed_repeats, n_items, normaliser=None, deltas=False, max_len=None,
