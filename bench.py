@@ -339,8 +339,8 @@ def run_ours(args, rank, world, local_rank):
     # ---- warm-up ---------------------------------------------------------------------------------------------------
     for i in range(max(args.warmup, 3)):
         step(dev_batches[i % N_ROTATING_BATCHES], scratch_records)
-    if world > 1:
-        dp.allreduce_records(scratch_records)          # NCCL communicator set-up outside the timed region
+    if world > 1:     # NCCL communicator and protocol set-up for this message size outside the timed region
+        dp.allreduce_records(loss_log.reshape(-1, loss_log.shape[-1]), objective._records)
     barrier()
 
     # ---- timed region: exactly K steps, device-resident inputs ---------------------------------------------------------

@@ -341,11 +341,15 @@ int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, int64_t ldx,
 
 /* ---------------------------------------------------------------------------------------------------------------
  * K8  batched MLPG ("next" row 1 of the scope table) -- replaces viz.synthesis.MLPG (morgana/viz/synthesis.py:79-180)
- *     with the reference's default windows [1], [-0.5, 0, 0.5], [1, -2, 1] (synthesis.py:122-127): for every utterance and
- *     static dimension, the pentadiagonal system (sum_k W_k^T diag(1/var_k) W_k) c = sum_k W_k^T (mean_k / var_k) is built
- *     and solved in fp64 over n + 2 * padding edge-replicated frames; c without the padding is the trajectory.
+ *     for windows that reach at most one frame to either side (the reference's defaults [1], [-0.5, 0, 0.5], [1, -2, 1],
+ *     synthesis.py:122-127, or any other 1 .. 4 such windows): for every utterance and static dimension, the pentadiagonal
+ *     system (sum_k W_k^T diag(1/var_k) W_k) c = sum_k W_k^T (mean_k / var_k) is built and solved in fp64 over n + 2 * padding
+ *     edge-replicated frames; c without the padding is the trajectory.
  *
- * means      (B, T, 3 * feat_dim) fp32, layout [static | delta | delta-delta]; strides in elements, inner contiguous.
+ * means      (B, T, n_windows * feat_dim) fp32, layout [window 0 | window 1 | ...] (static | delta | delta-delta for the
+ *            defaults); strides in elements, inner contiguous.
+ * windows    HOST array of n_windows x 3 doubles, window k's coefficients at frame offsets (-1, 0, +1) (0 where the window
+ *            does not reach), or NULL for the reference's three default windows (n_windows is then ignored).
  * variances  same layout; per frame (v_sb, v_st as for means), per utterance (v_st = 0) or global (v_sb = v_st = 0).
  * seq_len    (B,) int64 or NULL (all T frames).  out (B, T, feat_dim) fp32; frames past seq_len are zero.
  * workspace  mg_mlpg_workspace_bytes(B, T, feat_dim, padding) bytes of device memory (no initialisation needed).
@@ -353,7 +357,7 @@ int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, int64_t ldx,
 int64_t mg_mlpg_workspace_bytes(int B, int64_t T, int feat_dim, int padding);
 int mg_mlpg_f32(const float* means, int64_t m_sb, int64_t m_st, const float* variances, int64_t v_sb, int64_t v_st,
                 const int64_t* seq_len, float* out, int64_t o_sb, int64_t o_st, int B, int64_t T, int feat_dim, int padding,
-                void* workspace, int64_t workspace_bytes, mg_stream_t stream);
+                const double* windows, int n_windows, void* workspace, int64_t workspace_bytes, mg_stream_t stream);
 
 /* losses.KLD_standard_normal (morgana/losses.py:64-67): loss = mean over rows of -0.5 * sum_d (1 + log_variance - mean^2 -
  * exp(log_variance)), mean / log_variance contiguous (rows, latent_dim) fp32.  loss: one float on the device (or NULL).
@@ -371,6 +375,10 @@ int mg_both_nonzero_u8(const float* const* features, int n_features, int64_t n, 
 /* fp32 -> bf16 row conversion with K padding: feeds K7 from the fp32 frame-rate features and weights of the example models'
  * nn.Linear layers (README.rst:65-73, models/RNN_SPSS.py:33-41); pads K to ld_out with 0. */
 int mg_cast_pad_bf16(const float* x, int64_t ldx, void* out, int64_t ld_out, int64_t rows, int K, mg_stream_t stream);
+/* fp32 weight (N, K), row stride ldw -> its transpose (K, ld_out >= N) in bf16, columns N.. zero: the B operand of the input
+ * gradient of nn.Linear, grad_x = g @ W (autograd's mm in `loss.backward()`, experiment_builder.py:470), run as g @ (W^T)^T
+ * through mg_linear_bf16.  One small launch per layer and step, instead of a transpose + pad + copy of the bf16 weight. */
+int mg_cast_transpose_bf16(const float* w, int64_t ldw, void* out, int64_t ld_out, int N, int K, mg_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -89,7 +89,7 @@ PROTOTYPES = {
                                   c_f32, c_void_p]),
     'mg_mlpg_workspace_bytes': (c_i64, [c_int, c_i64, c_int, c_int]),
     'mg_mlpg_f32': (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_void_p, c_i64, c_i64, c_int, c_i64, c_int,
-                            c_int, c_void_p, c_i64, c_void_p]),
+                            c_int, ctypes.POINTER(ctypes.c_double), c_int, c_void_p, c_i64, c_void_p]),
     'mg_linear_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_void_p, c_void_p, c_i64, c_int, c_int, c_int, c_int,
                                c_int, c_void_p]),
     'mg_act_grad_workspace_bytes': (c_i64, [c_i64, c_int]),
@@ -104,6 +104,7 @@ PROTOTYPES = {
                                            c_void_p]),
     'mg_both_nonzero_u8': (c_int, [ctypes.POINTER(c_void_p), c_int, c_i64, c_void_p, c_void_p]),
     'mg_cast_pad_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_i64, c_int, c_void_p]),
+    'mg_cast_transpose_bf16': (c_int, [c_void_p, c_i64, c_void_p, c_i64, c_int, c_int, c_void_p]),
 }
 
 LIB_PATH = _build.LIB_PATH

@@ -357,7 +357,37 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
   }
 }
 
+// W (N, K) fp32 row-major -> W^T (K, ld_out >= N) bf16, columns N.. zero: the B operand of the input-gradient GEMM
+// (grad_x = g @ W runs through the forward kernel as g @ (W^T)^T).  32 x 32 tiles through shared memory, both sides coalesced.
+__global__ void __launch_bounds__(256)
+cast_transpose_kernel(const float* __restrict__ w, int64_t ldw, __nv_bfloat16* __restrict__ out, int64_t ld_out, int N, int K) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
+  for (int r = ty; r < 32; r += 8) {
+    const int n = n0 + r, k = k0 + tx;
+    tile[r][tx] = (n < N && k < K) ? __ldg(w + static_cast<int64_t>(n) * ldw + k) : 0.f;
+  }
+  __syncthreads();
+  for (int r = ty; r < 32; r += 8) {
+    const int k = k0 + r, n = n0 + tx;
+    if (k < K && n < ld_out) out[static_cast<int64_t>(k) * ld_out + n] = __float2bfloat16_rn(tile[tx][r]);
+  }
+}
+
 }  // namespace
+
+extern "C" int mg_cast_transpose_bf16(const float* w, int64_t ldw, void* out, int64_t ld_out, int N, int K, mg_stream_t stream_) {
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  MG_REQUIRE(N >= 0 && K >= 0 && ldw >= K && ld_out >= N, "mg_cast_transpose_bf16: bad shape");
+  MG_REQUIRE(ld_out % 8 == 0 && mg_aligned(out, 16), "mg_cast_transpose_bf16: output rows must be 16-byte aligned");
+  if (K == 0 || ld_out == 0) return MG_OK;
+  MG_REQUIRE(out != nullptr && (N == 0 || w != nullptr), "mg_cast_transpose_bf16: NULL buffer");
+  dim3 grid(static_cast<unsigned>((K + 31) / 32), static_cast<unsigned>((ld_out + 31) / 32));
+  cast_transpose_kernel<<<grid, 256, 0, stream>>>(w, ldw, static_cast<__nv_bfloat16*>(out), ld_out, N, K);
+  MG_LAUNCH_OK();
+  return MG_OK;
+}
 
 extern "C" int mg_cast_pad_bf16(const float* x, int64_t ldx, void* out, int64_t ld_out, int64_t rows, int K,
                                 mg_stream_t stream_) {

@@ -26,10 +26,13 @@
 //          c_j = g_j - U_L x_{j-1} - U_R x_j for its frames, with no dependence between frames.
 //          This is exact block elimination in a nested-dissection order (no truncation), fp64 throughout as in the
 //          reference; the output is fp32.  ~4 L / 32 + 2 S dependent steps instead of 2 L.
+#include <string.h>
+
 #include "mg_common.cuh"
 
 namespace {
 
+constexpr int kMaxWindows = 4;
 constexpr int kWork = 8;            // doubles per (system, frame) in the workspace: one 64-byte line
 constexpr int kSolveWarps = 4;      // systems per CTA of the solve kernel
 constexpr int kAhead = 4;           // frames whose operands are requested before the dependent arithmetic of a batch
@@ -43,6 +46,8 @@ struct MlpgParams {
   double* work;        // [B * F systems][L_max frames][kWork]
   int64_t m_sb, m_st, v_sb, v_st, o_sb, o_st, T, L_max;
   int B, F, padding;
+  int n_windows;            // 1 .. kMaxWindows windows of extent <= 1 frame on either side
+  double coef[4][3];        // window k at offsets (-1, 0, +1)
 };
 
 __device__ __forceinline__ int64_t mlpg_valid(const MlpgParams& prm, int i) {
@@ -81,18 +86,38 @@ __global__ void __launch_bounds__(256) mlpg_build_kernel(const MlpgParams prm) {
     tau = 1.0 / v;
     bt = m * tau;     // one fp64 division per operand pair (within 1 ulp of m / v)
   };
-  // window coefficients at offsets (-1, 0, +1): w0 = (0, 1, 0), w1 = (-0.5, 0, 0.5), w2 = (1, -2, 1)
-  double bt0, tau0, bt1[3], tau1[3], bt2[3], tau2[3];
-  load(a, 0, bt0, tau0);
-#pragma unroll
-  for (int j = 0; j < 3; ++j) {
-    load(a - 1 + j, 1, bt1[j], tau1[j]);
-    load(a - 1 + j, 2, bt2[j], tau2[j]);
+  // Window k has coefficients c_k at offsets (-1, 0, +1) (defaults: (0, 1, 0), (-0.5, 0, 0.5), (1, -2, 1)); with W_k[t][t + j] =
+  // c_k[j] truncated at the ends:
+  //   P[a][a]   = sum_k sum_{t = a-1..a+1} c_k[a - t]^2 tau_k[t]
+  //   P[a][a+1] = sum_k c_k[0] c_k[+1] tau_k[a] + c_k[-1] c_k[0] tau_k[a+1]
+  //   P[a][a+2] = sum_k c_k[-1] c_k[+1] tau_k[a+1]
+  //   b[a]      = sum_k sum_{t = a-1..a+1} c_k[a - t] (mean_k / var_k)[t]
+  // Zero coefficients are skipped (warp-uniform), so the default windows cost what they did before.
+  double p0 = 0., p1 = 0., p2 = 0., bsum = 0.;
+  for (int k = 0; k < prm.n_windows; ++k) {
+    const double cm = prm.coef[k][0], c0 = prm.coef[k][1], cp = prm.coef[k][2];
+    double bt, tau;
+    if (c0 != 0.) {
+      load(a, k, bt, tau);
+      p0 += c0 * c0 * tau;
+      p1 += c0 * cp * tau;
+      bsum += c0 * bt;
+    }
+    if (cp != 0.) {            // frame a - 1 reaches a through its +1 coefficient
+      load(a - 1, k, bt, tau);
+      p0 += cp * cp * tau;
+      bsum += cp * bt;
+    }
+    if (cm != 0.) {            // frame a + 1 reaches a through its -1 coefficient
+      load(a + 1, k, bt, tau);
+      p0 += cm * cm * tau;
+      p1 += cm * c0 * tau;
+      p2 += cm * cp * tau;
+      bsum += cm * bt;
+    }
   }
-  const double p0 = tau0 + 4.0 * tau2[1] + 0.25 * tau1[0] + tau2[0] + 0.25 * tau1[2] + tau2[2];
-  const double p1 = a + 1 < L ? -2.0 * tau2[1] - 2.0 * tau2[2] : 0.;
-  const double p2 = a + 2 < L ? -0.25 * tau1[2] + tau2[2] : 0.;
-  const double bsum = bt0 - 2.0 * bt2[1] + 0.5 * bt1[0] + bt2[0] - 0.5 * bt1[2] + bt2[2];
+  if (a + 1 >= L) p1 = 0.;
+  if (a + 2 >= L) p2 = 0.;
   double2* w = reinterpret_cast<double2*>(prm.work + ((static_cast<int64_t>(i) * F + d) * prm.L_max + a) * kWork);
   w[0] = make_double2(p0, p1);
   w[1] = make_double2(p2, bsum);
@@ -343,7 +368,8 @@ extern "C" int64_t mg_mlpg_workspace_bytes(int B, int64_t T, int feat_dim, int p
 
 extern "C" int mg_mlpg_f32(const float* means, int64_t m_sb, int64_t m_st, const float* variances, int64_t v_sb, int64_t v_st,
                            const int64_t* seq_len, float* out, int64_t o_sb, int64_t o_st, int B, int64_t T, int feat_dim,
-                           int padding, void* workspace, int64_t workspace_bytes, mg_stream_t stream_) {
+                           int padding, const double* windows, int n_windows, void* workspace, int64_t workspace_bytes,
+                           mg_stream_t stream_) {
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   MG_REQUIRE(B >= 0 && T >= 0 && feat_dim >= 0 && padding >= 0, "mg_mlpg_f32: negative shape");
   MG_REQUIRE(B <= 65535 * 32, "mg_mlpg_f32: B too large");
@@ -357,6 +383,15 @@ extern "C" int mg_mlpg_f32(const float* means, int64_t m_sb, int64_t m_st, const
   prm.m_sb = m_sb; prm.m_st = m_st; prm.v_sb = v_sb; prm.v_st = v_st; prm.o_sb = o_sb; prm.o_st = o_st;
   prm.T = T; prm.L_max = T + 2 * static_cast<int64_t>(padding);
   prm.B = B; prm.F = feat_dim; prm.padding = padding;
+  if (windows == nullptr) {      // the reference's defaults (synthesis.py:122-127)
+    static const double defaults[3][3] = {{0., 1., 0.}, {-0.5, 0., 0.5}, {1., -2., 1.}};
+    prm.n_windows = 3;
+    memcpy(prm.coef, defaults, sizeof(defaults));
+  } else {
+    MG_REQUIRE(n_windows >= 1 && n_windows <= kMaxWindows, "mg_mlpg_f32: %d windows (1 .. %d are provided)", n_windows, kMaxWindows);
+    prm.n_windows = n_windows;
+    memcpy(prm.coef, windows, sizeof(double) * 3 * n_windows);
+  }
   const int64_t build_threads = static_cast<int64_t>(B) * prm.L_max * feat_dim;
   const int64_t build_ctas = (build_threads + 255) / 256;
   const int64_t systems = static_cast<int64_t>(B) * feat_dim;

@@ -6,9 +6,9 @@ a forward pass that is one ``mg_linear_bf16`` launch with the bias and the sigmo
 
 Forward tolerance (stated in tests/test_gpu_parity.py): bf16 operands, fp32 accumulation -> <= 2 % of the output range
 against the fp32 layer, 2e-3 against the exact product of the bf16-rounded operands.
-Backward: the input gradient ``g @ W`` runs through the same tcgen05 kernel (``y = g @ (W^T)^T`` with a transposed bf16
-copy of the weight) where the reduction is long enough; the sigmoid's backward, the bf16 cast of the gradient and the bias
-gradient are one pass (``mg_act_grad_bf16``); the weight gradient ``g^T @ x`` reduces over the frame axis: MN-major tcgen05
+Backward: the input gradient ``g @ W`` runs through the same tcgen05 kernel for every layer width (``y = g @ (W^T)^T``; the
+transposed bf16 copy of the weight is one ``mg_cast_transpose_bf16`` launch from the fp32 master weight); the sigmoid's
+backward, the bf16 cast of the gradient and the bias gradient are one pass (``mg_act_grad_bf16``); the weight gradient ``g^T @ x`` reduces over the frame axis: MN-major tcgen05
 operands straight from the row-major tensors, frames split over the SMs, slices summed in a fixed order
 (``mg_linear_wgrad_bf16``).
 """
@@ -17,21 +17,18 @@ import torch
 from morgana_b200 import ops
 
 
-_DGRAD_MIN_REDUCTION = 256   # out_features from which the input gradient goes through the tcgen05 kernel
-
-
 class _LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2d, weight, bias, weight_bf16, act, out_dtype):
         x_bf16 = ops.cast_pad_bf16(x2d) if x2d.dtype == torch.float32 else x2d
         y = ops.linear_bf16(x_bf16, weight_bf16, bias, act=act, out_dtype=out_dtype)
-        ctx.save_for_backward(x_bf16, weight_bf16, y if act == 'sigmoid' else None)
+        ctx.save_for_backward(x_bf16, weight_bf16, y if act == 'sigmoid' else None, weight)
         ctx.act, ctx.k, ctx.has_bias, ctx.x_dtype = act, weight.shape[1], bias is not None, x2d.dtype
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
-        x_bf16, weight_bf16, y = ctx.saved_tensors
+        x_bf16, weight_bf16, y, weight = ctx.saved_tensors
         k, n = ctx.k, weight_bf16.shape[0]
         if grad_y.dtype not in (torch.float32, torch.bfloat16):
             grad_y = grad_y.to(torch.float32)
@@ -41,15 +38,10 @@ class _LinearFn(torch.autograd.Function):
         g16, grad_b = ops.act_grad_bf16(grad_y, y if ctx.act == 'sigmoid' else None,
                                         want_bias_grad=ctx.has_bias and ctx.needs_input_grad[2])
         grad_x = None
-        if ctx.needs_input_grad[0] and n < _DGRAD_MIN_REDUCTION:
-            # short reductions (the 128- / 32- / 1-wide layers): two K blocks per tile leave the persistent pipeline mostly
-            # filling and draining -- the library GEMM is faster there (README MLP training step 0.81 vs 0.86 ms)
-            grad_x = torch.matmul(g16[:, :n], weight_bf16[:, :k]).to(ctx.x_dtype)
-        elif ctx.needs_input_grad[0]:
-            # dgrad on the tensor cores: (M, N) @ (N, K) as the forward kernel sees it, x' = g16 (M, N'), w' = W^T (K, N')
-            n_pad = g16.shape[1]
-            w_t = weight_bf16[:, :k].t()
-            w_t = w_t.contiguous() if n == n_pad else torch.nn.functional.pad(w_t, (0, n_pad - n))
+        if ctx.needs_input_grad[0]:
+            # dgrad on the tensor cores, every width: (M, N') @ (N', K) as the forward kernel sees it, x' = g16 (M, N'),
+            # w' = W^T (K, N') cast + transposed from the fp32 weight by one small kernel (N' = N rounded up to 8, zero padded)
+            w_t = ops.cast_transpose_bf16(weight.detach())
             grad_x = ops.linear_bf16(g16, w_t, None, act=None, out_dtype=torch.float32 if ctx.x_dtype == torch.float32
                                      else torch.bfloat16)
         grad_w = None

@@ -749,6 +749,23 @@ def cast_pad_bf16(x, k_padded=None):
     return out
 
 
+def cast_transpose_bf16(weight):
+    """fp32 ``(N, K)`` weight -> its transpose ``(K, round_up(N, 8))`` in bf16 (zero padding columns): the B operand of the
+    input-gradient GEMM ``g @ W`` as :func:`linear_bf16` takes it."""
+    _require_cuda(weight, 'weight')
+    if weight.dim() != 2 or weight.dtype != torch.float32:
+        raise TypeError('cast_transpose_bf16 takes a 2-D float32 tensor')
+    if weight.shape[1] > 1 and weight.stride(1) != 1:
+        weight = weight.contiguous()
+    N, K = weight.shape
+    ld_out = (N + 7) // 8 * 8
+    out = torch.empty((K, ld_out), dtype=torch.bfloat16, device=weight.device)
+    with _device_of(weight):
+        check(lib.mg_cast_transpose_bf16(_ptr(weight), weight.stride(0) if N else K, _ptr(out), ld_out, N, K, _stream()),
+              'mg_cast_transpose_bf16')
+    return out
+
+
 _ACTS = {None: _lib.ACT_NONE, 'none': _lib.ACT_NONE, 'sigmoid': _lib.ACT_SIGMOID}
 
 
@@ -862,21 +879,46 @@ def linear_wgrad_bf16(g, x, out_features=None, in_features=None):
 _mlpg_workspaces = {}
 
 
-def mlpg(means, variances, padding_size=0, seq_len=None):
-    """Maximum-likelihood parameter generation for (B, T, 3F) [static | delta | delta-delta] means on the device.
+def mlpg_window_table(windows):
+    """The reference's ``windows`` argument -- a list of ``(l, u, win_coeff)`` with ``len(win_coeff) == l + u + 1``
+    (viz/synthesis.py:8-29) -- as rows of coefficients at frame offsets (-1, 0, +1).  Windows reaching further than one frame
+    to either side would widen the band of the system beyond the pentadiagonal solver: NotImplementedError."""
+    rows = []
+    for l, u, coeff in windows:
+        l, u = int(l), int(u)
+        coeff = [float(c) for c in coeff]
+        if l < 0 or u < 0 or len(coeff) != l + u + 1:
+            raise AssertionError('window (l, u, win_coeff) needs len(win_coeff) == l + u + 1')      # synthesis.py:31-32
+        if l > 1 or u > 1:
+            raise NotImplementedError('MLPG windows that reach more than one frame to either side are not provided '
+                                      '(got l={}, u={})'.format(l, u))
+        rows.append([coeff[l - 1] if l == 1 else 0., coeff[l], coeff[l + 1] if u == 1 else 0.])
+    if not 1 <= len(rows) <= 4:
+        raise NotImplementedError('MLPG takes 1 to 4 windows, got {}'.format(len(rows)))
+    return rows
 
-    ``variances``: (3F,) global, (B, 3F) per utterance or (B, T, 3F) per frame.  Returns (B, T, F) float32.
+
+def mlpg(means, variances, padding_size=0, seq_len=None, windows=None):
+    """Maximum-likelihood parameter generation for (B, T, W * F) means laid out window after window ([static | delta |
+    delta-delta] for the default windows) on the device.
+
+    ``variances``: (W * F,) global, (B, W * F) per utterance or (B, T, W * F) per frame.  ``windows``: None (the reference's
+    three defaults) or the rows :func:`mlpg_window_table` makes.  Returns (B, T, F) float32.
     """
     _require_cuda(means, 'means')
     _require_cuda(variances, 'variances')
     if means.dtype != torch.float32 or variances.dtype != torch.float32:
         raise TypeError('mlpg takes float32 means and variances')
-    if means.dim() != 3 or means.shape[2] % 3 != 0:
-        raise ValueError('means must be (batch_size, seq_len, 3 * feat_dim)')
+    n_windows = 3 if windows is None else len(windows)
+    if means.dim() != 3 or means.shape[2] % n_windows != 0:
+        raise ValueError('means must be (batch_size, seq_len, n_windows * feat_dim)')
     if means.stride(2) != 1:
         means = means.contiguous()
     B, T, D3 = means.shape
-    F = D3 // 3
+    F = D3 // n_windows
+    table = None
+    if windows is not None:
+        table = (ctypes.c_double * (3 * n_windows))(*[c for row in windows for c in row])
     variances = variances.contiguous()
     if variances.dim() == 1 and variances.shape[0] == D3:
         v_sb, v_st = 0, 0
@@ -899,7 +941,7 @@ def mlpg(means, variances, padding_size=0, seq_len=None):
         _mlpg_workspaces[key] = ws
     with _device_of(means):
         check(lib.mg_mlpg_f32(_ptr(means), means.stride(0), means.stride(1), _ptr(variances), v_sb, v_st, _ptr(seq_len), _ptr(out),
-                              out.stride(0), out.stride(1), B, T, F, int(padding_size), _ptr(ws), ws.numel() * 8, _stream()),
+                              out.stride(0), out.stride(1), B, T, F, int(padding_size), table, n_windows, _ptr(ws), ws.numel() * 8, _stream()),
               'mg_mlpg_f32')
     return out
 

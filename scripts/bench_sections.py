@@ -211,7 +211,9 @@ def other_configs(dev, peaks, reference_path=None):
 def training_section(rank, world, dev, peaks, steps=40, batch_size=32):
     """BASELINE.json configs[4]: README F0 MLP, data-parallel: every rank trains on its own 32 utterances per step, ONE NCCL
     all-reduce of the flat gradient buffer per step (trainer.GradientBucket), fused Adam, multi-tensor EMA, RMSE metric.
-    Weak scaling; times are CUDA events, max over ranks; the all-reduce is bracketed by its own events on every step."""
+    Weak scaling; CUDA events, max over ranks.  Three timings of the same step: eager (what a Python training loop gets:
+    host-bound at this batch size), replayed from a CUDA graph (device time), and the same graph without the all-reduce --
+    the difference is the collective's exposed time."""
     import morgana_b200 as mg
     from morgana_b200 import nn as mnn, trainer, workloads
     dims = [600, 512, 128, 32, 1]
@@ -219,81 +221,143 @@ def training_section(rank, world, dev, peaks, steps=40, batch_size=32):
     layers = torch.nn.ModuleList([mnn.Linear(dims[i], dims[i + 1], act='sigmoid' if i < 3 else None,
                                              out_dtype=torch.bfloat16 if i < 3 else torch.float32, device=dev) for i in range(4)])
     ema_layers = torch.nn.ModuleList([mnn.Linear(dims[i], dims[i + 1], device=dev) for i in range(4)])
-    ema_layers.load_state_dict(layers.state_dict())
     if world > 1:
         for p in layers.parameters():
             dist.broadcast(p.data, 0)
+    ema_layers.load_state_dict(layers.state_dict())
+    initial = {k: v.clone() for k, v in layers.state_dict().items()}
     bucket = trainer.GradientBucket(layers.parameters())
-    opt = torch.optim.Adam(layers.parameters(), lr=0.01, fused=True)
+    opt = torch.optim.Adam(layers.parameters(), lr=0.01, fused=True, capturable=True)
     ema = mg.utils.ExponentialMovingAverage(ema_layers, 0.999)
     rmse = mg.metrics.RMSE()
     rmse.reset_state()
-    batches = []
+    raw = []
     for i in range(4):
         ling = workloads.linguistic_batch(batch_size=batch_size, seed=4096 + 31 * i + 1009 * rank)     # this rank's shard
-        T = int(ling['n_frames'].max())
         g = torch.Generator().manual_seed(99 + i + 1009 * rank)
-        batches.append({'lab': ling['lab'].to(dev), 'dur': ling['dur'].to(dev), 'n_frames': ling['n_frames'].to(dev), 'T': T,
-                        'target': torch.randn(batch_size, T, 1, generator=g).to(dev), 'frames': int(ling['n_frames'].sum()),
-                        'mmin': ling['mmin'].to(dev), 'mmax': ling['mmax'].to(dev)})
-    ar_events = []
+        raw.append((ling, torch.randn(batch_size, int(ling['n_frames'].max()), 1, generator=g)))
+    # static shapes (one P and T for the run) so the step can be captured; the kernels mask by n_frames, padding changes nothing
+    P_max = max(l['lab'].shape[1] for l, _ in raw)
+    T_max = max(int(l['n_frames'].max()) for l, _ in raw)
+    if world > 1:
+        dims_t = torch.tensor([P_max, T_max], device=dev)
+        dist.all_reduce(dims_t, op=dist.ReduceOp.MAX)
+        P_max, T_max = (int(v) for v in dims_t.tolist())
+    pad = torch.nn.functional.pad
+    batches = []
+    for ling, tgt in raw:
+        batches.append({'lab': pad(ling['lab'], (0, 0, 0, P_max - ling['lab'].shape[1])).to(dev),
+                        'dur': pad(ling['dur'], (0, 0, 0, P_max - ling['dur'].shape[1])).to(dev),
+                        'n_frames': ling['n_frames'].to(dev), 'target': pad(tgt, (0, 0, 0, T_max - tgt.shape[1])).to(dev),
+                        'frames': int(ling['n_frames'].sum())})
+    mmin, mmax = raw[0][0]['mmin'].to(dev), raw[0][0]['mmax'].to(dev)
+    static = {k: torch.empty_like(batches[0][k]) for k in ('lab', 'dur', 'n_frames', 'target')}
     stream = torch.cuda.current_stream()
 
-    def train_step(b, timed):
+    def train_step(b, exchange=True):
         bucket.zero()
-        h = mg.utils.upsample_to_repetitions(b['lab'], b['dur'], normaliser=('minmax', b['mmin'], b['mmax']), max_len=b['T'],
+        h = mg.utils.upsample_to_repetitions(b['lab'], b['dur'], normaliser=('minmax', mmin, mmax), max_len=T_max,
                                              out_dtype=torch.bfloat16)
         for layer in layers:
             h = layer(h)
         loss = mg.losses.mse(h, b['target'], b['n_frames'])
         loss.backward()
-        if world > 1:
-            if timed:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
+        if exchange:
             bucket.all_reduce()
-            if timed:
-                e1.record(stream)
-                ar_events.append((e0, e1))
         opt.step()
         ema.update_params(layers)
         rmse.accumulate(b['target'], h.detach(), seq_len=b['n_frames'])
         return loss
 
+    def load(b):
+        for k in static:
+            static[k].copy_(b[k])
+
+    def reset():
+        layers.load_state_dict(initial)
+        ema_layers.load_state_dict(initial)
+        for state in opt.state.values():
+            for value in state.values():
+                if isinstance(value, torch.Tensor):
+                    value.zero_()
+
+    def timed(run_step):
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        frames, loss = 0, None
+        start.record(stream)
+        for i in range(steps):
+            loss = run_step(batches[i % 4])
+            frames += batches[i % 4]['frames']
+        stop.record(stream)
+        torch.cuda.synchronize()
+        stats = torch.tensor([start.elapsed_time(stop) / steps, float(frames)], dtype=torch.float64, device=dev)
+        if world > 1:
+            t = stats[:1].clone()
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            f = stats[1:].clone()
+            dist.all_reduce(f)
+            stats = torch.cat([t, f])
+        ms, frames = stats.tolist()
+        return ms, frames, float(loss.detach())
+
+    # eager
     for i in range(5):
-        first = train_step(batches[i % 4], False)
-    first_loss = float(first.detach())
+        first = train_step(batches[i % 4])
+    reset()
+    first_loss = float(train_step(batches[0]).detach())
+    eager_ms, frames, eager_last = timed(train_step)
+
+    # captured: warm up on a side stream as torch.cuda.graphs asks, reset the state in place, capture, replay
+    graphs = {}
+    side = torch.cuda.Stream(device=dev)
+    for name, exchange in (('with_allreduce', True), ('without_allreduce', False)):
+        side.wait_stream(stream)
+        with torch.cuda.stream(side):
+            for i in range(3):
+                load(batches[i % 4])
+                train_step(static, exchange)
+        stream.wait_stream(side)
+        reset()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = train_step(static, exchange)
+        graphs[name] = (graph, static_loss)
+
+    def replay(name):
+        graph, static_loss = graphs[name]
+
+        def run(b):
+            load(b)
+            graph.replay()
+            return static_loss
+        return run
+    graph_ms, _, graph_last = timed(replay('with_allreduce'))
+    reset()
+    bare_ms, _, _ = timed(replay('without_allreduce'))
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    frames = 0
-    start.record(stream)
-    for i in range(steps):
-        loss = train_step(batches[i % 4], True)
-        frames += batches[i % 4]['frames']
-    stop.record(stream)
-    torch.cuda.synchronize()
-    ms = start.elapsed_time(stop) / steps
-    ar_ms = sum(a.elapsed_time(b) for a, b in ar_events) / len(ar_events) if ar_events else 0.
-    stats = torch.tensor([ms, ar_ms, float(frames)], dtype=torch.float64, device=dev)
-    if world > 1:
-        t = stats[:2].clone()
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        f = stats[2:].clone()
-        dist.all_reduce(f)
-        stats = torch.cat([t, f])
-    ms, ar_ms, frames = stats.tolist()
+    for graph, _ in graphs.values():       # a captured NCCL all-reduce must be released before the process group goes away
+        graph.reset()
+    graphs.clear()
     n_par = bucket.flat.numel()
-    return {'config': 'configs[4] / configs[0] model: README F0 MLP 600-512-128-32-1, %d utterances per rank per step, eager '
+    exposed = max(graph_ms - bare_ms, 0.) if world > 1 else 0.
+    return {'config': 'configs[4] / configs[0] model: README F0 MLP 600-512-128-32-1, %d utterances per rank per step '
                       '(one process per GPU; utterances sharded)' % batch_size,
-            'n_gpus': world, 'steps': steps, 'ms_per_step': round(ms, 4), 'valid_frames_per_s': round(frames / (ms * steps) * 1e3),
-            'gradient_allreduce': {'bytes': 4 * n_par, 'ms': round(ar_ms, 4), 'share_of_step': round(ar_ms / ms, 4) if ms else None,
-                                   'what': 'one NCCL all-reduce of the flat fp32 gradient buffer after backward (no overlap: the '
-                                           'four layers\' gradients are %d KB, the collective is launch-latency sized)' % (4 * n_par // 1024)},
-            'loss_first_last': [round(first_loss, 5), round(float(loss.detach()), 5)],
+            'n_gpus': world, 'steps': steps,
+            'ms_per_step': round(graph_ms, 4), 'valid_frames_per_s': round(frames / (graph_ms * steps) * 1e3),
+            'eager_ms_per_step': round(eager_ms, 4), 'eager_valid_frames_per_s': round(frames / (eager_ms * steps) * 1e3),
+            'gradient_allreduce': {'bytes': 4 * n_par, 'exposed_ms': round(exposed, 4),
+                                   'share_of_step': round(exposed / graph_ms, 4) if graph_ms else None,
+                                   'step_without_it_ms': round(bare_ms, 4),
+                                   'what': 'one NCCL all-reduce of the flat fp32 gradient buffer (%d KB) between backward and Adam, '
+                                           'captured in the step\'s CUDA graph; exposed = step with - step without the collective'
+                                           % (4 * n_par // 1024)},
+            'loss_first_last': [round(first_loss, 5), round(graph_last, 5)],
             'step': 'upsample_to_repetitions (fused minmax, bf16 frames) -> 4 x nn.Linear (tcgen05 forward, act-grad, weight-gradient, '
-                    'input-gradient kernels) -> losses.mse -> backward -> all-reduce -> fused Adam -> EMA (K6) -> RMSE metric'}
+                    'input-gradient kernels) -> losses.mse -> backward -> all-reduce -> fused Adam -> EMA (K6) -> RMSE metric; '
+                    'ms_per_step = the whole step replayed from one CUDA graph, eager_ms_per_step = the same Python loop un-captured'}
 
 
 if __name__ == '__main__':

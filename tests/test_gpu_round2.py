@@ -180,3 +180,204 @@ def test_sequence_mask_on_cuda_lengths(mg, dtype):
     # it multiplies into (B, T, D) tensors as the reference's callers use it (losses.py:34-37)
     x = torch.ones(5, 7, 3, device='cuda')
     assert (x * mg.utils.sequence_mask(seq_len, dtype=torch.float32)).sum().item() == 3. * 18
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# a14 backward: the input gradient of every layer width runs through the tcgen05 kernel (no library GEMM)
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('M,K,N', [(1000, 32, 1), (777, 128, 32), (2049, 512, 128), (300, 256, 187), (513, 64, 3), (4100, 512, 256),
+                                   (64, 600, 512)])
+def test_cast_transpose_and_short_reduction_dgrad(mg, M, K, N):
+    rng = np.random.default_rng(M + K + N)
+    w = (rng.standard_normal((N, K)) * 0.1).astype(np.float32)
+    wt = mg.ops.cast_transpose_bf16(dev(w))
+    n_pad = (N + 7) // 8 * 8
+    assert wt.shape == (K, n_pad) and wt.dtype == torch.bfloat16
+    want_wt = torch.zeros(K, n_pad, dtype=torch.bfloat16)
+    want_wt[:, :N] = torch.from_numpy(w).t().to(torch.bfloat16)
+    assert torch.equal(wt.cpu().view(torch.int16), want_wt.view(torch.int16)), 'cast + transpose is not the rounded transpose'
+
+    layer = mg.nn.Linear(K, N, device='cuda')
+    with torch.no_grad():
+        layer.weight.copy_(dev(w))
+    x = dev(rng.standard_normal((M, K)).astype(np.float32)).requires_grad_()
+    grad_y = rng.standard_normal((M, N)).astype(np.float32)
+    layer(x).backward(dev(grad_y))
+    g16 = torch.from_numpy(grad_y).to(torch.bfloat16).float().numpy().astype(np.float64)
+    w16 = torch.from_numpy(w).to(torch.bfloat16).float().numpy().astype(np.float64)
+    want = g16 @ w16                                             # exact product of the bf16-rounded operands
+    got = x.grad.cpu().numpy()
+    # bf16 operands, fp32 accumulation over N <= 512 terms: 2e-3 of the result's range (the forward layer's stated tolerance)
+    assert np.abs(got - want).max() <= 2e-3 * max(np.abs(want).max(), 1e-6)
+    x16 = torch.from_numpy(x.detach().cpu().numpy()).to(torch.bfloat16).float().numpy().astype(np.float64)
+    want_w = g16.T @ x16
+    assert np.abs(layer.weight.grad.cpu().numpy() - want_w).max() <= 1e-3 * max(np.abs(want_w).max(), 1e-6)
+
+
+def test_nn_linear_backward_makes_no_library_gemm(mg):
+    """The whole backward of a layer is our kernels: K7g (activation gradient), cast + transpose, K7 (input gradient), K7w."""
+    layer = mg.nn.Linear(128, 32, act='sigmoid', device='cuda')
+    x = torch.randn(4096, 128, device='cuda', requires_grad=True)
+    from torch.profiler import profile, ProfilerActivity
+    y = layer(x)
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        y.sum().backward()
+        torch.cuda.synchronize()
+    names = [e.key for e in prof.key_averages()]
+    assert not any(('gemm' in n.lower() or 'cutlass' in n.lower() or 'cublas' in n.lower() or 'sgemm' in n.lower()) for n in names), names
+    assert any('linear_tcgen05' in n for n in names) and any('wgrad' in n for n in names), names
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# torch custom operators: CUDA kernel + fake kernel + autograd formula agree (torch.library.opcheck), and a function made of
+# them traces under torch.compile (aot_eager: dynamo + AOT autograd through the fake kernels; no code generation)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_custom_ops_pass_opcheck_and_trace(mg):
+    T = torch.ops.morgana_b200
+    rng = np.random.default_rng(0)
+    x = dev(rng.random((3, 7, 16), dtype=np.float32))
+    dur = dev(rng.integers(0, 5, (3, 7, 1)))
+    T_len = int(dur.sum(dim=(1, 2)).max())
+    p0, p1 = dev(np.zeros(16, np.float32)), dev((rng.random(16) + 0.5).astype(np.float32))
+    checks = ('test_schema', 'test_faketensor', 'test_autograd_registration')
+    torch.library.opcheck(T.upsample_norm, (x.clone().requires_grad_(), dur, p0, p1, 'minmax', T_len), test_utils=checks)
+    pred, tgt = dev(rng.standard_normal((3, T_len, 16)).astype(np.float32)), dev(rng.standard_normal((3, T_len, 16)).astype(np.float32))
+    n = dur.sum(dim=(1, 2))
+    torch.library.opcheck(T.masked_loss, (pred.clone().requires_grad_(), tgt, n, 'mse'), test_utils=checks)
+    torch.library.opcheck(T.normalise, (pred.clone().requires_grad_(), p0, p1, 'mvn', False), test_utils=checks)
+
+    def objective(x, pred):
+        frames = T.upsample_norm(x, dur, p0, p1, 'minmax', T_len)
+        return T.masked_loss(frames + pred, tgt, n, 'mse')
+
+    xe, pe = x.clone().requires_grad_(), pred.clone().requires_grad_()
+    eager = objective(xe, pe)
+    eager.backward()
+    xc, pc = x.clone().requires_grad_(), pred.clone().requires_grad_()
+    compiled = torch.compile(objective, backend='aot_eager', fullgraph=True)(xc, pc)
+    compiled.backward()
+    assert compiled.item() == eager.item() and torch.equal(xc.grad, xe.grad) and torch.equal(pc.grad, pe.grad)
+    # the same numbers as the direct (ctypes) path of the drop-in functions
+    xd, pd = x.clone().requires_grad_(), pred.clone().requires_grad_()
+    direct = mg.losses.mse(mg.utils.upsample_to_repetitions(xd, dur, normaliser=('minmax', p0, p1), max_len=T_len) + pd, tgt, n)
+    direct.backward()
+    assert direct.item() == eager.item() and torch.equal(xd.grad, xe.grad) and torch.equal(pd.grad, pe.grad)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# oracle parity at BASELINE.json sizes (not self-consistency: the NumPy oracle on the full tensors)
+# ----------------------------------------------------------------------------------------------------------------------
+def test_config2_full_size_fused_upsample_equals_the_oracle(mg):
+    """configs[1]: 256 utterances x ~60 phones, dur U{1..30}, 600-dim labels, seed 1234 -- the 837 MB output, bit for bit."""
+    from morgana_b200 import workloads
+    ling = workloads.linguistic_batch(batch_size=256, seed=1234)
+    lab, dur = ling['lab'].numpy(), ling['dur'].numpy()
+    want = O.normalise_upsample(lab, dur, 'minmax', ling['mmin'].numpy(), ling['mmax'].numpy())
+    assert want.shape == (256, int(ling['n_frames'].max()), 600) and want.nbytes > 800e6
+    for path in ('auto', 'direct'):
+        got = mg.ops.upsample(ling['lab'].cuda(), ling['dur'].cuda(), norm=('minmax', ling['mmin'].cuda(), ling['mmax'].cuda()),
+                              path=path)
+        assert np.array_equal(got.cpu().numpy(), want), path
+        del got
+    # through the reference's signature + the standalone normaliser: the composition the fused kernel replaces
+    norm_lab = mg.data.normalise_minmax(ling['lab'].cuda(), ling['mmin'].cuda(), ling['mmax'].cuda())
+    valid_phone = (torch.arange(lab.shape[1])[None, :] < ling['n_phones'][:, None])[:, :, None].cuda()
+    got, n_frames = mg.utils.upsample_to_repetitions(norm_lab * valid_phone, ling['dur'].cuda(), return_lengths=True)
+    assert np.array_equal(n_frames.cpu().numpy(), ling['n_frames'].numpy())
+    assert np.array_equal(got.cpu().numpy(), want)
+    # packed wire format (no phone padding on the wire), same bits
+    valid = valid_phone[:, :, 0].cpu()
+    got = mg.utils.upsample_packed_to_repetitions(ling['lab'][valid].cuda(), ling['dur'][:, :, 0][valid].cuda(), ling['n_phones'].cuda(),
+                                                  normaliser=('minmax', ling['mmin'].cuda(), ling['mmax'].cuda()))
+    assert np.array_equal(got.cpu().numpy(), want)
+
+
+def test_config3_full_size_objective_equals_the_oracle(mg):
+    """configs[2]: 1024 utterances x U{300..1200} frames x 187 dims: loss, metric sums / counts (all of it) and the gradient
+    (every element of the first 128 utterances) of the one-launch objective against the fp64 NumPy oracle; and the drop-in
+    losses.mse / metrics.RMSE on the full tensors."""
+    from morgana_b200 import workloads
+    from morgana_b200.fused import AcousticObjective
+    n = workloads.acoustic_lengths(batch_size=1024, seed=1234)
+    ac = workloads.acoustic_batch(n, seed=1234)
+    p, t, nn_ = ac['pred'].numpy(), ac['target'].numpy(), n.numpy()
+    pred, target, n_frames = ac['pred'].cuda(), ac['target'].cuda(), n.cuda()
+    objective = AcousticObjective()
+    total, grad = objective(pred, target, n_frames)
+    want_total = (O.masked_loss(p[..., 0:3], t[..., 0:3], nn_) + O.masked_loss(p[..., 4:184], t[..., 4:184], nn_) +
+                  O.masked_loss(p[..., 184:187], t[..., 184:187], nn_) + O.masked_loss(p[..., 3:4], t[..., 3:4], nn_, 'bce')) / 4.
+    assert abs(total.item() - want_total) <= REL * abs(want_total), (total.item(), want_total)
+    voiced_p = p[..., 3:4] > 0.5
+    want_metrics = {'LF0_RMSE_Hz': O.lf0_acc(t[..., 0:1], p[..., 0:1], voiced_p, nn_),
+                    'VUV_accuracy': O.mean_acc((ac['voiced'].numpy() == voiced_p).astype(np.float32), nn_),
+                    'MCEP_distortion': O.melcep_acc(t[..., 4:64], p[..., 4:64], nn_),
+                    'BAP_distortion': O.distortion_acc(t[..., 184:185], p[..., 184:185], nn_)}
+    for name, (s, c) in want_metrics.items():
+        got = objective.metrics[name]
+        assert float(got.count) == c, name
+        assert abs(float(got.sum) - s) <= REL * abs(s), (name, float(got.sum), s)
+    sub = slice(0, 128)
+    g = grad[sub].cpu().numpy()
+    for sl, kind in [(slice(0, 3), 'mse'), (slice(4, 184), 'mse'), (slice(184, 187), 'mse'), (slice(3, 4), 'bce')]:
+        # the gradient of the mean over ALL 1024 utterances: the oracle on a sub-batch scales by its own batch size
+        want = 0.25 * O.masked_loss_grad(p[sub][..., sl], t[sub][..., sl], nn_[sub], kind) * (128. / 1024.)
+        np.testing.assert_allclose(g[..., sl], want, rtol=3e-6 if kind == 'bce' else REL, atol=1e-14)
+    valid = np.arange(p.shape[1])[None, :] < nn_[:, None]
+    assert not grad.cpu().numpy()[~valid].any(), 'gradient of padding frames must be zero'
+    # the drop-in pieces on the full tensors
+    loss = mg.losses.mse(pred, target, n_frames)
+    want = O.masked_loss(p, t, nn_)
+    assert abs(loss.item() - want) <= REL * abs(want)
+    rmse = mg.metrics.RMSE()
+    rmse.reset_state()
+    rmse.accumulate(target, pred, seq_len=n_frames)
+    s, c = O.rmse_acc(t, p, nn_)
+    assert float(rmse.count) == c and abs(float(rmse.sum) - s) <= REL * abs(s)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# f1 MLPG: the reference's OWN function (viz/synthesis.py:79-180, mirrored in oracle/_ref, on the bandmat stand-in) as checker
+# ----------------------------------------------------------------------------------------------------------------------
+MLPG_WINDOWS = {
+    'default': None,
+    'static+delta': [(0, 0, np.array([1.0])), (1, 1, np.array([-0.5, 0.0, 0.5]))],
+    'one-sided': [(0, 0, np.array([1.0])), (1, 0, np.array([-1.0, 1.0])), (0, 1, np.array([-1.0, 1.0]))],
+    'four': [(0, 0, np.array([1.0])), (1, 1, np.array([-0.5, 0.0, 0.5])), (1, 1, np.array([1.0, -2.0, 1.0])),
+             (1, 1, np.array([0.25, 0.5, 0.25]))],
+}
+
+
+@pytest.mark.parametrize('name', sorted(MLPG_WINDOWS))
+@pytest.mark.parametrize('var_kind', ['global', 'frame'])
+def test_mlpg_equals_the_reference_function_for_any_three_tap_windows(mg, name, var_kind):
+    from oracle import ref_loader
+    if not ref_loader.available():
+        pytest.fail('the reference mirror oracle/_ref is missing (python oracle/make_ref.py in the build container)')
+    ref_loader.import_reference()
+    from morgana.viz.synthesis import MLPG as reference_mlpg
+    from morgana_b200.viz.synthesis import MLPG
+    windows = MLPG_WINDOWS[name]
+    W = 3 if windows is None else len(windows)
+    rng = np.random.default_rng(len(name))
+    B, T, F, pad = 4, 70, 5, 12
+    means = rng.standard_normal((B, T, W * F)).astype(np.float32)
+    seq_len = np.array([70, 41, 9, 1])
+    if var_kind == 'global':
+        var = (rng.random(W * F) + 0.3).astype(np.float32)
+    else:
+        var = (rng.random((B, T, W * F)) + 0.3).astype(np.float32)
+    want = reference_mlpg(means.astype(np.float64), var.astype(np.float64), windows=windows, padding_size=pad, seq_len=seq_len)
+    got = MLPG(dev(means), dev(var), windows=windows, padding_size=pad, seq_len=dev(seq_len))
+    assert got.shape == (B, T, F) and got.dtype == torch.float32
+    np.testing.assert_allclose(got.cpu().numpy(), want, rtol=1e-5, atol=1e-5)
+    # NumPy in -> float64 NumPy out, as the reference's callers expect (models/RNN_SPSS.py:111-116)
+    got_np = MLPG(means, var, windows=windows, padding_size=pad, seq_len=seq_len)
+    assert isinstance(got_np, np.ndarray) and got_np.dtype == np.float64
+    np.testing.assert_allclose(got_np, want, rtol=1e-5, atol=1e-5)
+
+
+def test_mlpg_rejects_windows_wider_than_the_band(mg):
+    from morgana_b200.viz.synthesis import MLPG
+    means = torch.randn(1, 20, 2, device='cuda')
+    with pytest.raises(NotImplementedError):
+        MLPG(means, torch.ones(2, device='cuda'), windows=[(0, 0, np.array([1.0])), (2, 2, np.array([1., -8., 0., 8., -1.]) / 12.)])

@@ -275,3 +275,39 @@ def test_wgrad_plan_invariants(mg):
         if pair:
             assert N > 128 and tile_k % 128 == 0
         assert _lib.lib.mg_linear_wgrad_workspace_bytes(M, N, K) == 4 * splits * n_tiles * tile_rows * k_tiles * tile_k
+
+
+def test_custom_ops_have_fake_kernels_and_autograd_formulas(mg):
+    """torch.ops.morgana_b200.*: shape / dtype propagation on meta tensors (no memory, no GPU) for every operator, and
+    a backward pass traced through fake tensors (register_fake + register_autograd)."""
+    import torch
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    T = torch.ops.morgana_b200
+    for name in mg.torch_ops.OPERATORS:
+        assert hasattr(T, name), name
+
+    def meta(*shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device='meta')
+    ends, n_frames, summary = T.dur_scan(meta(4, 10, 1, dtype=torch.int64))
+    assert ends.shape == (4, 10) and ends.dtype == torch.int32 and n_frames.shape == (4,) and summary.shape == (4,)
+    assert T.upsample_norm(meta(4, 10, 600), meta(4, 10, 1, dtype=torch.int64), None, None, 'none', 77).shape == (4, 77, 600)
+    assert T.upsample_norm_backward(meta(4, 77, 600), meta(4, 10, dtype=torch.int64), None, None, 'none').shape == (4, 10, 600)
+    assert T.pad_collate(meta(100, 187), meta(4, dtype=torch.int64), 30).shape == (4, 30, 187)
+    assert T.normalise(meta(4, 77, 187), meta(187), meta(187), 'mvn', False).shape == (4, 77, 187)
+    loss = T.masked_loss(meta(4, 77, 187), meta(4, 77, 187), meta(4, dtype=torch.int64), 'mse')
+    assert loss.shape == () and loss.dtype == torch.float32
+    y = T.linear_bf16(meta(100, 600, dtype=torch.bfloat16), meta(512, 600, dtype=torch.bfloat16), meta(512), 'sigmoid', True)
+    assert y.shape == (100, 512) and y.dtype == torch.bfloat16
+    g16, grad_b = T.act_grad_bf16(meta(100, 187), None)
+    assert g16.shape == (100, 192) and g16.dtype == torch.bfloat16 and grad_b.shape == (187,)
+    assert T.linear_wgrad_bf16(meta(100, 192, dtype=torch.bfloat16), meta(100, 256, dtype=torch.bfloat16), 187, 256).shape == (187, 256)
+    assert T.cast_transpose_bf16(meta(187, 256)).shape == (256, 192)
+    assert T.mlpg(meta(3, 50, 9), meta(9), 10, None).shape == (3, 50, 3)
+    with FakeTensorMode():
+        x = torch.empty(4, 10, 600, device='meta', requires_grad=True)
+        frames = T.upsample_norm(x, torch.empty(4, 10, 1, dtype=torch.int64, device='meta'), torch.empty(600, device='meta'),
+                                 torch.empty(600, device='meta'), 'minmax', 77)
+        h = T.linear_bf16(frames.reshape(-1, 600).to(torch.bfloat16), torch.empty(8, 600, dtype=torch.bfloat16, device='meta'),
+                          None, 'sigmoid', False)
+        T.masked_loss(h.reshape(4, 77, 8), torch.empty(4, 77, 8, device='meta'), None, 'mse').backward()
+        assert x.grad.shape == (4, 10, 600)
