@@ -15,6 +15,7 @@ if not _building:
     from morgana_b200 import losses        # noqa: F401
     from morgana_b200 import metrics       # noqa: F401
     from morgana_b200 import data          # noqa: F401
+    from morgana_b200 import nn            # noqa: F401
     from morgana_b200 import torch_ops     # noqa: F401  (registers torch.ops.morgana_b200.*)
     from morgana_b200.patch import patch, unpatch   # noqa: F401
 

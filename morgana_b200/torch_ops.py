@@ -79,8 +79,8 @@ def _normalise(x, p0, p1, kind, inverse):
 
 
 def _masked_loss(predictions, targets, seq_len, kind):
-    with torch.no_grad():
-        return ops.masked_loss(predictions, targets, seq_len, kind)
+    with torch.no_grad():     # (a fresh 0-dim tensor: the direct path returns a view into its 48-byte result record)
+        return ops.masked_loss(predictions, targets, seq_len, kind).clone()
 
 
 def _masked_loss_backward(grad_output, predictions, targets, seq_len, kind):

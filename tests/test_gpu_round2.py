@@ -224,8 +224,10 @@ def test_nn_linear_backward_makes_no_library_gemm(mg):
         y.sum().backward()
         torch.cuda.synchronize()
     names = [e.key for e in prof.key_averages()]
-    assert not any(('gemm' in n.lower() or 'cutlass' in n.lower() or 'cublas' in n.lower() or 'sgemm' in n.lower()) for n in names), names
-    assert any('linear_tcgen05' in n for n in names) and any('wgrad' in n for n in names), names
+    offenders = [n for n in names if any(word in n.lower() for word in ('gemm', 'cutlass', 'cublas', 'gemv'))]
+    assert not offenders, offenders
+    ours = [n for n in names if 'tcgen05' in n or 'act_grad' in n or 'cast_transpose' in n]
+    assert any('linear_tcgen05' in n for n in ours) and any('wgrad' in n for n in ours) and any('cast_transpose' in n for n in ours), ours
 
 
 # ----------------------------------------------------------------------------------------------------------------------
