@@ -15,7 +15,14 @@ _PATHS = {'auto': _lib.PATH_AUTO, 'bulk': _lib.PATH_BULK, 'direct': _lib.PATH_DI
 _INT_DTYPES = (torch.int64, torch.int32, torch.int16, torch.int8, torch.uint8)
 
 
+_raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+
+
 def _stream():
+    """The current CUDA stream of the current device as the integer handle the C ABI takes (no Stream object is built:
+    ~0.3 us instead of ~2 us per launch)."""
+    if _raw_stream is not None:
+        return _raw_stream(torch.cuda.current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -609,6 +616,14 @@ def masked_loss(predictions, targets, seq_len=None, kind='mse'):
     if predictions.shape[0] == 0 or predictions.shape[2] == 0:
         return torch.full((), float('nan'), dtype=torch.float32, device=predictions.device)
     seq_len = _seq_len_arg(seq_len, predictions.shape[0], predictions.device)
+    if not (torch.is_grad_enabled() and (predictions.requires_grad or (targets is not None and targets.requires_grad))):
+        # validation / metrics: no graph to build, one launch and a view of the record (skips ~10 us of autograd bookkeeping)
+        B, T, D = predictions.shape
+        record = new_output_records(1, predictions.device)
+        with _device_of(predictions):
+            term = make_term(_LOSS_KINDS[kind], predictions, targets, result=record[0])
+            masked_reduce([term], seq_len, B, T, predictions.device)
+        return record[0].view(torch.float32)[F32_LOSS]
     return _MaskedLossFn.apply(predictions, targets, seq_len, _LOSS_KINDS[kind])
 
 
