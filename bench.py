@@ -470,12 +470,23 @@ def run_ours(args, rank, world, local_rank):
     extras = {}
     if not args.no_extras:
         sections = load_by_path('_mg_bench_sections', 'scripts', 'bench_sections.py')
+        # the extra sections never cost the headline line: a failure is reported in place (N > 1: every rank must agree, so the
+        # training section, which holds collectives, is only guarded at N = 1)
         t0 = time.time()
-        extras['training'] = sections.training_section(rank, world, dev, pk)
+        if world == 1:
+            try:
+                extras['training'] = sections.training_section(rank, world, dev, pk)
+            except Exception as exc:       # noqa: BLE001
+                extras['training'] = {'error': '%s: %s' % (type(exc).__name__, str(exc).splitlines()[0][:300])}
+        else:
+            extras['training'] = sections.training_section(rank, world, dev, pk)
         windows.append((t0, time.time()))
         if world == 1:
             t0 = time.time()
-            extras['other_configs'] = sections.other_configs(dev, pk, ReferencePath())
+            try:
+                extras['other_configs'] = sections.other_configs(dev, pk, ReferencePath())
+            except Exception as exc:       # noqa: BLE001
+                extras['other_configs'] = {'error': '%s: %s' % (type(exc).__name__, str(exc).splitlines()[0][:300])}
             windows.append((t0, time.time()))
     if sampler is not None:
         sampler.stop()

@@ -305,7 +305,7 @@ def training_section(rank, world, dev, peaks, steps=40, batch_size=32):
 
     # eager
     for i in range(5):
-        first = train_step(batches[i % 4])
+        train_step(batches[i % 4])        # nothing keeps the loss: a live autograd graph pins the AccumulateGrad nodes to this stream
     reset()
     first_loss = float(train_step(batches[0]).detach())
     eager_ms, frames, eager_last = timed(train_step)
@@ -323,7 +323,7 @@ def training_section(rank, world, dev, peaks, steps=40, batch_size=32):
         reset()
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
-            static_loss = train_step(static, exchange)
+            static_loss = train_step(static, exchange).detach()
         graphs[name] = (graph, static_loss)
 
     def replay(name):
