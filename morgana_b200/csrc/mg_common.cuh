@@ -91,6 +91,31 @@ __device__ __forceinline__ uint64_t mg_policy_evict_first() {
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
   return policy;
 }
+// Small, re-used data (tables, lengths, per-CTA records) asks L2 to keep it: the streams around it are hundreds of MB per launch
+// and would otherwise push it to DRAM between two uses.
+__device__ __forceinline__ uint64_t mg_policy_evict_last() {
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(policy));
+  return policy;
+}
+__device__ __forceinline__ uint32_t mg_ld_keep_u32(const void* p, uint64_t policy) {
+  uint32_t v;
+  asm volatile("ld.global.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ int64_t mg_ld_keep_s64(const void* p, uint64_t policy) {
+  int64_t v;
+  asm volatile("ld.global.L2::cache_hint.s64 %0, [%1], %2;" : "=l"(v) : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ double2 mg_ld_keep_cg_f64x2(const void* p, uint64_t policy) {   // from L2, never a stale L1 line
+  double2 v;
+  asm volatile("ld.global.cg.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(v.x), "=d"(v.y) : "l"(p), "l"(policy));
+  return v;
+}
+__device__ __forceinline__ void mg_st_keep_f64x2(void* p, double2 v, uint64_t policy) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(p), "d"(v.x), "d"(v.y), "l"(policy) : "memory");
+}
 __device__ __forceinline__ void mg_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 // Wait until at most N of this thread's bulk groups still have their SOURCE (shared memory) unread.
 template <int N>
@@ -115,6 +140,13 @@ __device__ __forceinline__ void mg_bulk_load(void* smem_dst, const void* gsrc, u
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    mg_smem_addr(smem_dst)),
                "l"(gsrc), "r"(bytes), "r"(mg_smem_addr(bar))
+               : "memory");
+}
+// The same with an L2 eviction-priority hint (a read-once stream should not push the rest of the working set out of L2).
+__device__ __forceinline__ void mg_bulk_load_hint(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+                   mg_smem_addr(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(mg_smem_addr(bar)), "l"(policy)
                : "memory");
 }
 __device__ __forceinline__ void mg_mbar_wait(uint64_t* bar, uint32_t parity) {

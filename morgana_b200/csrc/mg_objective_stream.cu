@@ -23,9 +23,17 @@
 //     registers; after four stages the warp holds 32 rows, lane = row, and evaluates them on one code path.  (A first version
 //     with a dedicated warp evaluating 8 rows x 3 columns per stage ran at 2.2 us per stage -- a dependent chain of ~500
 //     instructions in one warp -- and was slower than the kernel it replaces; profiles/r2b_summary.md.)
+//   * Head start.  CTA c first takes the fixed stages [4c, 4c + 4): the producer lane issues their loads as soon as the barriers
+//     exist, before anything is known about the batch, so the DRAM latency of the first bytes overlaps the prologue (column
+//     programs, lengths, cost prefix, range search: ~5 us of every launch before this).  The cost-balanced partition then covers
+//     the stages behind those head starts; it is computed by the producer warp alone while the consumers already stream.
+//     (Handing the last sixth of the work out dynamically -- guided self-scheduling over an atomic counter, a record per job so
+//     the sums stay deterministic -- was built and measured: every job switch costs each warp ~600 instructions (flush of the
+//     special-column batch, shuffle folds, range search) = ~2 us, more than the ~8 us of imbalance it removes; dropped.)
 //   * Accumulators are carried across stages AND utterances in registers: per thread (sum, sum / n_b) of its loss slot and the
-//     sum of its metric slot, flushed into the weighted form only when the utterance changes.  One CTA-level reduction at the
-//     end of the kernel, one ticket, and the last CTA adds the per-CTA partials in index order.
+//     sum of its metric slot, folded into the weighted form only when the utterance changes.  At the end the consumer warps
+//     fold their lanes with a fixed shuffle tree, warp 0 adds the warps in order and writes the CTA's record [slot][cta].
+//     One ticket; the last CTA adds the records in CTA order.
 //
 // Determinism: the stage -> CTA assignment is a pure function of (B, T, seq_len, grid), every sum has a fixed order, no
 // floating-point atomics.
@@ -40,11 +48,13 @@ using namespace mgobj;
 
 constexpr int kRows = 8;            // rows per stage
 constexpr int kMaxRing = 16;
+constexpr int kHead = 4;            // stages of a CTA's head start (<= ring)
 constexpr int kMaxB = 1024;         // utterance lengths and the cost prefix live in shared memory
 constexpr int kSpPerWarp = 1;       // special columns a consumer warp evaluates in batches of 32 rows
 constexpr int kMaxSp = 16;          // batched special columns per CTA (any further one is evaluated by its own thread)
 constexpr int kMaxWarps = 8;        // 7 consumer warps (D <= 224) + producer: 256 threads, 128 registers at two CTAs per SM
-constexpr int kMaxCtas = 1024;      // bounds the per-CTA partials in the workspace
+constexpr int kMaxCtas = 1024;      // bounds the per-CTA records in the workspace
+constexpr int kFinishLoads = 10;    // records a lane of the last CTA keeps in flight: one round for 2 x 148 CTAs
 
 struct StreamParams {
   MgFinishSlot slots[MG_MAX_TERMS];
@@ -55,12 +65,13 @@ struct StreamParams {
   const mg_column* cols;
   const int64_t* seq_len;
   unsigned int* ticket;
-  double2* partials;     // [grid][n_slots][2]: (sum, sum / n_b), (weighted count, -)
+  double2* records;      // [n_slots][grid][2]: (sum, sum / n_b), (weighted count, -)
   int64_t T;
   int D, B, n_slots, ring, n_consumer_warps;
   int cost_valid, cost_pad;   // relative cost of a valid / padding row in the stage -> CTA partition
+  float load_first_frac;   // tuning: share of the bulk loads that carry the L2 evict-first hint
   int debug;   // tuning experiments only (MG_OBJ_DEBUG): 1 consumers skip the arithmetic, 2 no special columns, 4 no zero stores,
-               // 8 per-CTA %globaltimer stamps (entry, range known, first stage ready, stream done, partials written) -> `stamps`
+               // 8 per-CTA %globaltimer stamps -> `stamps`, 16 flip the L2 hint of the bulk loads, 32 plain gradient stores
   unsigned long long* stamps;
 };
 
@@ -74,18 +85,22 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(mg_smem_addr(bar)) : "memory");
 }
 
-// Walks the stages of a CTA's range; every role keeps its own copy and sees the same sequence.
+__device__ __forceinline__ void consumer_barrier(int n_threads) {   // named barrier 1: the consumer warps only
+  asm volatile("bar.sync 1, %0;" ::"r"(n_threads) : "memory");
+}
+
+// Walks a range of stages; every role keeps its own copy and sees the same sequence.
 struct StageCursor {
-  int64_t stage, stage_end;   // current stage and end of the CTA's range
+  int64_t stage, stage_end;   // current stage and end of the range
   int64_t total_rows;
   int64_t T;
   int b;                      // utterance of the stage's first row
   int64_t t0;                 // that row's index inside the utterance
   __device__ __forceinline__ void init(int64_t s_lo, int64_t s_hi, int64_t T_, int64_t total_rows_) {
     stage = s_lo; stage_end = s_hi; T = T_; total_rows = total_rows_;
-    const int64_t r = s_lo * kRows;
-    b = static_cast<int>(r / T_);
-    t0 = r - static_cast<int64_t>(b) * T_;
+    const unsigned r = static_cast<unsigned>(s_lo * kRows);      // B * T < 2^31 (host check): one 32-bit division
+    b = static_cast<int>(r / static_cast<unsigned>(T_));
+    t0 = static_cast<int64_t>(r) - static_cast<int64_t>(b) * T_;
   }
   __device__ __forceinline__ bool done() const { return stage >= stage_end; }
   __device__ __forceinline__ void next() {
@@ -98,14 +113,14 @@ struct StageCursor {
     t0 += n * kRows;
     while (t0 >= T) { t0 -= T; ++b; }
   }
-  // consecutive FULL stages (8 valid rows of utterance b) from here, inside the CTA's range
+  // consecutive FULL stages (8 valid rows of utterance b) from here, inside the range
   __device__ __forceinline__ int64_t full_run(const int* s_nb) const {
     const int64_t n_b = s_nb[b];
     if (t0 + kRows > n_b) return 0;
     const int64_t run = (n_b - t0) / kRows, cap = stage_end - stage;
     return run < cap ? run : cap;
   }
-  // consecutive PAD stages (8 padding rows of utterance b) from here, inside the CTA's range
+  // consecutive PAD stages (8 padding rows of utterance b) from here, inside the range
   __device__ __forceinline__ int64_t pad_run(const int* s_nb) const {
     if (t0 < s_nb[b] || t0 + kRows > T) return 0;
     const int64_t run = (T - t0) / kRows, cap = stage_end - stage;
@@ -120,8 +135,9 @@ struct StageCursor {
 
 enum StageKind { STAGE_FULL = 0, STAGE_MIXED = 1, STAGE_PAD = 2, STAGE_TAIL = 3 };
 
-// FULL: 8 valid rows of one utterance.  PAD: 8 padding rows (no load; zero gradient).  TAIL: the tensor's last, short stage
-// (its byte count need not be a multiple of 16: read from global memory).  MIXED: anything else that has 8 rows.
+// FULL: 8 valid rows of one utterance.  PAD: 8 padding rows (no load outside the head start; zero gradient).  TAIL: the
+// tensor's last, short stage (its byte count need not be a multiple of 16: read from global memory).  MIXED: anything else
+// that has 8 rows.
 __device__ __forceinline__ int classify(const StageCursor& c, const int* s_nb, int B) {
   if (c.rows() < kRows) return STAGE_TAIL;
   const int64_t n_b = s_nb[c.b];
@@ -133,6 +149,7 @@ __device__ __forceinline__ int classify(const StageCursor& c, const int* s_nb, i
   // the stage runs into the next utterance(s): padding only if every row is padding
   int b = c.b;
   int64_t t = c.t0;
+#pragma unroll 1
   for (int u = 0; u < kRows; ++u) {
     if (t < s_nb[b]) return STAGE_MIXED;
     if (++t >= c.T) { t = 0; ++b; }
@@ -140,30 +157,90 @@ __device__ __forceinline__ int classify(const StageCursor& c, const int* s_nb, i
   return STAGE_PAD;
 }
 
+// The cost-balanced partition covers the rows behind the head starts, [first_row, B * T).  Inside an utterance the rows left
+// of it count in row order: valid rows (cost_valid each), then padding rows (cost_pad each).
+struct CostModel {
+  int64_t T, first_row;
+  unsigned cost_valid, cost_pad;
+  __device__ __forceinline__ unsigned cut(int b) const {       // rows of utterance b that belong to the head starts
+    const int64_t c = first_row - static_cast<int64_t>(b) * T;
+    return static_cast<unsigned>(c < 0 ? 0 : (c > T ? T : c));
+  }
+  __device__ __forceinline__ unsigned cost(int b, unsigned n) const {
+    const unsigned c = cut(b), t = static_cast<unsigned>(T);
+    const unsigned valid = n > c ? n - c : 0u, from = n > c ? n : c;
+    return cost_valid * valid + cost_pad * (t - from);
+  }
+};
+
+// Cost position -> stage, rounded up to a stage.  Monotone in x, and the same function at both ends of every CTA's range, so the
+// ranges tile the stages exactly.
+__device__ __forceinline__ int64_t cost_to_stage(unsigned x, const CostModel& cm, const int* s_pref, const int* s_nb, int B,
+                                                 int64_t first_stage, int64_t n_stages) {
+  if (x == 0) return first_stage;
+  if (x >= static_cast<unsigned>(s_pref[B])) return n_stages;
+  int lo = 0, hi = B;                      // last b with pref[b] <= x
+#pragma unroll 1
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (static_cast<unsigned>(s_pref[mid]) <= x) lo = mid; else hi = mid; }
+  const unsigned y = x - static_cast<unsigned>(s_pref[lo]), n = static_cast<unsigned>(s_nb[lo]), c = cm.cut(lo);
+  const unsigned valid = n > c ? n - c : 0u, from = n > c ? n : c;
+  unsigned r_in = y < cm.cost_valid * valid ? c + y / cm.cost_valid
+                                            : (cm.cost_pad > 0 ? from + (y - cm.cost_valid * valid) / cm.cost_pad : static_cast<unsigned>(cm.T));
+  if (r_in > static_cast<unsigned>(cm.T)) r_in = static_cast<unsigned>(cm.T);
+  int64_t stage = (static_cast<int64_t>(lo) * cm.T + r_in + kRows - 1) / kRows;
+  if (stage < first_stage) stage = first_stage;
+  return stage > n_stages ? n_stages : stage;
+}
+
+// Everything outside the stage loop runs as cold code at ~25 cycles per instruction (instruction-cache misses served by an L2 that
+// is saturated with the data stream: profiles/r2e_summary.md), and lambdas inlined at several call sites made the kernel 11 k
+// instructions long.  The rare routines are therefore real functions with ONE copy each.
+struct Contribution { double l, m, n; };   // loss value, metric value, metric weight of one element
+
+__device__ __noinline__ double div_f64(double a, double b) { return a / b; }
+
 // One element of a special column from values held in registers.  `root_acc`: squared error summed over the column's
 // ROOT_SQDIFF group (only read when the column leads a group of more than one column).
 template <bool GRAD>
-__device__ __forceinline__ void special_value(const mg_column& sc, float pv, float yv, float mask_v, float root_acc, float* g,
-                                              float w_row, double& l_acc, double& m_acc, double& n_acc) {
+__device__ __noinline__ Contribution special_value(mg_column sc, float pv, float yv, float mask_v, float root_acc, float* g, float w_row) {
   const bool has_mask = sc.mask_col != MG_COL_NONE;
-  mg_column prog = sc;
-  prog.width = 1;
+  Contribution c;
+  c.l = c.m = c.n = 0.;
   if (sc.metric_kind == MG_RED_ROOT_SQDIFF && sc.width > 1) {
     float root = sqrtf(root_acc);                     // feature-axis sum of the group (metrics.py:661), then the root (:662)
     if (has_mask) {
       const float voiced = mask_v > 0.5f ? 1.f : 0.f;
       root = __fmul_rn(root, voiced);
-      n_acc += static_cast<double>(voiced);
+      c.n += static_cast<double>(voiced);
     }
-    m_acc += static_cast<double>(root);
-    prog.metric_kind = MG_COL_NONE;   // the loss part of the column (if any) still goes through general_one
+    c.m += static_cast<double>(root);
+    sc.metric_kind = MG_COL_NONE;   // the loss part of the column (if any) still goes through general_one
   }
-  general_one<GRAD>(prog, pv, yv, mask_v, has_mask, nullptr, nullptr, g, w_row, l_acc, m_acc, n_acc);
+  sc.width = 1;
+  general_one<GRAD>(sc, pv, yv, mask_v, has_mask, nullptr, nullptr, g, w_row, c.l, c.m, c.n);
+  return c;
+}
+
+// The lanes of a warp that feed slot s are summed with a fixed shuffle tree (slots in lane order of their first column) and
+// added to the warp's row `mine` [slot][3]: `a` to [s][0], `b2` to [s][second].
+__device__ __noinline__ void fold_lanes(double* mine, int slot_id, double a, double b2, int second, bool with_second) {
+  const int lane = threadIdx.x & 31;
+  unsigned todo = __ballot_sync(MG_FULL_MASK, slot_id >= 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int s = __shfl_sync(MG_FULL_MASK, slot_id, leader);
+    const bool in = slot_id == s;
+    todo &= ~__ballot_sync(MG_FULL_MASK, in);
+    const double va = mg_warp_sum(in ? a : 0.);
+    const double vb = with_second ? mg_warp_sum(in ? b2 : 0.) : 0.;
+    if (lane == 0) { mine[s * 3] += va; mine[s * 3 + second] += vb; }
+  }
 }
 
 __device__ __forceinline__ float root_group_acc(const mg_column& sc, int k, const float* row_p, const float* row_y) {
   const float d0 = __fsub_rn(row_y[k], row_p[k]);
   float acc = __fmul_rn(d0, d0);
+#pragma unroll 1
   for (int j = 1; j < sc.width; ++j) {
     const float dj = __fsub_rn(row_y[k + j], row_p[k + j]);
     acc = __fadd_rn(acc, __fmul_rn(dj, dj));
@@ -175,16 +252,14 @@ template <bool GRAD>
 __global__ void __launch_bounds__(kMaxWarps * 32, 2)
 objective_stream_kernel(const __grid_constant__ StreamParams prm) {
   extern __shared__ __align__(128) unsigned char smem_raw[];   // [ring x (pred stage | target stage)] [zero tile]
-  __shared__ __align__(8) uint64_t s_full[kMaxRing], s_empty[kMaxRing];
+  __shared__ __align__(8) uint64_t s_full[kMaxRing], s_empty[kMaxRing], s_range_bar;
   __shared__ mg_column s_cols[256];
   __shared__ int s_nb[kMaxB];
   __shared__ int s_pref[kMaxB + 1];          // exclusive prefix of the per-utterance cost
-  __shared__ int s_sp_col[kMaxSp];
-  __shared__ int s_n_sp, s_has_empty;
+  __shared__ int s_has_empty;
   __shared__ int64_t s_range[2];
-  __shared__ long long s_wvalid[kMaxWarps];
-  __shared__ int s_wsum[kMaxWarps];
-
+  __shared__ long long s_valid_total;
+  __shared__ double s_flush[kMaxWarps - 1][MG_MAX_TERMS][3];   // per-warp sums
   __shared__ double s_slot[MG_MAX_TERMS][3];
   __shared__ bool s_is_last;
 
@@ -193,134 +268,133 @@ objective_stream_kernel(const __grid_constant__ StreamParams prm) {
   const int producer_warp = n_cw;
   const int64_t T = prm.T;
   const int64_t total_rows = static_cast<int64_t>(B) * T;
+  const int64_t n_stages = (total_rows + kRows - 1) / kRows;
   const int stage_elems = kRows * D;
   const uint32_t stage_bytes = static_cast<uint32_t>(stage_elems) * 4u;
   float* s_ring = reinterpret_cast<float*>(smem_raw);
   float* s_zero = s_ring + static_cast<size_t>(ring) * 2 * stage_elems;
-  const int kCostValid = prm.cost_valid, kCostPad = GRAD ? prm.cost_pad : 0;
+  // head start of this CTA: stages [head_lo, head_hi); the partition covers [first_stage, n_stages)
+  const int n_head = ring < kHead ? ring : kHead;
+  const int64_t first_stage = min(static_cast<int64_t>(gridDim.x) * n_head, n_stages);
+  const int64_t head_lo = min(static_cast<int64_t>(blockIdx.x) * n_head, n_stages), head_hi = min(head_lo + n_head, n_stages);
 
   const bool stamp = (prm.debug & 8) != 0;
-  if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 0] = global_ns();
-  // ---- prologue: column programs, utterance lengths, cost prefix, this CTA's stage range -----------------------------------
-  for (int k = tid; k < D; k += blockDim.x) s_cols[k] = prm.cols[k];
-  for (int b = tid; b < B; b += blockDim.x) s_nb[b] = static_cast<int>(mg_valid_frames(prm.seq_len, b, T));
-  if (GRAD) for (int i = tid; i < stage_elems; i += blockDim.x) s_zero[i] = 0.f;
-  if (tid == 0) {
-    for (int i = 0; i < ring; ++i) { mg_mbar_init(&s_full[i], 1); mg_mbar_init(&s_empty[i], static_cast<uint32_t>(n_cw)); }
-    mg_mbar_fence_init();
+  if (stamp && tid == 0) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    prm.stamps[blockIdx.x * 16 + 0] = global_ns();
+    prm.stamps[blockIdx.x * 16 + 14] = smid;
+  }
+  // producer state (lane 0 of the producer warp)
+  int p_slot = 0;
+  uint32_t p_phase = 1;       // parity to wait for on the slot's "empty" barrier; the first pass over the ring does not wait
+  bool p_first_pass = true;
+  uint64_t policy;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, %1;" : "=l"(policy) : "f"(prm.load_first_frac));
+  // L2 policies, measured at config 2 (forward + gradient): loads normal + gradient stores evict-first 0.118 ms, both evict-first
+  // 0.121, loads evict-first + plain stores 0.129, both plain 0.1185.  Evict-first loads keep the kernel's own code and tables in
+  // L2 from launch to launch (prologue 3.1 -> 1.9 us, last CTA 4.3 -> 1.9 us) but cost the stream 4 % as soon as there are stores
+  // to write back, so only the forward-only form uses them (0.0767 -> 0.0746 ms); the small re-used data asks for evict-last.
+  auto load_stage = [&](int64_t stage) {
+    if (!p_first_pass) mg_mbar_wait(&s_empty[p_slot], p_phase);
+    const int64_t off = stage * stage_elems;
+    float* dst = s_ring + static_cast<size_t>(p_slot) * 2 * stage_elems;
+    mg_mbar_expect_tx(&s_full[p_slot], 2 * stage_bytes);
+    if (GRAD ? !(prm.debug & 16) : (prm.debug & 16) != 0) {
+      mg_bulk_load(dst, prm.pred + off, stage_bytes, &s_full[p_slot]);
+      mg_bulk_load(dst + stage_elems, prm.target + off, stage_bytes, &s_full[p_slot]);
+    } else {
+      mg_bulk_load_hint(dst, prm.pred + off, stage_bytes, &s_full[p_slot], policy);
+      mg_bulk_load_hint(dst + stage_elems, prm.target + off, stage_bytes, &s_full[p_slot], policy);
+    }
+    if (++p_slot == ring) { p_slot = 0; p_phase ^= 1u; p_first_pass = false; }
+  };
+  // ---- prologue: the producer lane goes straight to the barriers and the head start's loads; the other warps fetch the column
+  // programs and the utterance lengths meanwhile ---------------------------------------------------------------------------------
+  double scale = 1.;
+  if (GRAD && prm.grad_scale_dev != nullptr) scale = static_cast<double>(__ldg(prm.grad_scale_dev));   // in flight under the loads below
+  if (warp == producer_warp) {
+    if (lane == 0) {
+      for (int i = 0; i < ring; ++i) { mg_mbar_init(&s_full[i], 1); mg_mbar_init(&s_empty[i], static_cast<uint32_t>(n_cw)); }
+      mg_mbar_init(&s_range_bar, 1);
+      mg_mbar_fence_init();
+      for (int64_t st = head_lo; st < head_hi; ++st)
+        if ((st + 1) * kRows <= total_rows) load_stage(st);      // every full-size stage, whatever it holds (nothing is known yet)
+      if (stamp) prm.stamps[blockIdx.x * 16 + 12] = global_ns();
+    }
+  } else {
+    const int t2 = warp < producer_warp ? tid : tid - 32, nt = static_cast<int>(blockDim.x) - 32;
+    const uint64_t keep = mg_policy_evict_last();
+#pragma unroll 1
+    for (int b = t2; b < B; b += nt) {
+      int64_t n = T;
+      if (prm.seq_len != nullptr) { n = mg_ld_keep_s64(prm.seq_len + b, keep); n = n < 0 ? 0 : (n > T ? T : n); }   // as mg_valid_frames
+      s_nb[b] = static_cast<int>(n);
+    }
+    static_assert(sizeof(mg_column) == 12, "mg_column is read as three 32-bit words");
+#pragma unroll 1
+    for (int k = t2; k < 3 * D; k += nt) reinterpret_cast<uint32_t*>(s_cols)[k] = mg_ld_keep_u32(reinterpret_cast<const uint32_t*>(prm.cols) + k, keep);
+    if (GRAD) {
+#pragma unroll 1
+      for (int i = t2; i < stage_elems; i += nt) s_zero[i] = 0.f;
+      mg_fence_proxy_async_smem();   // the zero tile is read by the bulk-copy engine
+    }
   }
   __syncthreads();
   if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 8] = global_ns();
-  {
-    // exclusive prefix of the per-utterance cost, by the whole CTA: a shuffle scan per warp, warp totals through shared memory
-    const int nt = blockDim.x, n_warps = nt >> 5;
-    int carry = 0, empty = 0;
-    long long valid = 0;
-    for (int base = 0; base < B; base += nt) {
-      const int b = base + tid;
-      const int n = b < B ? s_nb[b] : 0;
-      const int cost = b < B ? kCostValid * n + kCostPad * (static_cast<int>(T) - n) : 0;
-      int incl = cost;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(MG_FULL_MASK, incl, o);
-        if (lane >= o) incl += v;
-      }
-      if (lane == 31) s_wsum[warp] = incl;
-      empty |= (b < B && n == 0) ? 1 : 0;
-      valid += n;
-      __syncthreads();
-      int before = 0, total = 0;
-      for (int w = 0; w < n_warps; ++w) { const int v = s_wsum[w]; total += v; if (w < warp) before += v; }
-      if (b < B) s_pref[b] = carry + before + incl - cost;
-      carry += total;
-      __syncthreads();
-    }
-    empty = __syncthreads_or(empty);
-    valid = mg_warp_sum(valid);
-    if (lane == 0) s_wvalid[warp] = valid;
-    if (tid == 0) { s_pref[B] = carry; s_has_empty = empty; }
-  }
-  if (warp == producer_warp) {
-    // special columns in column order; the first kSpPerWarp * n_cw of them are evaluated in batches (below), any further one
-    // by the thread that owns the column
-    int n_sp = 0;
-    for (int c0 = 0; c0 < D; c0 += 32) {
-      const int k = c0 + lane;
-      const bool special = k < D && !column_is_simple(s_cols[k]);
-      const unsigned bits = __ballot_sync(MG_FULL_MASK, special);
-      if (special) {
-        const int idx = n_sp + __popc(bits & ((1u << lane) - 1));
-        if (idx < kMaxSp) s_sp_col[idx] = k;
-      }
-      n_sp += __popc(bits);
-    }
-    const int cap = kSpPerWarp * n_cw < kMaxSp ? kSpPerWarp * n_cw : kMaxSp;
-    if (lane == 0) s_n_sp = n_sp < cap ? n_sp : cap;
-  }
-  if (GRAD) mg_fence_proxy_async_smem();   // the zero tile is read by the bulk-copy engine
-  __syncthreads();
-  if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 9] = global_ns();
-  if (tid == 0 || tid == 32) {
-    // cost position -> row (valid rows first inside an utterance), rounded up to a stage; the same function at both ends of
-    // every CTA's range, so the ranges tile the stages exactly.  Two threads, one end each.
-    const int e = tid >> 5;
-    const unsigned total_cost = static_cast<unsigned>(s_pref[B]);
-    const int64_t n_stages = (total_rows + kRows - 1) / kRows;
-    const unsigned c = blockIdx.x + e;
-    int64_t stage;
-    if (c >= gridDim.x) stage = n_stages;
-    else if (c == 0) stage = 0;
-    else {
-      // floor(total_cost * c / grid) up to the rounding of one double division: any monotone function of c works
-      const unsigned x = static_cast<unsigned>(static_cast<double>(total_cost) * static_cast<double>(c) / static_cast<double>(gridDim.x));
-      int lo = 0, hi = B;                      // last b with pref[b] <= x
-      while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (static_cast<unsigned>(s_pref[mid]) <= x) lo = mid; else hi = mid; }
-      const unsigned y = x - static_cast<unsigned>(s_pref[lo]), n = static_cast<unsigned>(s_nb[lo]);
-      const unsigned pad_div = kCostPad > 0 ? static_cast<unsigned>(kCostPad) : 1u;
-      unsigned r_in = y < static_cast<unsigned>(kCostValid) * n ? y / static_cast<unsigned>(kCostValid)
-                                                                : (kCostPad > 0 ? n + (y - static_cast<unsigned>(kCostValid) * n) / pad_div
-                                                                                : static_cast<unsigned>(T));
-      if (r_in > static_cast<unsigned>(T)) r_in = static_cast<unsigned>(T);
-      stage = (static_cast<int64_t>(lo) * T + r_in + kRows - 1) / kRows;
-      if (stage > n_stages) stage = n_stages;
-    }
-    s_range[e] = stage;
-  }
-  __syncthreads();
-  const int64_t s_lo = s_range[0], s_hi = s_range[1];
-  if (stamp && tid == 0) { prm.stamps[blockIdx.x * 16 + 1] = global_ns(); prm.stamps[blockIdx.x * 16 + 5] = static_cast<unsigned long long>(s_hi - s_lo); }
-  const int n_sp = s_n_sp;
-  double scale = 1.;
-  if (GRAD && prm.grad_scale_dev != nullptr) scale = static_cast<double>(__ldg(prm.grad_scale_dev));
   const double scale_over_b = scale / static_cast<double>(B);
 
-  // what each thread brings to the CTA reduction at the end: (slot, sum, weighted sum, count) contributions of its own column
-  // [0, 1] and of the special columns its warp evaluates [2 ..]
-  constexpr int kOut = 2 + 2 * kSpPerWarp;
-  int out_slot[kOut];
-  double out_sum[kOut], out_w[kOut], out_n[kOut];
-#pragma unroll
-  for (int e = 0; e < kOut; ++e) { out_slot[e] = -1; out_sum[e] = out_w[e] = out_n[e] = 0.; }
-
   if (warp == producer_warp) {
-    // ---- producer: bulk loads into the ring, zero gradients of padding-only stages ----------------------------------------
+    // ---- producer warp: cost prefix and this CTA's range (the consumers are already on the head start), then the loads ---------
+    CostModel cm;
+    cm.T = T; cm.first_row = first_stage * kRows;
+    cm.cost_valid = static_cast<unsigned>(prm.cost_valid); cm.cost_pad = GRAD ? static_cast<unsigned>(prm.cost_pad) : 0u;
+    {
+      unsigned carry = 0;
+      int empty = 0;
+      long long valid = 0;
+#pragma unroll 1
+      for (int base = 0; base < B; base += 32) {
+        const int b = base + lane;
+        const unsigned n = b < B ? static_cast<unsigned>(s_nb[b]) : 0u;
+        const unsigned cost = b < B ? cm.cost(b, n) : 0u;
+        unsigned incl = cost;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const unsigned v = __shfl_up_sync(MG_FULL_MASK, incl, o);
+          if (lane >= o) incl += v;
+        }
+        if (b < B) s_pref[b] = static_cast<int>(carry + incl - cost);
+        carry += __shfl_sync(MG_FULL_MASK, incl, 31);
+        empty |= (b < B && n == 0) ? 1 : 0;
+        valid += n;
+      }
+      empty = __any_sync(MG_FULL_MASK, empty);
+      valid = mg_warp_sum(valid);
+      if (lane == 0) { s_pref[B] = static_cast<int>(carry); s_has_empty = empty; s_valid_total = valid; }
+      __syncwarp();
+      if (stamp && lane == 0) prm.stamps[blockIdx.x * 16 + 13] = global_ns();
+    }
+    if (lane < 2) {
+      // one end of the range per lane
+      const unsigned total_cost = static_cast<unsigned>(s_pref[B]);
+      const unsigned c = blockIdx.x + lane;
+      int64_t stage;
+      if (c >= gridDim.x) stage = n_stages;
+      else {
+        // floor(total_cost * c / grid) up to the rounding of one double division: any monotone function of c works
+        const unsigned x = static_cast<unsigned>(static_cast<double>(total_cost) * static_cast<double>(c) / static_cast<double>(gridDim.x));
+        stage = cost_to_stage(x, cm, s_pref, s_nb, B, first_stage, n_stages);
+      }
+      s_range[lane] = stage;
+    }
+    __syncwarp();
     if (lane == 0) {
+      mbar_arrive(&s_range_bar);                   // release: the consumers read s_range after their wait
+      const int64_t s_lo = s_range[0], s_hi = s_range[1];
+      if (stamp) { prm.stamps[blockIdx.x * 16 + 1] = global_ns(); prm.stamps[blockIdx.x * 16 + 5] = static_cast<unsigned long long>(s_hi - s_lo); }
       StageCursor cur;
       cur.init(s_lo, s_hi, T, total_rows);
-      const uint64_t policy = mg_policy_evict_first();
-      int slot = 0;
-      uint32_t phase = 1;       // parity to wait for on the slot's "empty" barrier; the first pass over the ring does not wait
-      bool first_pass = true;
-      auto load_stage = [&](int64_t stage) {
-        if (!first_pass) mg_mbar_wait(&s_empty[slot], phase);
-        const int64_t off = stage * stage_elems;
-        float* dst = s_ring + static_cast<size_t>(slot) * 2 * stage_elems;
-        mg_mbar_expect_tx(&s_full[slot], 2 * stage_bytes);
-        mg_bulk_load(dst, prm.pred + off, stage_bytes, &s_full[slot]);
-        mg_bulk_load(dst + stage_elems, prm.target + off, stage_bytes, &s_full[slot]);
-        if (++slot == ring) { slot = 0; phase ^= 1u; first_pass = false; }
-      };
       while (!cur.done()) {
         int64_t run = cur.full_run(s_nb);
         if (run > 0) {                                   // a run of fully valid stages of one utterance
@@ -349,13 +423,29 @@ objective_stream_kernel(const __grid_constant__ StreamParams prm) {
       }
       if (GRAD) mg_bulk_wait_read<0>();   // the zero tile has been read by every bulk store (their writes complete asynchronously)
     }
-  } else {
-    // ---- consumers: thread t owns column t; warp w also evaluates special columns w, w + n_cw, ... in batches of 32 rows ----
+  } else if (warp < n_cw) {
+    // ---- consumers: thread t owns column t; warp w also evaluates special column w (in column order) in batches of 32 rows ----
     const bool active = tid < D;
     const mg_column col = active ? s_cols[tid] : s_cols[0];
     const bool simple = active && column_is_simple(col);
-    bool served = false;      // special column evaluated in batches (the first kSpPerWarp * n_cw of them)
-    for (int i = 0; i < n_sp; ++i) served = served || s_sp_col[i] == tid;
+    // special columns in column order: the first min(n_cw, kMaxSp) of them are evaluated in batches, warp w takes the w-th; any
+    // further one is evaluated by the thread that owns the column
+    int my_rank = -1, my_special_col = -1;
+    {
+      int n_before = 0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < D; c0 += 32) {
+        const int k = c0 + lane;
+        const bool special = k < D && !column_is_simple(s_cols[k]);
+        const unsigned bits = __ballot_sync(MG_FULL_MASK, special);
+        if (c0 == warp * 32 && special) my_rank = n_before + __popc(bits & ((1u << lane) - 1));
+        const int want = warp - n_before;          // the warp-th special column sits in this chunk?
+        if (want >= 0 && want < __popc(bits)) my_special_col = c0 + __fns(bits, 0, want + 1);
+        n_before += __popc(bits);
+      }
+    }
+    const int sp_cap = kSpPerWarp * n_cw < kMaxSp ? kSpPerWarp * n_cw : kMaxSp;
+    const bool served = active && !simple && my_rank >= 0 && my_rank < sp_cap;   // evaluated in batches by warp `my_rank`
     const bool own_special = active && !simple && !served;   // any further special column: its own thread evaluates it
     const bool use_loss = (simple || own_special) && col.loss_kind != MG_COL_NONE;
     const bool use_metric = (simple || own_special) && col.metric_kind != MG_COL_NONE;
@@ -367,17 +457,18 @@ objective_stream_kernel(const __grid_constant__ StreamParams prm) {
     double cur_l = 0., cur_m = 0., cur_n = 0., sum_l = 0., wsum_l = 0., sum_m = 0., sum_n = 0.;
     auto enter = [&](int b) {   // the utterance changes: fold the finished one into the weighted sums
       if (b == b_cur) return;
-      sum_l += cur_l; wsum_l += cur_l / n_cur; sum_m += cur_m; sum_n += cur_n;
+      sum_l += cur_l; wsum_l += div_f64(cur_l, n_cur); sum_m += cur_m; sum_n += cur_n;
       cur_l = cur_m = cur_n = 0.;
       b_cur = b;
       n_cur = b >= 0 ? static_cast<double>(s_nb[b]) : 1.;
-      w_row = use_loss ? static_cast<float>(static_cast<double>(col.loss_weight) * (scale_over_b / n_cur)) : 0.f;
+      w_row = use_loss ? static_cast<float>(static_cast<double>(col.loss_weight) * div_f64(scale_over_b, n_cur)) : 0.f;
       w2 = __fmul_rn(2.f, w_row);
     };
     // rows of a stage one at a time, from shared or global memory (mixed / tail stages and non-squared programs)
     auto slow_rows = [&](const float* sp, const float* sy, float* g, const StageCursor& cur, int n_rows) {
       int b = cur.b;
       int64_t t = cur.t0;
+#pragma unroll 1
       for (int u = 0; u < n_rows; ++u) {
         const bool valid = t < s_nb[b];
         if (valid && own_special) {
@@ -385,8 +476,9 @@ objective_stream_kernel(const __grid_constant__ StreamParams prm) {
           const float* row_p = sp + u * D - tid;
           const float* row_y = sy + u * D - tid;
           const float root = (col.metric_kind == MG_RED_ROOT_SQDIFF && col.width > 1) ? root_group_acc(col, tid, row_p, row_y) : 0.f;
-          special_value<GRAD>(col, row_p[tid], row_y[tid], col.mask_col != MG_COL_NONE ? row_p[col.mask_col] : 1.f, root,
-                              GRAD ? g + u * D : nullptr, w_row, cur_l, cur_m, cur_n);
+          const Contribution c = special_value<GRAD>(col, row_p[tid], row_y[tid], col.mask_col != MG_COL_NONE ? row_p[col.mask_col] : 1.f, root,
+                                                     GRAD ? g + u * D : nullptr, w_row);
+          cur_l += c.l; cur_m += c.m; cur_n += c.n;
         } else if (valid && simple) {
           enter(b);
           const float d = __fsub_rn(sp[u * D], sy[u * D]);
@@ -401,17 +493,16 @@ objective_stream_kernel(const __grid_constant__ StreamParams prm) {
       }
     };
 
-    // -- special columns of this warp: operands of 32 rows (four stages) are parked in registers, lane = row, then every
+    // -- special column of this warp: operands of 32 rows (four stages) are parked in registers, lane = row, then the
     // column is evaluated by the whole warp on one code path (~100 instructions per element: BCE, exp, root ...) ------------
     int n_my = 0;
     int my_k[kSpPerWarp];
     mg_column my_sc[kSpPerWarp];
 #pragma unroll
     for (int j = 0; j < kSpPerWarp; ++j) {
-      const int q = warp + j * n_cw;
       my_k[j] = 0;
       my_sc[j] = s_cols[0];
-      if (q < n_sp && !(prm.debug & 2)) { my_k[j] = s_sp_col[q]; my_sc[j] = s_cols[my_k[j]]; n_my = j + 1; }
+      if (j == 0 && my_special_col >= 0 && warp < sp_cap && !(prm.debug & 2)) { my_k[j] = my_special_col; my_sc[j] = s_cols[my_special_col]; n_my = j + 1; }
     }
     float b_pv[kSpPerWarp], b_yv[kSpPerWarp], b_mv[kSpPerWarp], b_root[kSpPerWarp];
     int b_utt = -1;               // utterance of this lane's parked row, -1: nothing parked
@@ -454,10 +545,9 @@ objective_stream_kernel(const __grid_constant__ StreamParams prm) {
         for (int j = 0; j < kSpPerWarp; ++j) {
           if (j < n_my) {   // warp-uniform
             const mg_column& sc = my_sc[j];
-            const float w = static_cast<float>(static_cast<double>(sc.loss_weight) * (scale_over_b / n_b));
-            double l = 0., m = 0., n = 0.;
-            special_value<GRAD>(sc, b_pv[j], b_yv[j], b_mv[j], b_root[j], GRAD ? prm.grad + b_off + my_k[j] : nullptr, w, l, m, n);
-            sp_sum_l[j] += l; sp_w_l[j] += l / n_b; sp_sum_m[j] += m; sp_sum_n[j] += n;
+            const float w = static_cast<float>(static_cast<double>(sc.loss_weight) * div_f64(scale_over_b, n_b));
+            const Contribution c = special_value<GRAD>(sc, b_pv[j], b_yv[j], b_mv[j], b_root[j], GRAD ? prm.grad + b_off + my_k[j] : nullptr, w);
+            sp_sum_l[j] += c.l; sp_w_l[j] += div_f64(c.l, n_b); sp_sum_m[j] += c.m; sp_sum_n[j] += c.n;
           }
         }
       }
@@ -480,7 +570,7 @@ objective_stream_kernel(const __grid_constant__ StreamParams prm) {
         for (int u = 0; u < kRows; ++u) {
           const float d = __fsub_rn(pv[u], yv[u]);
           part = __fadd_rn(part, __fmul_rn(d, d));
-          if (GRAD) __stcs(g + u * D, __fmul_rn(d, w2));
+          if (GRAD) { if (prm.debug & 32) g[u * D] = __fmul_rn(d, w2); else __stcs(g + u * D, __fmul_rn(d, w2)); }
         }
         cur_l += static_cast<double>(part);
         if (use_metric) cur_m += static_cast<double>(part);
@@ -489,216 +579,205 @@ objective_stream_kernel(const __grid_constant__ StreamParams prm) {
       }
     };
 
-    StageCursor cur;
-    cur.init(s_lo, s_hi, T, total_rows);
     int slot = 0;
     uint32_t phase = 0;
     int n_loaded = 0;    // stages that went through the ring (debug stamps)
-    while (!cur.done()) {
-      int64_t run = cur.full_run(s_nb);
-      if (run > 0) {
-        n_loaded += static_cast<int>(run);
-        enter(cur.b);
-        for (int64_t i = 0; i < run; ++i) {
-          const int64_t off = cur.stage * stage_elems;
-          mg_mbar_wait(&s_full[slot], phase);
-          if (stamp && tid == 0 && prm.stamps[blockIdx.x * 16 + 2] == 0) prm.stamps[blockIdx.x * 16 + 2] = global_ns();
-          const float* stage_p = s_ring + static_cast<size_t>(slot) * 2 * stage_elems;
-          full_stage(stage_p, off, cur);
-          if (n_my > 0) park(stage_p, stage_p + stage_elems, cur, off, STAGE_FULL);
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_empty[slot]);   // the stage's operands are in registers: the slot may be refilled
-          if (++slot == ring) { slot = 0; phase ^= 1u; }
-          if (batch_pos == 4) evaluate();
-          cur.stage += 1;
-          cur.t0 += kRows;
-        }
-        cur.advance(0);
-        continue;
+    if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 9] = global_ns();
+    // pass 0: the head start (every full-size stage was loaded, padding-only ones included: their zero gradient is written here);
+    // pass 1: this CTA's range of the partition (padding-only stages are the producer's)
+    for (int pass = 0; pass < 2; ++pass) {
+      StageCursor cur;
+      if (pass == 0) {
+        cur.init(head_lo, head_hi, T, total_rows);
+      } else {
+        mg_mbar_wait(&s_range_bar, 0);
+        cur.init(s_range[0], s_range[1], T, total_rows);
       }
-      run = cur.pad_run(s_nb);
-      if (run > 0) { cur.advance(run); continue; }
-      const int kind = classify(cur, s_nb, B);
-      if (kind == STAGE_PAD) { cur.next(); continue; }
-      const int64_t off = cur.stage * stage_elems;
-      float* g = GRAD ? prm.grad + off + tid : nullptr;
-      if (kind == STAGE_TAIL) {
-        if (active) slow_rows(prm.pred + off + tid, prm.target + off + tid, g, cur, cur.rows());
-        if (n_my > 0) { park(prm.pred + off, prm.target + off, cur, off, kind); if (batch_pos == 4) evaluate(); }
-        cur.next();
-        continue;
-      }
-      ++n_loaded;
-      mg_mbar_wait(&s_full[slot], phase);
-      const float* stage_p = s_ring + static_cast<size_t>(slot) * 2 * stage_elems;
-      if (active && !(prm.debug & 1)) {
-        if ((hot || served) && T >= kRows) {
-          // a boundary stage is at most: valid rows of utterance b | padding | valid rows of utterance b + 1 | padding
-          const int rows_a = static_cast<int>(min(static_cast<int64_t>(kRows), T - cur.t0));
-          const int valid_a = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(rows_a), s_nb[cur.b] - cur.t0)));
-          const int valid_b = rows_a < kRows ? min(kRows - rows_a, s_nb[cur.b + 1]) : 0;
-          const float* sp = stage_p + tid;
-          const float* sy = sp + stage_elems;
-          auto valid_rows = [&](int u0, int u1, int b) {
-            if (u1 <= u0 || !hot) return;
-            enter(b);
-            float part = 0.f;
-            for (int u = u0; u < u1; ++u) {
-              const float d = __fsub_rn(sp[u * D], sy[u * D]);
-              part = __fadd_rn(part, __fmul_rn(d, d));
-              if (GRAD) __stcs(g + u * D, __fmul_rn(d, w2));
-            }
-            cur_l += static_cast<double>(part);
-            if (use_metric) cur_m += static_cast<double>(part);
-          };
-          valid_rows(0, valid_a, cur.b);
-          valid_rows(rows_a, rows_a + valid_b, cur.b + 1);
-          if (GRAD) {
-            for (int u = valid_a; u < rows_a; ++u) __stcs(g + u * D, 0.f);
-            for (int u = rows_a + valid_b; u < kRows; ++u) __stcs(g + u * D, 0.f);
+      while (!cur.done()) {
+        int64_t run = cur.full_run(s_nb);
+        if (run > 0) {
+          n_loaded += static_cast<int>(run);
+          enter(cur.b);
+          for (int64_t i = 0; i < run; ++i) {
+            const int64_t off = cur.stage * stage_elems;
+            mg_mbar_wait(&s_full[slot], phase);
+            if (stamp && tid == 0 && prm.stamps[blockIdx.x * 16 + 2] == 0) prm.stamps[blockIdx.x * 16 + 2] = global_ns();
+            const float* stage_p = s_ring + static_cast<size_t>(slot) * 2 * stage_elems;
+            full_stage(stage_p, off, cur);
+            if (n_my > 0) park(stage_p, stage_p + stage_elems, cur, off, STAGE_FULL);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[slot]);   // the stage's operands are in registers: the slot may be refilled
+            if (++slot == ring) { slot = 0; phase ^= 1u; }
+            if (batch_pos == 4) evaluate();
+            cur.stage += 1;
+            cur.t0 += kRows;
           }
-        } else {
-          slow_rows(stage_p + tid, stage_p + stage_elems + tid, g, cur, kRows);
+          cur.advance(0);
+          continue;
         }
+        if (pass == 1) {
+          run = cur.pad_run(s_nb);
+          if (run > 0) { cur.advance(run); continue; }
+        }
+        const int kind = classify(cur, s_nb, B);
+        if (kind == STAGE_PAD && pass == 1) { cur.next(); continue; }
+        const int64_t off = cur.stage * stage_elems;
+        float* g = GRAD ? prm.grad + off + tid : nullptr;
+        if (kind == STAGE_TAIL) {
+          if (active) slow_rows(prm.pred + off + tid, prm.target + off + tid, g, cur, cur.rows());
+          if (n_my > 0) { park(prm.pred + off, prm.target + off, cur, off, kind); if (batch_pos == 4) evaluate(); }
+          cur.next();
+          continue;
+        }
+        ++n_loaded;
+        mg_mbar_wait(&s_full[slot], phase);
+        if (stamp && tid == 0 && prm.stamps[blockIdx.x * 16 + 2] == 0) prm.stamps[blockIdx.x * 16 + 2] = global_ns();
+        const float* stage_p = s_ring + static_cast<size_t>(slot) * 2 * stage_elems;
+        if (kind == STAGE_PAD) {
+          // a padding-only stage of the head start: it was loaded before anything was known; its gradient rows are zero
+#pragma unroll 1
+          if (GRAD && active) for (int u = 0; u < kRows; ++u) __stcs(g + u * D, 0.f);
+        } else if (active && !(prm.debug & 1)) {
+          if ((hot || served) && T >= kRows) {
+            // a boundary stage is at most: valid rows of utterance b | padding | valid rows of utterance b + 1 | padding
+            const int rows_a = static_cast<int>(min(static_cast<int64_t>(kRows), T - cur.t0));
+            const int valid_a = static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(rows_a), s_nb[cur.b] - cur.t0)));
+            const int valid_b = rows_a < kRows ? min(kRows - rows_a, s_nb[cur.b + 1]) : 0;
+            const float* sp = stage_p + tid;
+            const float* sy = sp + stage_elems;
+            auto valid_rows = [&](int u0, int u1, int b) {
+              if (u1 <= u0 || !hot) return;
+              enter(b);
+              float part = 0.f;
+#pragma unroll 1
+              for (int u = u0; u < u1; ++u) {
+                const float d = __fsub_rn(sp[u * D], sy[u * D]);
+                part = __fadd_rn(part, __fmul_rn(d, d));
+                if (GRAD) __stcs(g + u * D, __fmul_rn(d, w2));
+              }
+              cur_l += static_cast<double>(part);
+              if (use_metric) cur_m += static_cast<double>(part);
+            };
+            valid_rows(0, valid_a, cur.b);
+            valid_rows(rows_a, rows_a + valid_b, cur.b + 1);
+            if (GRAD) {
+#pragma unroll 1
+              for (int u = valid_a; u < rows_a; ++u) __stcs(g + u * D, 0.f);
+#pragma unroll 1
+              for (int u = rows_a + valid_b; u < kRows; ++u) __stcs(g + u * D, 0.f);
+            }
+          } else {
+            slow_rows(stage_p + tid, stage_p + stage_elems + tid, g, cur, kRows);
+          }
+        }
+        if (n_my > 0 && kind != STAGE_PAD) park(stage_p, stage_p + stage_elems, cur, off, kind);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[slot]);
+        if (++slot == ring) { slot = 0; phase ^= 1u; }
+        if (batch_pos == 4) evaluate();
+        cur.next();
       }
-      if (n_my > 0) park(stage_p, stage_p + stage_elems, cur, off, kind);
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_empty[slot]);
-      if (++slot == ring) { slot = 0; phase ^= 1u; }
-      if (batch_pos == 4) evaluate();
-      cur.next();
     }
     if (stamp && tid == 0) { prm.stamps[blockIdx.x * 16 + 3] = global_ns(); prm.stamps[blockIdx.x * 16 + 7] = static_cast<unsigned long long>(n_loaded); }
+
+    // ---- the CTA's record: the lanes of a warp that feed slot s are summed with a fixed shuffle tree (slots in lane order of
+    // their first column), the warps are added in warp order by warp 0 ---------------------------------------------------------
     if (n_my > 0) evaluate();
     enter(-2);   // fold the last utterance (b = -2 never matches)
-    if (use_loss) { out_slot[0] = col.loss_slot; out_sum[0] = sum_l; out_w[0] = wsum_l; }
-    if (use_metric) { out_slot[1] = col.metric_slot; out_sum[1] = sum_m; out_n[1] = sum_n; }
+    double* mine = &s_flush[warp][0][0];
+#pragma unroll 1
+    for (int i = lane; i < 3 * prm.n_slots; i += 32) mine[i] = 0.;
+    __syncwarp();
+    const bool warp_counts = __any_sync(MG_FULL_MASK, own_special && use_metric);   // only per-thread special columns count frames here
+    fold_lanes(mine, use_loss ? col.loss_slot : -1, sum_l, wsum_l, 1, true);
+    fold_lanes(mine, use_metric ? col.metric_slot : -1, sum_m, sum_n, 2, warp_counts);
 #pragma unroll
     for (int j = 0; j < kSpPerWarp; ++j) {
-      if (j < n_my) {
-        if (my_sc[j].loss_kind != MG_COL_NONE) { out_slot[2 + 2 * j] = my_sc[j].loss_slot; out_sum[2 + 2 * j] = sp_sum_l[j]; out_w[2 + 2 * j] = sp_w_l[j]; }
-        if (my_sc[j].metric_kind != MG_COL_NONE) { out_slot[3 + 2 * j] = my_sc[j].metric_slot; out_sum[3 + 2 * j] = sp_sum_m[j]; out_n[3 + 2 * j] = sp_sum_n[j]; }
+      if (j < n_my) {   // warp-uniform
+        fold_lanes(mine, my_sc[j].loss_kind != MG_COL_NONE ? my_sc[j].loss_slot : -1, sp_sum_l[j], sp_w_l[j], 1, true);
+        fold_lanes(mine, my_sc[j].metric_kind != MG_COL_NONE ? my_sc[j].metric_slot : -1, sp_sum_m[j], sp_sum_n[j], 2, true);
       }
     }
+    consumer_barrier(n_cw * 32);
+    if (warp == 0 && lane < prm.n_slots) {
+      double a = 0., w = 0., n = 0.;
+#pragma unroll 1
+      for (int cw = 0; cw < n_cw; ++cw) { a += s_flush[cw][lane][0]; w += s_flush[cw][lane][1]; n += s_flush[cw][lane][2]; }
+      double2* out = prm.records + (static_cast<int64_t>(lane) * gridDim.x + blockIdx.x) * 2;
+      const uint64_t keep = mg_policy_evict_last();
+      mg_st_keep_f64x2(out, make_double2(a, w), keep);
+      mg_st_keep_f64x2(out + 1, make_double2(n, 0.), keep);
+    }
   }
 
-  // ---- one CTA-level reduction: contributions parked in shared memory, warp s sums slot s over them in index order with a
-  // fixed shuffle tree.  (Folding inside each warp with ballots + fp64 shuffles first was 3.7 us slower per launch.) ---------
-  {
-  __syncthreads();   // every role is done with the ring: it becomes the scratch of the reduction
-  const int n_entries = kOut * blockDim.x;
-  double* s_v = reinterpret_cast<double*>(smem_raw);           // [3][n_entries]
-  signed char* s_s = reinterpret_cast<signed char*>(s_v + 3 * n_entries);
-#pragma unroll
-  for (int e = 0; e < kOut; ++e) {
-    const int i = e * blockDim.x + tid;
-    s_v[i] = out_sum[e];
-    s_v[n_entries + i] = out_w[e];
-    s_v[2 * n_entries + i] = out_n[e];
-    s_s[i] = static_cast<signed char>(out_slot[e]);
-  }
+  // ---- ticket: the last CTA adds the records in CTA order and writes the result records.  The records were written by warp 0
+  // before the barrier; the fence of the ticket thread is cumulative over what the barrier ordered before it. -----------------
   __syncthreads();
-  const int n_warps = blockDim.x >> 5;
-  for (int slot = warp; slot < prm.n_slots; slot += n_warps) {
-    double a = 0., w = 0., n = 0.;
-    for (int i = lane; i < n_entries; i += 32) {
-      if (s_s[i] == slot) { a += s_v[i]; w += s_v[n_entries + i]; n += s_v[2 * n_entries + i]; }
-    }
-    a = mg_warp_sum(a); w = mg_warp_sum(w); n = mg_warp_sum(n);
-    if (lane == 0) { s_slot[slot][0] = a; s_slot[slot][1] = w; s_slot[slot][2] = n; }
-  }
-  __syncthreads();
-  }
-
-  // ---- ticket: the last CTA adds the per-CTA partials in index order and writes the result records.  The producer warp
-  // publishes: its threads have no gradient stores in flight, so their release fence does not wait for the CTA's stream of
-  // stores to drain (a fence in a consumer thread does). ------------------------------------------------------------------
-  if (warp == producer_warp) {
-    if (lane < prm.n_slots) {
-      double2* out = prm.partials + (static_cast<int64_t>(blockIdx.x) * prm.n_slots + lane) * 2;
-      out[0] = make_double2(s_slot[lane][0], s_slot[lane][1]);
-      out[1] = make_double2(s_slot[lane][2], 0.);
-      __threadfence();
-    }
-    __syncwarp();
-    if (lane == 0) {
-      if (stamp) prm.stamps[blockIdx.x * 16 + 4] = global_ns();
-      const bool last = atomicAdd(prm.ticket, 1u) == gridDim.x - 1;
-      if (last) __threadfence();     // acquire: the other threads read after the barrier below, through L2 (__ldcg)
-      s_is_last = last;
-    }
+  if (tid == producer_warp * 32) {
+    __threadfence();
+    if (stamp) prm.stamps[blockIdx.x * 16 + 4] = global_ns();
+    const bool last = atomicAdd(prm.ticket, 1u) == gridDim.x - 1;
+    if (last) __threadfence();     // acquire: the other threads read after the barrier below, through L2 (__ldcg)
+    s_is_last = last;
   }
   __syncthreads();
   if (!s_is_last) return;
   if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 10] = global_ns();
-  mg_term_result old;
-  memset(&old, 0, sizeof(old));
-  if (tid < prm.n_slots && prm.slots[tid].accumulate) old = *prm.slots[tid].result;   // in flight under the loads below
   {
-    // partials [cta][slot]: `per` threads per slot, thread i of a slot takes CTAs i, i + per, ... (index order per thread, twelve
-    // records in flight); then the slot's threads are summed in thread order with a fixed shuffle tree
-    double* s_v = reinterpret_cast<double*>(smem_raw);           // [n_slots][3][per]
-    const int per = blockDim.x / prm.n_slots;                     // >= 18 (n_slots <= 12, >= 224 threads)
-    const int slot = tid / per, idx = tid - slot * per;
-    if (slot < prm.n_slots) {
-      double a = 0., w = 0., n = 0.;
-      for (unsigned c0 = idx; c0 < gridDim.x; c0 += 12 * per) {
-        double2 v0[12], v1[12];
+    // records [slot][cta]: a warp per slot, lane i takes CTAs i, i + 32, ... in CTA order (consecutive lanes on consecutive
+    // records, kFinishLoads of them in flight), the lanes are summed with a fixed shuffle tree and lane 0 writes the slot's result
+    const unsigned n_rec = gridDim.x;
+    const int n_warps = blockDim.x >> 5;
+    const uint64_t keep = mg_policy_evict_last();
+    for (int sl_i = warp; sl_i < prm.n_slots; sl_i += n_warps) {
+      const MgFinishSlot& sl = prm.slots[sl_i];
+      const bool weighted = sl.weighted != 0;
+      double old_s = 0., old_c = 0.;
+      if (lane == 0 && sl.accumulate) { old_s = sl.result->sum; old_c = sl.result->count; }   // streaming-metric state, in flight under the loads
+      const double2* rec = prm.records + static_cast<int64_t>(sl_i) * n_rec * 2;
+      double s = 0., w = 0., n = 0.;
+      for (unsigned j0 = lane; j0 < n_rec; j0 += kFinishLoads * 32) {
+        double2 v0[kFinishLoads];
+        double v1[kFinishLoads];
 #pragma unroll
-        for (int j = 0; j < 12; ++j) {
-          const unsigned c = c0 + j * per;
-          if (c < gridDim.x) {
-            const double2* in = prm.partials + (static_cast<int64_t>(c) * prm.n_slots + slot) * 2;
-            v0[j] = __ldcg(in);
-            v1[j] = __ldcg(in + 1);
+        for (int u = 0; u < kFinishLoads; ++u) {
+          const unsigned j = j0 + u * 32;
+          v0[u] = make_double2(0., 0.);
+          v1[u] = 0.;
+          if (j < n_rec) {
+            v0[u] = mg_ld_keep_cg_f64x2(rec + 2 * static_cast<int64_t>(j), keep);
+            if (weighted) v1[u] = mg_ld_keep_cg_f64x2(rec + 2 * static_cast<int64_t>(j) + 1, keep).x;
           }
         }
 #pragma unroll
-        for (int j = 0; j < 12; ++j)
-          if (c0 + j * per < gridDim.x) { a += v0[j].x; w += v0[j].y; n += v1[j].x; }
+        for (int u = 0; u < kFinishLoads; ++u) { s += v0[u].x; w += v0[u].y; n += v1[u]; }
       }
-      s_v[(slot * 3 + 0) * per + idx] = a;
-      s_v[(slot * 3 + 1) * per + idx] = w;
-      s_v[(slot * 3 + 2) * per + idx] = n;
-    }
-    __syncthreads();
-    if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 11] = global_ns();
-    const int n_warps = blockDim.x >> 5;
-    for (int sl = warp; sl < prm.n_slots; sl += n_warps) {
-      double a = 0., w = 0., n = 0.;
-      for (int i = lane; i < per; i += 32) {
-        a += s_v[(sl * 3 + 0) * per + i];
-        w += s_v[(sl * 3 + 1) * per + i];
-        n += s_v[(sl * 3 + 2) * per + i];
+      if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 11] = global_ns();
+      s = mg_warp_sum(s); w = mg_warp_sum(w);
+      if (weighted) n = mg_warp_sum(n);
+      if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 15] = global_ns();
+      if (lane == 0) {
+        double c;
+        double l = w / (static_cast<double>(B) * static_cast<double>(sl.D));   // torch.mean over (B, D), losses.py:42
+        if (s_has_empty) l = __longlong_as_double(0x7ff8000000000000LL);   // an empty utterance contributes 0 / 0 (losses.py:39)
+        if (weighted) c = n;
+        else if (prm.seq_len != nullptr) c = static_cast<double>(s_valid_total);                          // frames (metrics.py:393-394)
+        else c = static_cast<double>(B) * static_cast<double>(T) * (sl.per_frame ? 1. : static_cast<double>(sl.D));   // numel (:390)
+        s += old_s;
+        c += old_c;
+        mg_term_result res;
+        res.sum = s;
+        res.count = c;
+        res.loss = l;
+        res.isum = static_cast<int64_t>(s);
+        res.sum_f32 = static_cast<float>(s);
+        res.count_f32 = static_cast<float>(c);
+        res.loss_f32 = static_cast<float>(l);
+        res.weighted_loss_f32 = 0.f;
+        *sl.result = res;
+        s_slot[sl_i][0] = sl.in_total ? static_cast<double>(sl.weight) * l : 0.;
       }
-      a = mg_warp_sum(a); w = mg_warp_sum(w); n = mg_warp_sum(n);
-      if (lane == 0) { s_slot[sl][0] = a; s_slot[sl][1] = w; s_slot[sl][2] = n; }
     }
-  }
-  __syncthreads();
-  if (tid < prm.n_slots) {
-    const MgFinishSlot& sl = prm.slots[tid];
-    double s = s_slot[tid][0], c;
-    double l = s_slot[tid][1] / (static_cast<double>(B) * static_cast<double>(sl.D));   // torch.mean over (B, D), losses.py:42
-    if (s_has_empty) l = __longlong_as_double(0x7ff8000000000000LL);   // an empty utterance contributes 0 / 0 (losses.py:39)
-    if (sl.weighted) c = s_slot[tid][2];
-    else if (prm.seq_len != nullptr) { long long v = 0; for (int w2 = 0; w2 < (blockDim.x >> 5); ++w2) v += s_wvalid[w2]; c = static_cast<double>(v); }                          // frames (metrics.py:393-394)
-    else c = static_cast<double>(B) * static_cast<double>(T) * (sl.per_frame ? 1. : static_cast<double>(sl.D));   // numel (:390)
-    if (sl.accumulate) {
-      s += old.sum;
-      c += old.count;
-    }
-    mg_term_result res;
-    res.sum = s;
-    res.count = c;
-    res.loss = l;
-    res.isum = static_cast<int64_t>(s);
-    res.sum_f32 = static_cast<float>(s);
-    res.count_f32 = static_cast<float>(c);
-    res.loss_f32 = static_cast<float>(l);
-    res.weighted_loss_f32 = 0.f;
-    *sl.result = res;
-    s_slot[tid][0] = sl.in_total ? static_cast<double>(sl.weight) * l : 0.;
   }
   __syncthreads();
   if (tid == 0) {
@@ -722,8 +801,11 @@ int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
   if (!enabled) return MG_STREAM_NOT_APPLICABLE;
   const int D = a.D, B = a.B;
   const int64_t T = a.T;
-  // preconditions: contiguous (B, T, D) tensors on 16-byte aligned bases, D <= 224, B <= 1024
-  if (D > (kMaxWarps - 1) * 32 || B > kMaxB || T < 1 || static_cast<int64_t>(B) * T * 3 >= (int64_t(1) << 31)) return MG_STREAM_NOT_APPLICABLE;
+  const int cost_valid = env_int("MG_OBJ_COST_VALID", a.grad != nullptr ? 6 : 2);
+  const int cost_pad = env_int("MG_OBJ_COST_PAD", 1);
+  // preconditions: contiguous (B, T, D) tensors on 16-byte aligned bases, D <= 224, B <= 1024, costs in 32 bits
+  if (D > (kMaxWarps - 1) * 32 || B > kMaxB || T < 1 || cost_valid < 1 || cost_valid > 16 || cost_pad < 0 || cost_pad > 16) return MG_STREAM_NOT_APPLICABLE;
+  if (static_cast<int64_t>(B) * T * (cost_valid > cost_pad ? cost_valid : cost_pad) >= (int64_t(1) << 31) - (int64_t(1) << 24)) return MG_STREAM_NOT_APPLICABLE;
   if (a.p_st != D || a.t_st != D || a.p_sb != T * D || a.t_sb != T * D) return MG_STREAM_NOT_APPLICABLE;
   if (!mg_aligned(a.pred, 16) || !mg_aligned(a.target, 16)) return MG_STREAM_NOT_APPLICABLE;
   if (a.grad != nullptr && (a.g_st != D || a.g_sb != T * D || !mg_aligned(a.grad, 16))) return MG_STREAM_NOT_APPLICABLE;
@@ -732,14 +814,13 @@ int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
   const int sms = mg_cached_sm_count();
   const int ctas_per_sm = env_int("MG_OBJ_CTAS_PER_SM", 2);
   const int n_cw = (D + 31) / 32;
-  const int threads = (n_cw + 1) * 32;
+  int n_warps = n_cw + 1;                      // consumers + producer ...
+  if (n_warps < a.n_slots) n_warps = a.n_slots < kMaxWarps ? a.n_slots : kMaxWarps;   // ... + idle warps so that the last CTA has a warp per slot
+  const int threads = n_warps * 32;
   const size_t stage_pair = static_cast<size_t>(2) * kRows * D * sizeof(float);
   const size_t zero_bytes = a.grad != nullptr ? static_cast<size_t>(kRows) * D * sizeof(float) : 0;
-  size_t reduce_bytes = static_cast<size_t>(2 + 2 * kSpPerWarp) * threads * (3 * sizeof(double) + 1) + 64;
-  const size_t finish_bytes = static_cast<size_t>(a.n_slots) * 3 * threads * sizeof(double);   // scratch of the last CTA
-  if (reduce_bytes < finish_bytes) reduce_bytes = finish_bytes;
   // shared memory per CTA: 227 KB per SM minus ~13 KB of static arrays and 1 KB of reserve per CTA
-  const size_t budget = (static_cast<size_t>(227) * 1024) / ctas_per_sm - 14 * 1024;
+  const size_t budget = (static_cast<size_t>(227) * 1024) / ctas_per_sm - 15 * 1024;
   int ring = env_int("MG_OBJ_RING", 0);
   // measured at config 2 (D = 187, two CTAs per SM): ring 2 / 3 / 4 / 5 / 6 / 8 -> 0.140 / 0.124 / 0.123 / 0.132 / 0.136 / 0.138 ms:
   // four 12 KB stages per CTA cover the latency; a deeper ring only takes shared memory away from L1
@@ -750,7 +831,6 @@ int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
   if (ring > kMaxRing) ring = kMaxRing;
   if (ring < 2) return MG_STREAM_NOT_APPLICABLE;
   size_t smem = static_cast<size_t>(ring) * stage_pair + zero_bytes;
-  if (smem < reduce_bytes) smem = reduce_bytes;
 
   const int64_t n_stages = (static_cast<int64_t>(B) * T + kRows - 1) / kRows;
   int64_t grid = static_cast<int64_t>(sms) * ctas_per_sm;
@@ -777,13 +857,14 @@ int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
   prm.cols = a.cols; prm.seq_len = a.seq_len;
   unsigned char* base = static_cast<unsigned char*>(a.workspace);
   prm.ticket = reinterpret_cast<unsigned int*>(base);
-  prm.partials = reinterpret_cast<double2*>(base + kMgTicketBytes);
+  prm.records = reinterpret_cast<double2*>(base + kMgTicketBytes);
   prm.T = T; prm.D = D; prm.B = B; prm.n_slots = a.n_slots; prm.ring = ring; prm.n_consumer_warps = n_cw;
   prm.debug = env_int("MG_OBJ_DEBUG", 0);
   prm.stamps = reinterpret_cast<unsigned long long*>(base + kMgTicketBytes + 512 * 1024);
   if ((prm.debug & 8) && a.workspace_bytes < kMgTicketBytes + 512 * 1024 + grid * 128) prm.debug &= ~8;
-  prm.cost_valid = env_int("MG_OBJ_COST_VALID", a.grad != nullptr ? 6 : 2);
-  prm.cost_pad = env_int("MG_OBJ_COST_PAD", 1);
+  prm.load_first_frac = static_cast<float>(env_int("MG_OBJ_LOAD_FIRST_PCT", 100)) / 100.f;
+  prm.cost_valid = cost_valid;
+  prm.cost_pad = cost_pad;
 
   if (smem > 200 * 1024) return MG_STREAM_NOT_APPLICABLE;
   if (a.grad != nullptr) MG_CUDA_OK(cudaFuncSetAttribute(objective_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
