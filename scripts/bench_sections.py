@@ -29,6 +29,24 @@ def timeit(fn, n_iter=20, warmup=3):
     return s.elapsed_time(e) / n_iter
 
 
+def timeit_flushed(fn, n_iter=20, warmup=3, flush_mb=512):
+    """Like :func:`timeit` for working sets that fit the 126 MB L2: a buffer larger than L2 is overwritten between two
+    timed calls (outside the event pairs), so every call starts from HBM."""
+    flush = torch.empty(flush_mb << 20, dtype=torch.uint8, device='cuda')
+    for _ in range(warmup):
+        fn()
+    pairs = []
+    for _ in range(n_iter):
+        flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        pairs.append((s, e))
+    torch.cuda.synchronize()
+    return sum(a.elapsed_time(b) for a, b in pairs) / n_iter
+
+
 class _Stock(object):
     """The reference's own functions on CUDA tensors (oracle/_ref through oracle/ref_loader.py); the restated op chain
     (oracle/aten_chain.py) when the mirror is absent."""
@@ -155,9 +173,13 @@ def other_configs(dev, peaks, reference_path=None):
     model, ema_ours, ema_stock = _Shapes(), _Shapes(), _Shapes()
     n_par = sum(p.numel() for p in model.parameters())
     ema = mg.utils.ExponentialMovingAverage(ema_ours, 0.999)
-    stock_ms = timeit(lambda: stock.ema(ema_stock, model), 10, 2)
-    row('C4', 'ExponentialMovingAverage.update_params, %d parameters in %d tensors (K6)' % (n_par, len(model.p)),
-        timeit(lambda: ema.update_params(model)), 12 * n_par, None, stock_ms)
+    # 138 MB of state is about the size of the L2: back-to-back calls would be served from it (8.9 TB/s "of HBM"), so the L2 is
+    # flushed between calls; the back-to-back figure is kept in the note (in training the optimiser has just touched the parameters)
+    stock_ms = timeit_flushed(lambda: stock.ema(ema_stock, model), 10, 2)
+    warm_ms = timeit(lambda: ema.update_params(model))
+    row('C4', 'ExponentialMovingAverage.update_params, %d parameters in %d tensors (K6), L2 flushed between calls' % (n_par, len(model.p)),
+        timeit_flushed(lambda: ema.update_params(model)), 12 * n_par, None, stock_ms,
+        note='back to back (state partly resident in the 126 MB L2): %.4f ms' % warm_ms)
     del model, ema_ours, ema_stock
 
     # ---- the tcgen05 layers (K7 forward, K7g, K7w) at the config-2 frame count -----------------------------------------
