@@ -567,7 +567,11 @@ extern "C" int mg_masked_objective_f32(const float* pred, int64_t p_sb, int64_t 
   const size_t smem = ring_bytes + side_bytes;
   MG_REQUIRE(smem <= 200 * 1024, "mg_masked_objective_f32: D=%d needs %zu bytes of shared memory", D, smem);
   dim3 grid(static_cast<unsigned>(n_chunks), static_cast<unsigned>(B));
-  if (smem > 32 * 1024) {   // static + dynamic shared memory above 48 KB needs the opt-in (the kernel has ~5 KB static)
+  static bool attr_done[64] = {};   // per device
+  int device = 0;
+  MG_CUDA_OK(cudaGetDevice(&device));
+  if (smem > 32 * 1024 && !attr_done[device & 63]) {   // static + dynamic shared memory above 48 KB needs the opt-in (the kernel has ~5 KB static)
+    attr_done[device & 63] = true;
     MG_CUDA_OK(cudaFuncSetAttribute(masked_objective_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MG_CUDA_OK(cudaFuncSetAttribute(masked_objective_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     MG_CUDA_OK(cudaFuncSetAttribute(masked_objective_kernel<true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));

@@ -794,6 +794,15 @@ int env_int(const char* name, int fallback) {
   return (e && *e) ? atoi(e) : fallback;
 }
 
+// Tuning knobs, read from the environment once per process (a dozen getenv calls per launch cost ~1.5 us of host time).
+struct Tuning {
+  int cost_valid_grad, cost_valid_fwd, cost_pad, ctas_per_sm, ring, debug, load_first_pct;
+  Tuning()
+      : cost_valid_grad(env_int("MG_OBJ_COST_VALID", 6)), cost_valid_fwd(env_int("MG_OBJ_COST_VALID", 2)), cost_pad(env_int("MG_OBJ_COST_PAD", 1)),
+        ctas_per_sm(env_int("MG_OBJ_CTAS_PER_SM", 2)), ring(env_int("MG_OBJ_RING", 0)), debug(env_int("MG_OBJ_DEBUG", 0)),
+        load_first_pct(env_int("MG_OBJ_LOAD_FIRST_PCT", 100)) {}
+};
+
 }  // namespace
 
 int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
@@ -801,8 +810,9 @@ int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
   if (!enabled) return MG_STREAM_NOT_APPLICABLE;
   const int D = a.D, B = a.B;
   const int64_t T = a.T;
-  const int cost_valid = env_int("MG_OBJ_COST_VALID", a.grad != nullptr ? 6 : 2);
-  const int cost_pad = env_int("MG_OBJ_COST_PAD", 1);
+  static const Tuning tune;
+  const int cost_valid = a.grad != nullptr ? tune.cost_valid_grad : tune.cost_valid_fwd;
+  const int cost_pad = tune.cost_pad;
   // preconditions: contiguous (B, T, D) tensors on 16-byte aligned bases, D <= 224, B <= 1024, costs in 32 bits
   if (D > (kMaxWarps - 1) * 32 || B > kMaxB || T < 1 || cost_valid < 1 || cost_valid > 16 || cost_pad < 0 || cost_pad > 16) return MG_STREAM_NOT_APPLICABLE;
   if (static_cast<int64_t>(B) * T * (cost_valid > cost_pad ? cost_valid : cost_pad) >= (int64_t(1) << 31) - (int64_t(1) << 24)) return MG_STREAM_NOT_APPLICABLE;
@@ -812,7 +822,7 @@ int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
   if (static_cast<int64_t>(B) * T < 4 * kRows) return MG_STREAM_NOT_APPLICABLE;
 
   const int sms = mg_cached_sm_count();
-  const int ctas_per_sm = env_int("MG_OBJ_CTAS_PER_SM", 2);
+  const int ctas_per_sm = tune.ctas_per_sm;
   const int n_cw = (D + 31) / 32;
   int n_warps = n_cw + 1;                      // consumers + producer ...
   if (n_warps < a.n_slots) n_warps = a.n_slots < kMaxWarps ? a.n_slots : kMaxWarps;   // ... + idle warps so that the last CTA has a warp per slot
@@ -821,7 +831,7 @@ int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
   const size_t zero_bytes = a.grad != nullptr ? static_cast<size_t>(kRows) * D * sizeof(float) : 0;
   // shared memory per CTA: 227 KB per SM minus ~13 KB of static arrays and 1 KB of reserve per CTA
   const size_t budget = (static_cast<size_t>(227) * 1024) / ctas_per_sm - 15 * 1024;
-  int ring = env_int("MG_OBJ_RING", 0);
+  int ring = tune.ring;
   // measured at config 2 (D = 187, two CTAs per SM): ring 2 / 3 / 4 / 5 / 6 / 8 -> 0.140 / 0.124 / 0.123 / 0.132 / 0.136 / 0.138 ms:
   // four 12 KB stages per CTA cover the latency; a deeper ring only takes shared memory away from L1
   if (ring <= 0) {
@@ -859,16 +869,22 @@ int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
   prm.ticket = reinterpret_cast<unsigned int*>(base);
   prm.records = reinterpret_cast<double2*>(base + kMgTicketBytes);
   prm.T = T; prm.D = D; prm.B = B; prm.n_slots = a.n_slots; prm.ring = ring; prm.n_consumer_warps = n_cw;
-  prm.debug = env_int("MG_OBJ_DEBUG", 0);
+  prm.debug = tune.debug;
   prm.stamps = reinterpret_cast<unsigned long long*>(base + kMgTicketBytes + 512 * 1024);
   if ((prm.debug & 8) && a.workspace_bytes < kMgTicketBytes + 512 * 1024 + grid * 128) prm.debug &= ~8;
-  prm.load_first_frac = static_cast<float>(env_int("MG_OBJ_LOAD_FIRST_PCT", 100)) / 100.f;
+  prm.load_first_frac = static_cast<float>(tune.load_first_pct) / 100.f;
   prm.cost_valid = cost_valid;
   prm.cost_pad = cost_pad;
 
   if (smem > 200 * 1024) return MG_STREAM_NOT_APPLICABLE;
-  if (a.grad != nullptr) MG_CUDA_OK(cudaFuncSetAttribute(objective_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-  else MG_CUDA_OK(cudaFuncSetAttribute(objective_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  static bool attr_done[64] = {};   // the attribute is per device (several GPUs in one process are allowed)
+  int device = 0;
+  MG_CUDA_OK(cudaGetDevice(&device));
+  if (!attr_done[device & 63]) {
+    MG_CUDA_OK(cudaFuncSetAttribute(objective_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    MG_CUDA_OK(cudaFuncSetAttribute(objective_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_done[device & 63] = true;
+  }
   if (a.grad != nullptr) objective_stream_kernel<true><<<static_cast<unsigned>(grid), threads, smem, stream>>>(prm);
   else objective_stream_kernel<false><<<static_cast<unsigned>(grid), threads, smem, stream>>>(prm);
   MG_LAUNCH_OK();

@@ -448,7 +448,13 @@ int launch_bulk(const unsigned char* x, int64_t x_sb, int64_t x_sp, const int32_
   const size_t smem = static_cast<size_t>(kUpWarps * kUpSlots + zero_rows) * row_bytes + ends_bytes;
   auto kernel = upsample_bulk_kernel<MODE, OUT_BF16>;
   if (smem > 48 * 1024) {
-    MG_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    static int attr_smem[64] = {};   // per instantiation and device: the largest size asked for so far
+    int device = 0;
+    MG_CUDA_OK(cudaGetDevice(&device));
+    if (static_cast<int>(smem) > attr_smem[device & 63]) {
+      MG_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+      attr_smem[device & 63] = static_cast<int>(smem);
+    }
   }
   dim3 grid(static_cast<unsigned>((T + rows - 1) / rows), static_cast<unsigned>(B));
   kernel<<<grid, kUpThreads, smem, stream>>>(x, x_sb, x_sp, ends, p0, p1, p_sb, out, P, static_cast<int>(in_row_bytes / 16),

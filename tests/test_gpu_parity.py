@@ -260,7 +260,7 @@ def test_losses_vs_oracle_random_and_strided(mg, B, T, D, kind):
     value.backward()
     want_grad = np.zeros_like(wide)
     want_grad[:, :, 3:3 + D] = O.masked_loss_grad(wide[:, :, 3:3 + D], y, seq_len, kind)
-    np.testing.assert_allclose(wide_t.grad.cpu().numpy(), want_grad, rtol=3e-6 if kind == 'bce' else REL, atol=1e-12)   # bce: fp32 division by p (1 - p)
+    np.testing.assert_allclose(wide_t.grad.cpu().numpy(), want_grad, rtol=REL, atol=1e-12)   # measured: mse 1.7e-7, l1 0, bce 2.4e-7 (scripts/measure_grad_errors.py)
     # contiguous operands take the vector path; same answer to the bit across runs
     c = dev(np.ascontiguousarray(wide[:, :, 3:3 + D]))
     v1, v2 = fn(c, dev(y), dev(seq_len)), fn(c, dev(y), dev(seq_len))
@@ -700,7 +700,8 @@ def test_kld_standard_normal_large_and_deterministic(mg):
     assert abs(loss.item() - want) <= 1e-6 * abs(want)
     assert mg.losses.KLD_standard_normal(md, lvd).item() == loss.item()
     loss.backward()
-    np.testing.assert_allclose(md.grad.cpu().numpy(), want_gm, rtol=3e-6, atol=1e-12)
+    np.testing.assert_allclose(md.grad.cpu().numpy(), want_gm, rtol=REL, atol=1e-12)       # measured 1.1e-7
+    # 1 - exp(lv) cancels near lv = 0: relative error is meaningless there (the reference's fp32 path has the same property)
     np.testing.assert_allclose(lvd.grad.cpu().numpy(), want_glv, rtol=3e-6, atol=1e-10)
 
 
