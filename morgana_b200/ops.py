@@ -16,13 +16,18 @@ _INT_DTYPES = (torch.int64, torch.int32, torch.int16, torch.int8, torch.uint8)
 
 
 _raw_stream = getattr(torch._C, '_cuda_getCurrentRawStream', None)
+_raw_device = getattr(torch._C, '_cuda_getDevice', None)     # the C call behind torch.cuda.current_device(), without its lazy-init check
+
+
+def _current_device():
+    return _raw_device() if _raw_device is not None else torch.cuda.current_device()
 
 
 def _stream():
     """The current CUDA stream of the current device as the integer handle the C ABI takes (no Stream object is built:
     ~0.3 us instead of ~2 us per launch)."""
     if _raw_stream is not None:
-        return _raw_stream(torch.cuda.current_device())
+        return _raw_stream(_current_device())
     return torch.cuda.current_stream().cuda_stream
 
 
@@ -41,7 +46,7 @@ class _device_of(object):
         self.prev = None
 
     def __enter__(self):
-        cur = torch.cuda.current_device()
+        cur = _current_device()
         if self.idx is not None and self.idx != cur:
             self.prev = cur
             torch.cuda.set_device(self.idx)

@@ -627,6 +627,47 @@ def test_fused_objective_vs_oracle(mg, B, min_p, max_p, bap_static):
         assert no_grad is None and loss_only.item() == total.item()       # bit-reproducible run to run
 
 
+@pytest.mark.parametrize('lengths,T', [
+    ([61], 61),                       # 8 stages, 2 CTAs: the tensor's short last stage lies inside a head start
+    ([5, 3, 5, 1, 4, 5, 2], 5),       # utterances shorter than a stage: every stage spans several of them
+    ([40, 0, 17, 64, 64, 1], 64),     # an empty utterance (loss nan, everything else defined), full-length ones
+    ([9] * 300, 13),                  # many short utterances, 4 padding rows each
+    ([700, 3, 350], 701),             # T odd: no stage boundary ever coincides with an utterance boundary
+    ([1200, 1187, 33, 640], 1200),    # a full-length row first
+    ([16] * 8, 16),                   # no padding anywhere, every stage full
+    ([1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12], 40),   # mostly padding: padding-only stages in the head starts
+])
+def test_fused_objective_edge_shapes(mg, lengths, T):
+    """The persistent objective kernel on shapes that exercise its stage classification (full / mixed / padding-only / short last
+    stage), the fixed head starts and the cost partition behind them, against the fp64 oracle."""
+    from morgana_b200 import workloads
+    from morgana_b200.fused import AcousticObjective
+    n = np.asarray(lengths, dtype=np.int64)
+    ac = workloads.acoustic_batch(torch.from_numpy(n), max_len=T, seed=len(lengths) + T)
+    p, t = ac['pred'].numpy(), ac['target'].numpy()
+    has_empty = bool((n == 0).any())
+    with np.errstate(invalid='ignore', divide='ignore'):
+        want_total, want_grad, want_metrics = _objective_oracle(p, t, ac['voiced'].numpy(), n)
+    pred, target, n_frames = ac['pred'].cuda(), ac['target'].cuda(), torch.from_numpy(n).cuda()
+    objective = AcousticObjective()
+    total, grad = objective(pred, target, n_frames)
+    if has_empty:
+        assert np.isnan(total.item())                          # 0 / 0 for the empty utterance, as the reference (losses.py:39)
+        keep = n > 0
+        np.testing.assert_allclose(grad.cpu().numpy()[keep], want_grad[keep], rtol=REL, atol=1e-12)
+        assert (grad.cpu().numpy()[~keep] == 0).all()          # an empty utterance is padding only
+    else:
+        assert rel_err(total.item(), want_total) <= REL
+        np.testing.assert_allclose(grad.cpu().numpy(), want_grad, rtol=REL, atol=1e-12)
+    for name, (s_want, c_want) in want_metrics.items():
+        got = objective.metrics[name]
+        assert float(got.count) == c_want, name
+        assert rel_err(got.sum, s_want) <= REL or abs(float(got.sum) - s_want) <= 1e-12, name
+    again, _ = objective(pred, target, n_frames, want_grad=False)
+    if not has_empty:
+        assert again.item() == total.item()                    # forward-only form: same bits
+
+
 def test_fused_objective_matches_drop_in_composition(mg):
     """What models/RNN_SPSS.py:120-139 computes through the drop-in ops == the one-launch objective."""
     from morgana_b200 import workloads
