@@ -44,6 +44,7 @@ void mg_set_error(const char* fmt, ...);
   } while (0)
 
 int mg_cached_sm_count();
+bool mg_pdl_enabled();   // programmatic dependent launch for the kernels of the path (MG_PDL=0 switches it off)
 
 static inline bool mg_aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
@@ -161,6 +162,30 @@ __device__ __forceinline__ void mg_mbar_wait(uint64_t* bar, uint32_t parity) {
       "}\n" ::"r"(mg_smem_addr(bar)),
       "r"(parity)
       : "memory");
+}
+
+// --- programmatic dependent launch ------------------------------------------------------------------------------------
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while the kernel before it in
+// the stream is still running; it MUST execute mg_pdl_wait() before its first access to global memory -- the wait returns when
+// the prerequisite grid has completed and its memory operations are visible, so stream order is kept for everything after it.
+// What runs before the wait (barrier initialisation, shared-memory fills) overlaps the previous kernel's tail, and the launch
+// latency is hidden.  Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void mg_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void mg_pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t mg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = mg_pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 // --- warp / CTA reductions in a fixed order ------------------------------------------------------------------------

@@ -1,4 +1,6 @@
 // Library plumbing: version, last-error buffer, device queries.
+#include <stdlib.h>
+
 #include "mg_common.cuh"
 
 static thread_local char g_last_error[512] = "";
@@ -22,6 +24,11 @@ int mg_cached_sm_count() {
     cached_count = count;
   }
   return cached_count;
+}
+
+bool mg_pdl_enabled() {
+  static const bool enabled = []() { const char* e = getenv("MG_PDL"); return !(e && *e == '0'); }();
+  return enabled;
 }
 
 extern "C" int mg_abi_version(void) { return MG_ABI_VERSION; }

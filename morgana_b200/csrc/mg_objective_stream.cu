@@ -311,13 +311,25 @@ objective_stream_kernel(const __grid_constant__ StreamParams prm) {
   };
   // ---- prologue: the producer lane goes straight to the barriers and the head start's loads; the other warps fetch the column
   // programs and the utterance lengths meanwhile ---------------------------------------------------------------------------------
+  // Programmatic dependent launch: the barriers and the zero tile are set up while the kernel before this one drains; nothing
+  // above the wait touches global memory.  All CTAs of this grid are resident from the start, so the next kernel in the stream
+  // may launch at once: its CTAs take the SMs of the CTAs that finish early and wait there for this grid to complete.
+  if (tid == producer_warp * 32) {
+    for (int i = 0; i < ring; ++i) { mg_mbar_init(&s_full[i], 1); mg_mbar_init(&s_empty[i], static_cast<uint32_t>(n_cw)); }
+    mg_mbar_init(&s_range_bar, 1);
+    mg_mbar_fence_init();
+  } else if (GRAD && warp != producer_warp) {
+    const int t2 = warp < producer_warp ? tid : tid - 32, nt = static_cast<int>(blockDim.x) - 32;
+#pragma unroll 1
+    for (int i = t2; i < stage_elems; i += nt) s_zero[i] = 0.f;
+    mg_fence_proxy_async_smem();   // the zero tile is read by the bulk-copy engine
+  }
+  mg_pdl_wait();
+  mg_pdl_launch_dependents();
   double scale = 1.;
   if (GRAD && prm.grad_scale_dev != nullptr) scale = static_cast<double>(__ldg(prm.grad_scale_dev));   // in flight under the loads below
   if (warp == producer_warp) {
     if (lane == 0) {
-      for (int i = 0; i < ring; ++i) { mg_mbar_init(&s_full[i], 1); mg_mbar_init(&s_empty[i], static_cast<uint32_t>(n_cw)); }
-      mg_mbar_init(&s_range_bar, 1);
-      mg_mbar_fence_init();
       for (int64_t st = head_lo; st < head_hi; ++st)
         if ((st + 1) * kRows <= total_rows) load_stage(st);      // every full-size stage, whatever it holds (nothing is known yet)
       if (stamp) prm.stamps[blockIdx.x * 16 + 12] = global_ns();
@@ -334,11 +346,6 @@ objective_stream_kernel(const __grid_constant__ StreamParams prm) {
     static_assert(sizeof(mg_column) == 12, "mg_column is read as three 32-bit words");
 #pragma unroll 1
     for (int k = t2; k < 3 * D; k += nt) reinterpret_cast<uint32_t*>(s_cols)[k] = mg_ld_keep_u32(reinterpret_cast<const uint32_t*>(prm.cols) + k, keep);
-    if (GRAD) {
-#pragma unroll 1
-      for (int i = t2; i < stage_elems; i += nt) s_zero[i] = 0.f;
-      mg_fence_proxy_async_smem();   // the zero tile is read by the bulk-copy engine
-    }
   }
   __syncthreads();
   if (stamp && tid == 0) prm.stamps[blockIdx.x * 16 + 8] = global_ns();
@@ -885,8 +892,8 @@ int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
     MG_CUDA_OK(cudaFuncSetAttribute(objective_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_done[device & 63] = true;
   }
-  if (a.grad != nullptr) objective_stream_kernel<true><<<static_cast<unsigned>(grid), threads, smem, stream>>>(prm);
-  else objective_stream_kernel<false><<<static_cast<unsigned>(grid), threads, smem, stream>>>(prm);
+  if (a.grad != nullptr) MG_CUDA_OK(mg_launch_pdl(objective_stream_kernel<true>, dim3(static_cast<unsigned>(grid)), dim3(threads), smem, stream, prm));
+  else MG_CUDA_OK(mg_launch_pdl(objective_stream_kernel<false>, dim3(static_cast<unsigned>(grid)), dim3(threads), smem, stream, prm));
   MG_LAUNCH_OK();
   return MG_OK;
 }

@@ -15,6 +15,8 @@ __global__ void __launch_bounds__(kScanWarpsPerCta * 32)
 dur_scan_kernel(const DurT* __restrict__ dur, int64_t dur_stride_b, int B, int P, int32_t* __restrict__ ends,
                 int64_t* __restrict__ n_frames, unsigned long long* __restrict__ summary,
                 const int32_t* __restrict__ item_ends, int64_t total_items) {
+  mg_pdl_wait();                  // nothing before this touches global memory
+  mg_pdl_launch_dependents();     // one short wave: the next kernel's CTAs may take the free SMs right away (they wait for this grid)
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * kScanWarpsPerCta + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -74,11 +76,11 @@ extern "C" int mg_dur_scan(const void* dur, int dur_is_i32, int64_t dur_stride_b
   const int grid = (B + kScanWarpsPerCta - 1) / kScanWarpsPerCta;
   auto* summary_u = reinterpret_cast<unsigned long long*>(summary);
   if (dur_is_i32) {
-    dur_scan_kernel<int32_t><<<grid, kScanWarpsPerCta * 32, 0, stream>>>(static_cast<const int32_t*>(dur), dur_stride_b,
-                                                                        B, P, ends, n_frames, summary_u, nullptr, 0);
+    MG_CUDA_OK(mg_launch_pdl(dur_scan_kernel<int32_t>, dim3(grid), dim3(kScanWarpsPerCta * 32), 0, stream, static_cast<const int32_t*>(dur),
+                             dur_stride_b, B, P, ends, n_frames, summary_u, static_cast<const int32_t*>(nullptr), static_cast<int64_t>(0)));
   } else {
-    dur_scan_kernel<long long><<<grid, kScanWarpsPerCta * 32, 0, stream>>>(static_cast<const long long*>(dur),
-                                                                          dur_stride_b, B, P, ends, n_frames, summary_u, nullptr, 0);
+    MG_CUDA_OK(mg_launch_pdl(dur_scan_kernel<long long>, dim3(grid), dim3(kScanWarpsPerCta * 32), 0, stream, static_cast<const long long*>(dur),
+                             dur_stride_b, B, P, ends, n_frames, summary_u, static_cast<const int32_t*>(nullptr), static_cast<int64_t>(0)));
   }
   MG_LAUNCH_OK();
   return MG_OK;
@@ -95,11 +97,11 @@ extern "C" int mg_dur_scan_packed(const void* dur, int dur_is_i32, const int32_t
   const int grid = (B + kScanWarpsPerCta - 1) / kScanWarpsPerCta;
   auto* summary_u = reinterpret_cast<unsigned long long*>(summary);
   if (dur_is_i32) {
-    dur_scan_kernel<int32_t><<<grid, kScanWarpsPerCta * 32, 0, stream>>>(static_cast<const int32_t*>(dur), 0, B, 0, ends,
-                                                                        n_frames, summary_u, item_ends, total_items);
+    MG_CUDA_OK(mg_launch_pdl(dur_scan_kernel<int32_t>, dim3(grid), dim3(kScanWarpsPerCta * 32), 0, stream, static_cast<const int32_t*>(dur),
+                             static_cast<int64_t>(0), B, 0, ends, n_frames, summary_u, item_ends, total_items));
   } else {
-    dur_scan_kernel<long long><<<grid, kScanWarpsPerCta * 32, 0, stream>>>(static_cast<const long long*>(dur), 0, B, 0, ends,
-                                                                          n_frames, summary_u, item_ends, total_items);
+    MG_CUDA_OK(mg_launch_pdl(dur_scan_kernel<long long>, dim3(grid), dim3(kScanWarpsPerCta * 32), 0, stream, static_cast<const long long*>(dur),
+                             static_cast<int64_t>(0), B, 0, ends, n_frames, summary_u, item_ends, total_items));
   }
   MG_LAUNCH_OK();
   return MG_OK;

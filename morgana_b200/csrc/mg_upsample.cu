@@ -115,6 +115,8 @@ upsample_bulk_kernel(const unsigned char* __restrict__ x, int64_t x_sb, int64_t 
   unsigned char* zero_tile = smem + static_cast<size_t>(kUpWarps * kUpSlots) * row_bytes;
   int32_t* smem_ends = reinterpret_cast<int32_t*>(zero_tile + static_cast<size_t>(zero_rows) * row_bytes);
 
+  mg_pdl_wait();   // programmatic dependent launch: this grid may be resident before the duration scan has finished
+  mg_pdl_launch_dependents();   // counts once the LAST wave has started: the next grid then takes the slots this one frees
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
   const int64_t t0 = static_cast<int64_t>(blockIdx.x) * rows_per_cta;
@@ -457,8 +459,8 @@ int launch_bulk(const unsigned char* x, int64_t x_sb, int64_t x_sp, const int32_
     }
   }
   dim3 grid(static_cast<unsigned>((T + rows - 1) / rows), static_cast<unsigned>(B));
-  kernel<<<grid, kUpThreads, smem, stream>>>(x, x_sb, x_sp, ends, p0, p1, p_sb, out, P, static_cast<int>(in_row_bytes / 16),
-                                              T, rows, zero_rows, item_ends, total_items);
+  MG_CUDA_OK(mg_launch_pdl(kernel, grid, dim3(kUpThreads), smem, stream, x, x_sb, x_sp, ends, p0, p1, p_sb, out, P,
+                           static_cast<int>(in_row_bytes / 16), T, rows, zero_rows, item_ends, total_items));
   MG_LAUNCH_OK();
   return MG_OK;
 }
