@@ -31,6 +31,8 @@ __device__ __forceinline__ float ema1(float s, float x, float c) {
 }
 
 __global__ void __launch_bounds__(kEmaThreads) ema_kernel(const __grid_constant__ EmaParams prm) {
+  mg_pdl_wait();                 // programmatic dependent launch (mg_common.cuh): nothing above touches global memory
+  mg_pdl_launch_dependents();
   // Which tensor does this CTA's chunk belong to?  (<= 64 entries in constant-bank parameter space.)
   int lo = 0, hi = prm.n_tensors;
   const int cta = blockIdx.x;
@@ -116,7 +118,7 @@ extern "C" int mg_ema_update_f32(float* const* shadow, const float* const* param
     prm.chunk_begin[count] = chunks;
     prm.n_tensors = count;
     prm.one_minus_decay = one_minus_decay;
-    ema_kernel<<<static_cast<unsigned>(chunks), kEmaThreads, 0, stream>>>(prm);
+    MG_CUDA_OK(mg_launch_pdl(ema_kernel, dim3(static_cast<unsigned>(chunks)), dim3(kEmaThreads), 0, stream, prm));
     MG_LAUNCH_OK();
   }
   return MG_OK;

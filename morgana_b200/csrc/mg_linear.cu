@@ -33,6 +33,8 @@ constexpr int kCastThreads = 256;
 __global__ void __launch_bounds__(kCastThreads)
 cast_pad_kernel(const float* __restrict__ x, int64_t ldx, __nv_bfloat16* __restrict__ out, int64_t ld_out, int64_t rows,
                 int K, int groups_per_row) {
+  mg_pdl_wait();                 // programmatic dependent launch (mg_common.cuh): nothing above touches global memory
+  mg_pdl_launch_dependents();
   const int64_t total = rows * groups_per_row;
   for (int64_t idx = static_cast<int64_t>(blockIdx.x) * kCastThreads + threadIdx.x; idx < total;
        idx += static_cast<int64_t>(gridDim.x) * kCastThreads) {
@@ -136,8 +138,6 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
     for (int a = 0; a < kAccStages; ++a) { mg_mbar_init(&s_acc_full[a], 1); mg_mbar_init(&s_acc_empty[a], (PAIR ? 2 : 1) * kEpilogueGroups); }
     mg_mbar_fence_init();
   }
-  for (int i = threadIdx.x; i < kMaxBias; i += kGemmThreads)
-    s_bias[i] = (prm.bias != nullptr && i < prm.N) ? __ldg(prm.bias + i) : 0.f;
   if (warp == 2) {   // one warp owns the TMEM allocation (and frees it at the end); in a pair, the same warp of both CTAs
     if (PAIR) {
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(mg_smem_addr(&s_tmem_base)), "n"(kTmemCols) : "memory");
@@ -147,6 +147,12 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
+  // Programmatic dependent launch: barriers, tensor-map prefetch and the tensor-memory allocation above overlap the previous
+  // kernel's tail; the first global read (the bias) comes after the wait.
+  mg_pdl_wait();
+  mg_pdl_launch_dependents();
+  for (int i = threadIdx.x; i < kMaxBias; i += kGemmThreads)
+    s_bias[i] = (prm.bias != nullptr && i < prm.N) ? __ldg(prm.bias + i) : 0.f;
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything is signalled across CTAs
   else __syncthreads();
@@ -362,6 +368,8 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 __global__ void __launch_bounds__(256)
 cast_transpose_kernel(const float* __restrict__ w, int64_t ldw, __nv_bfloat16* __restrict__ out, int64_t ld_out, int N, int K) {
   __shared__ float tile[32][33];
+  mg_pdl_wait();                 // programmatic dependent launch (mg_common.cuh): nothing above touches global memory
+  mg_pdl_launch_dependents();
   const int k0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;      // 32 x 8 threads
   for (int r = ty; r < 32; r += 8) {
@@ -384,7 +392,7 @@ extern "C" int mg_cast_transpose_bf16(const float* w, int64_t ldw, void* out, in
   if (K == 0 || ld_out == 0) return MG_OK;
   MG_REQUIRE(out != nullptr && (N == 0 || w != nullptr), "mg_cast_transpose_bf16: NULL buffer");
   dim3 grid(static_cast<unsigned>((K + 31) / 32), static_cast<unsigned>((ld_out + 31) / 32));
-  cast_transpose_kernel<<<grid, 256, 0, stream>>>(w, ldw, static_cast<__nv_bfloat16*>(out), ld_out, N, K);
+  MG_CUDA_OK(mg_launch_pdl(cast_transpose_kernel, grid, dim3(256), 0, stream, w, ldw, static_cast<__nv_bfloat16*>(out), ld_out, N, K));
   MG_LAUNCH_OK();
   return MG_OK;
 }
@@ -401,8 +409,8 @@ extern "C" int mg_cast_pad_bf16(const float* x, int64_t ldx, void* out, int64_t 
   int64_t blocks = (total + kCastThreads - 1) / kCastThreads;
   const int64_t cap = static_cast<int64_t>(mg_cached_sm_count()) * 16;
   if (blocks > cap) blocks = cap;
-  cast_pad_kernel<<<static_cast<unsigned>(blocks), kCastThreads, 0, stream>>>(
-      x, ldx, static_cast<__nv_bfloat16*>(out), ld_out, rows, K, groups);
+  MG_CUDA_OK(mg_launch_pdl(cast_pad_kernel, dim3(static_cast<unsigned>(blocks)), dim3(kCastThreads), 0, stream, x, ldx,
+                           static_cast<__nv_bfloat16*>(out), ld_out, rows, K, groups));
   MG_LAUNCH_OK();
   return MG_OK;
 }
@@ -484,18 +492,20 @@ extern "C" int mg_linear_bf16(const void* x, int64_t ldx, const void* w, int64_t
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = kGemmSmem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = mg_pdl_enabled() ? 2 : 1;
     if (wide) MG_CUDA_OK(cudaLaunchKernelEx(&cfg, linear_tcgen05_kernel<2>, map_x, map_w, map_y, prm));
     else MG_CUDA_OK(cudaLaunchKernelEx(&cfg, linear_tcgen05_kernel<1>, map_x, map_w, map_y, prm));
   } else {
     const unsigned n_ctas = static_cast<unsigned>(n_tiles_total < sms ? n_tiles_total : sms);   // persistent: one CTA per SM
-    linear_tcgen05_kernel<0><<<n_ctas, kGemmThreads, kGemmSmem, stream>>>(map_x, map_w, map_y, prm);
+    MG_CUDA_OK(mg_launch_pdl(linear_tcgen05_kernel<0>, dim3(n_ctas), dim3(kGemmThreads), kGemmSmem, stream, map_x, map_w, map_y, prm));
   }
   MG_LAUNCH_OK();
   return MG_OK;

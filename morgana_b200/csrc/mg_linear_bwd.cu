@@ -99,6 +99,8 @@ template <bool VEC>
 __global__ void __launch_bounds__(kActThreads, 3)
 act_grad_kernel(const ActGradParams prm) {
   __shared__ double s_sum[kActThreads][9];   // padded: the finish reads a column of it
+  mg_pdl_wait();                 // programmatic dependent launch (mg_common.cuh): nothing above touches global memory
+  mg_pdl_launch_dependents();
   const int G = static_cast<int>(prm.ld_out / 8);
   const int R = kActThreads / G;             // G <= 256 is checked by the host
   const int tid = threadIdx.x;
@@ -142,6 +144,8 @@ act_grad_kernel(const ActGradParams prm) {
 __global__ void __launch_bounds__(256)
 bias_grad_finish_kernel(const double* __restrict__ partial, int n_ctas, int64_t ld, int N, float* __restrict__ bias_grad) {
   __shared__ double s_part[8][33];
+  mg_pdl_wait();                 // programmatic dependent launch (mg_common.cuh): nothing above touches global memory
+  mg_pdl_launch_dependents();
   const int col = blockIdx.x * 32 + (threadIdx.x & 31), l = threadIdx.x >> 5;
   double s = 0.;
   if (col < N)
@@ -230,6 +234,8 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
       asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
   }
+  mg_pdl_wait();                 // programmatic dependent launch (mg_common.cuh): nothing above touches global memory
+  mg_pdl_launch_dependents();
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   if (PAIR) cluster_sync_all(); else __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -308,6 +314,8 @@ wgrad_tcgen05_kernel(const __grid_constant__ CUtensorMap map_g, const __grid_con
 __global__ void __launch_bounds__(256)
 wgrad_finish_kernel(const float* __restrict__ partial, int splits, int64_t slice_elems, int64_t ld, int N, int K,
                     float* __restrict__ grad_w, int64_t ldw, int vec_out) {
+  mg_pdl_wait();                 // programmatic dependent launch (mg_common.cuh): nothing above touches global memory
+  mg_pdl_launch_dependents();
   const int groups = (K + 3) / 4;
   const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (idx >= static_cast<int64_t>(N) * groups) return;
@@ -341,6 +349,8 @@ wgrad_finish_kernel(const float* __restrict__ partial, int splits, int64_t slice
 __global__ void __launch_bounds__(256)
 wgrad_finish_warp_kernel(const float* __restrict__ partial, int splits, int64_t slice_elems, int64_t ld, int N, int K,
                          float* __restrict__ grad_w, int64_t ldw, int vec_out) {
+  mg_pdl_wait();                 // programmatic dependent launch (mg_common.cuh): nothing above touches global memory
+  mg_pdl_launch_dependents();
   const int groups = (K + 3) / 4;
   const int64_t idx = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
@@ -443,11 +453,11 @@ extern "C" int mg_act_grad_bf16(const void* grad_y, int grad_is_bf16, int64_t ld
   // 16-byte row segments in both operands: strides of 4 fp32 / 8 bf16 elements
   const bool vec = N % 8 == 0 && ldg % (grad_is_bf16 ? 8 : 4) == 0 && mg_aligned(grad_y, 16) &&
                    (y == nullptr || (ldy % (y_is_bf16 ? 8 : 4) == 0 && mg_aligned(y, 16)));
-  if (vec) act_grad_kernel<true><<<n_ctas, kActThreads, 0, stream>>>(prm);
-  else act_grad_kernel<false><<<n_ctas, kActThreads, 0, stream>>>(prm);
+  if (vec) MG_CUDA_OK(mg_launch_pdl(act_grad_kernel<true>, dim3(n_ctas), dim3(kActThreads), 0, stream, prm));
+  else MG_CUDA_OK(mg_launch_pdl(act_grad_kernel<false>, dim3(n_ctas), dim3(kActThreads), 0, stream, prm));
   MG_LAUNCH_OK();
   if (bias_grad != nullptr) {
-    bias_grad_finish_kernel<<<(N + 31) / 32, 256, 0, stream>>>(prm.partial, n_ctas, ld_out, N, bias_grad);
+    MG_CUDA_OK(mg_launch_pdl(bias_grad_finish_kernel, dim3((N + 31) / 32), dim3(256), 0, stream, static_cast<const double*>(prm.partial), static_cast<int>(n_ctas), ld_out, N, bias_grad));
     MG_LAUNCH_OK();
   }
   return MG_OK;
@@ -518,16 +528,18 @@ extern "C" int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, i
     cfg.blockDim = dim3(kWgThreads);
     cfg.dynamicSmemBytes = kWgSmem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = mg_pdl_enabled() ? 2 : 1;
     MG_CUDA_OK(cudaLaunchKernelEx(&cfg, wgrad_tcgen05_kernel<true>, map_g, map_x, prm));
   } else {
-    wgrad_tcgen05_kernel<false><<<units, kWgThreads, kWgSmem, stream>>>(map_g, map_x, prm);
+    MG_CUDA_OK(mg_launch_pdl(wgrad_tcgen05_kernel<false>, dim3(units), dim3(kWgThreads), kWgSmem, stream, map_g, map_x, prm));
   }
   MG_LAUNCH_OK();
   const int64_t slice = static_cast<int64_t>(plan.n_tiles) * plan.tile_rows * plan.k_tiles * plan.tile_k;
@@ -535,11 +547,11 @@ extern "C" int mg_linear_wgrad_bf16(const void* g, int64_t ldg, const void* x, i
   const int vec_out = (ldw % 4 == 0 && mg_aligned(grad_w, 16)) ? 1 : 0;
   const int64_t ld_partial = static_cast<int64_t>(plan.k_tiles) * plan.tile_k;
   if (plan.splits > 16)
-    wgrad_finish_warp_kernel<<<static_cast<unsigned>((elems * 32 + 255) / 256), 256, 0, stream>>>(
-        prm.partial, plan.splits, slice, ld_partial, N, K, grad_w, ldw, vec_out);
+    MG_CUDA_OK(mg_launch_pdl(wgrad_finish_warp_kernel, dim3(static_cast<unsigned>((elems * 32 + 255) / 256)), dim3(256), 0, stream,
+                             static_cast<const float*>(prm.partial), plan.splits, slice, ld_partial, N, K, grad_w, ldw, vec_out));
   else
-    wgrad_finish_kernel<<<static_cast<unsigned>((elems + 255) / 256), 256, 0, stream>>>(
-        prm.partial, plan.splits, slice, ld_partial, N, K, grad_w, ldw, vec_out);
+    MG_CUDA_OK(mg_launch_pdl(wgrad_finish_kernel, dim3(static_cast<unsigned>((elems + 255) / 256)), dim3(256), 0, stream,
+                             static_cast<const float*>(prm.partial), plan.splits, slice, ld_partial, N, K, grad_w, ldw, vec_out));
   MG_LAUNCH_OK();
   return MG_OK;
 }

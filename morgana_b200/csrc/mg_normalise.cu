@@ -34,6 +34,8 @@ __global__ void __launch_bounds__(kNormThreads)
 normalise_kernel(const float* __restrict__ x, const float* __restrict__ p0, const float* __restrict__ p1,
                  float* __restrict__ out, int64_t first_elem, int64_t n_units, int D, int64_t rows_per_param,
                  int64_t step_rows, int step_cols) {
+  mg_pdl_wait();                 // programmatic dependent launch (mg_common.cuh): nothing above touches global memory
+  mg_pdl_launch_dependents();
   const int64_t tid = static_cast<int64_t>(blockIdx.x) * kNormThreads + threadIdx.x;
   const int64_t n_threads = static_cast<int64_t>(gridDim.x) * kNormThreads;
   // (row, col) of this thread's first element; afterwards advance by n_threads * VEC elements per iteration:
@@ -98,8 +100,8 @@ int launch(const float* x, const float* p0, const float* p1, int mode, int inver
   const int step_cols = static_cast<int>(stride_elems % D);
   const unsigned grid = static_cast<unsigned>(blocks);
 #define MG_NORM_LAUNCH(MODE, INV)                                                                             \
-  normalise_kernel<VEC, MODE, INV><<<grid, kNormThreads, 0, stream>>>(x, p0, p1, out, first_elem, n_units, D, \
-                                                                       rows_per_param, step_rows, step_cols)
+  MG_CUDA_OK(mg_launch_pdl(normalise_kernel<VEC, MODE, INV>, dim3(grid), dim3(kNormThreads), 0, stream, x, p0, p1, out, first_elem, \
+                           n_units, D, rows_per_param, step_rows, step_cols))
   if (mode == MG_NORM_MVN) {
     if (inverse) MG_NORM_LAUNCH(MG_NORM_MVN, true); else MG_NORM_LAUNCH(MG_NORM_MVN, false);
   } else {

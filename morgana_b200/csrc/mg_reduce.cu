@@ -400,6 +400,8 @@ __global__ void __launch_bounds__(kRedThreads, 4)
 masked_reduce_kernel(const __grid_constant__ ReduceParams prm) {
   __shared__ double s_red[96];
   __shared__ bool s_is_last;
+  mg_pdl_wait();                 // programmatic dependent launch (mg_common.cuh): nothing above touches global memory
+  mg_pdl_launch_dependents();
   double* s_a = s_red;
   double* s_b = s_red + 32;
 
@@ -545,7 +547,7 @@ extern "C" int mg_masked_reduce(const mg_term* terms, int n_terms, const int64_t
   { const char* e = getenv("MG_RED_SLICE_MODE"); if (e) prm.slice_mode = atoi(e); }
 
   dim3 grid(static_cast<unsigned>(max_chunks), static_cast<unsigned>(B), static_cast<unsigned>(n_terms));
-  masked_reduce_kernel<<<grid, kRedThreads, 0, stream>>>(prm);
+  MG_CUDA_OK(mg_launch_pdl(masked_reduce_kernel, grid, dim3(kRedThreads), 0, stream, prm));
   MG_LAUNCH_OK();
   return MG_OK;
 }
