@@ -344,22 +344,24 @@ def run_ours(args, rank, world, local_rank):
     barrier()
 
     # ---- timed region: exactly K steps, device-resident inputs ---------------------------------------------------------
-    # A pair of event records costs ~3 us of the stream's time, so the probe brackets K2 on steps 0, 4, 8, ... and K4b on steps
-    # 2, 6, 10, ...; the averages are still taken live, inside the timed region, on the launching stream.
+    # A pair of event records costs ~3 us of the stream's time and keeps the bracketed launch from overlapping its neighbours
+    # (programmatic dependent launch), so the probe brackets K2 on steps 0, 8, 16, ... and K4b on steps 4, 12, 20, ... (every 4th
+    # step each in runs shorter than 32 steps); the averages are still taken live, inside the timed region, on the launching stream.
     k2_probe, k4b_probe = ops.KernelProbe('K2'), ops.KernelProbe('K4b')
     k2_steps, k4b_steps = [], []
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     frames_done = 0
+    period = 8 if args.steps >= 32 else 4
     barrier()
     wall0 = time.time()
     start.record(stream)
     for i in range(args.steps):
         batch = dev_batches[i % N_ROTATING_BATCHES]
-        if i % 4 == 0:
+        if i % period == 0:
             k2_steps.append(i)
             with k2_probe:
                 step(batch, loss_log[i])
-        elif i % 4 == 2:
+        elif i % period == period // 2:
             k4b_steps.append(i)
             with k4b_probe:
                 step(batch, loss_log[i])
