@@ -303,7 +303,7 @@ def training_section(rank, world, dev, peaks, steps=40, batch_size=32):
                 if isinstance(value, torch.Tensor):
                     value.zero_()
 
-    def timed(run_step):
+    def timed(run_step, steps=steps):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
@@ -359,6 +359,11 @@ def training_section(rank, world, dev, peaks, steps=40, batch_size=32):
     graph_ms, _, graph_last = timed(replay('with_allreduce'))
     reset()
     bare_ms, _, _ = timed(replay('without_allreduce'))
+    # BASELINE.json configs[4] to the letter: ONE epoch over 4096 utterances sharded over the ranks, 32 per rank per step (strong
+    # scaling of the epoch: 128 / 64 / 32 / 16 steps per rank at 1 / 2 / 4 / 8 GPUs); each rank's shard cycles over its 4 batches
+    reset()
+    epoch_steps = max(4096 // (batch_size * world), 1)
+    epoch_step_ms, epoch_frames, _ = timed(replay('with_allreduce'), epoch_steps)
     torch.cuda.synchronize()
     for graph, _ in graphs.values():       # a captured NCCL all-reduce must be released before the process group goes away
         graph.reset()
@@ -376,6 +381,10 @@ def training_section(rank, world, dev, peaks, steps=40, batch_size=32):
                                    'what': 'one NCCL all-reduce of the flat fp32 gradient buffer (%d KB) between backward and Adam, '
                                            'captured in the step\'s CUDA graph; exposed = step with - step without the collective'
                                            % (4 * n_par // 1024)},
+            'epoch_of_4096_utterances': {'steps_per_rank': epoch_steps, 'ms': round(epoch_step_ms * epoch_steps, 3),
+                                         'valid_frames_per_s': round(epoch_frames / (epoch_step_ms * epoch_steps) * 1e3),
+                                         'what': 'configs[4] as written: 4096 utterances sharded over the ranks, 32 per rank per step, '
+                                                 'the captured step replayed steps_per_rank times (CUDA events, max over ranks)'},
             'loss_first_last': [round(first_loss, 5), round(graph_last, 5)],
             'step': 'upsample_to_repetitions (fused minmax, bf16 frames) -> 4 x nn.Linear (tcgen05 forward, act-grad, weight-gradient, '
                     'input-gradient kernels) -> losses.mse -> backward -> all-reduce -> fused Adam -> EMA (K6) -> RMSE metric; '
