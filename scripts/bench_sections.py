@@ -135,7 +135,21 @@ def other_configs(dev, peaks, reference_path=None):
         k2_bytes + 4 * 187 * (2 * F + B * T), F, stock_step,
         note='stock = %s: data.normalise_minmax, utils.upsample_to_repetitions, 3 x losses.mse + losses.bce + backward, '
              '4 x metrics.accumulate' % stock.kind)
-    del pred2, target2, voiced2, ac
+    # K4b alone: back-to-back launches alternating between two input pairs (each pair is 0.5 GB: nothing of one launch's inputs is
+    # left in L2 for the next); consecutive launches overlap head and tail (programmatic dependent launch), no event in between
+    pred2b, target2b = pred2.clone(), target2.clone()
+    pairs, turn = ((pred2, target2), (pred2b, target2b)), [0]
+
+    def objective_alone():
+        turn[0] ^= 1
+        return objective(pairs[turn[0]][0], pairs[turn[0]][1], n2)
+    k4b_bytes = 4 * 187 * (2 * F + B * T)
+    row('C2', 'the objective alone (K4b: 3 mse + bce + gradient + 4 metrics), back-to-back launches on two input pairs',
+        timeit(objective_alone, 40, 5), k4b_bytes, F, None,
+        note='inside the bench step the same kernel is timed between two event records, right after K2: see roofline_k4b')
+    row('C2', 'the objective alone, forward only (no gradient)', timeit(lambda: objective(pred2, target2, n2, want_grad=False), 40, 5),
+        4 * 187 * 2 * F, F, None)
+    del pred2, target2, voiced2, ac, pred2b, target2b, pairs
 
     # ---- config 3: 1024 utterances, 187-dim targets -------------------------------------------------------------------
     n3 = workloads.acoustic_lengths(batch_size=1024, seed=1234)
