@@ -283,6 +283,12 @@ typedef struct mg_slot {
   float weight;
 } mg_slot;
 
+/* host-only: the stage -> CTA partition of the persistent row-stream form of mg_masked_objective_f32 for given utterance lengths
+ * (HOST array, or NULL for full-length utterances) on a device with `sms` SMs, computed with the same functions the device runs:
+ * out[0] = grid, out[1] = first stage behind the fixed head starts, out[2] = number of 8-row stages, out[3 .. 3 + grid] = range
+ * boundaries.  Returns 1 when the shape is not one the stream form takes.  Used by the CPU tests (partition invariants). */
+int mg_objective_stream_plan(const int64_t* seq_len_host, int B, int64_t T, int D, int has_grad, int n_slots, int sms,
+                             int64_t* out, int64_t out_len);
 int mg_masked_objective_f32(const float* pred, int64_t p_sb, int64_t p_st, const float* target, int64_t t_sb, int64_t t_st,
                             float* grad, int64_t g_sb, int64_t g_st, const float* grad_scale_dev,
                             const mg_column* cols, int D, const mg_slot* slots, int n_slots,

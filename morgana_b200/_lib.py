@@ -85,6 +85,7 @@ PROTOTYPES = {
     'mg_masked_objective_f32': (c_int, [c_void_p, c_i64, c_i64, c_void_p, c_i64, c_i64, c_void_p, c_i64, c_i64, c_void_p,
                                         c_void_p, c_int, ctypes.POINTER(Slot), c_int, c_void_p, c_int, c_i64, c_void_p,
                                         c_i64, c_void_p]),
+    'mg_objective_stream_plan': (c_int, [ctypes.POINTER(c_i64), c_int, c_i64, c_int, c_int, c_int, c_int, ctypes.POINTER(c_i64), c_i64]),
     'mg_ema_update_f32': (c_int, [ctypes.POINTER(c_void_p), ctypes.POINTER(c_void_p), ctypes.POINTER(c_i64), c_int,
                                   c_f32, c_void_p]),
     'mg_mlpg_workspace_bytes': (c_i64, [c_int, c_i64, c_int, c_int]),

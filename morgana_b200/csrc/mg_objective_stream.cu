@@ -162,11 +162,11 @@ __device__ __forceinline__ int classify(const StageCursor& c, const int* s_nb, i
 struct CostModel {
   int64_t T, first_row;
   unsigned cost_valid, cost_pad;
-  __device__ __forceinline__ unsigned cut(int b) const {       // rows of utterance b that belong to the head starts
+  __host__ __device__ __forceinline__ unsigned cut(int b) const {       // rows of utterance b that belong to the head starts
     const int64_t c = first_row - static_cast<int64_t>(b) * T;
     return static_cast<unsigned>(c < 0 ? 0 : (c > T ? T : c));
   }
-  __device__ __forceinline__ unsigned cost(int b, unsigned n) const {
+  __host__ __device__ __forceinline__ unsigned cost(int b, unsigned n) const {
     const unsigned c = cut(b), t = static_cast<unsigned>(T);
     const unsigned valid = n > c ? n - c : 0u, from = n > c ? n : c;
     return cost_valid * valid + cost_pad * (t - from);
@@ -175,7 +175,7 @@ struct CostModel {
 
 // Cost position -> stage, rounded up to a stage.  Monotone in x, and the same function at both ends of every CTA's range, so the
 // ranges tile the stages exactly.
-__device__ __forceinline__ int64_t cost_to_stage(unsigned x, const CostModel& cm, const int* s_pref, const int* s_nb, int B,
+__host__ __device__ __forceinline__ int64_t cost_to_stage(unsigned x, const CostModel& cm, const int* s_pref, const int* s_nb, int B,
                                                  int64_t first_stage, int64_t n_stages) {
   if (x == 0) return first_stage;
   if (x >= static_cast<unsigned>(s_pref[B])) return n_stages;
@@ -810,6 +810,37 @@ struct Tuning {
         load_first_pct(env_int("MG_OBJ_LOAD_FIRST_PCT", 100)) {}
 };
 
+// Launch geometry: consumer warps, threads, ring depth, shared memory and grid of the stream kernel for one problem size.
+struct StreamGeometry { int n_cw, threads, ring; size_t smem; int64_t grid, n_stages; };
+
+StreamGeometry stream_geometry(int B, int64_t T, int D, bool has_grad, int n_slots, int sms, int ctas_per_sm, int ring_override) {
+  StreamGeometry g;
+  g.n_cw = (D + 31) / 32;
+  int n_warps = g.n_cw + 1;                      // consumers + producer ...
+  if (n_warps < n_slots) n_warps = n_slots < kMaxWarps ? n_slots : kMaxWarps;   // ... + idle warps so that the last CTA has a warp per slot
+  g.threads = n_warps * 32;
+  const size_t stage_pair = static_cast<size_t>(2) * kRows * D * sizeof(float);
+  const size_t zero_bytes = has_grad ? static_cast<size_t>(kRows) * D * sizeof(float) : 0;
+  // shared memory per CTA: 227 KB per SM minus ~13 KB of static arrays and 1 KB of reserve per CTA
+  const size_t budget = (static_cast<size_t>(227) * 1024) / ctas_per_sm - 15 * 1024;
+  int ring = ring_override;
+  // measured at config 2 (D = 187, two CTAs per SM): ring 2 / 3 / 4 / 5 / 6 / 8 -> 0.140 / 0.124 / 0.123 / 0.132 / 0.136 / 0.138 ms:
+  // four 12 KB stages per CTA cover the latency; a deeper ring only takes shared memory away from L1
+  if (ring <= 0) {
+    ring = budget > zero_bytes ? static_cast<int>((budget - zero_bytes) / stage_pair) : 0;
+    if (ring > 4) ring = 4;
+  }
+  if (ring > kMaxRing) ring = kMaxRing;
+  g.ring = ring;
+  g.smem = static_cast<size_t>(ring) * stage_pair + zero_bytes;
+  g.n_stages = (static_cast<int64_t>(B) * T + kRows - 1) / kRows;
+  int64_t grid = static_cast<int64_t>(sms) * ctas_per_sm;
+  if (grid > g.n_stages / 4) grid = g.n_stages / 4 > 0 ? g.n_stages / 4 : 1;     // tiny batches: at least four stages per CTA
+  if (grid > kMaxCtas) grid = kMaxCtas;
+  g.grid = grid;
+  return g;
+}
+
 }  // namespace
 
 int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
@@ -828,31 +859,11 @@ int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
   if (a.grad != nullptr && (a.g_st != D || a.g_sb != T * D || !mg_aligned(a.grad, 16))) return MG_STREAM_NOT_APPLICABLE;
   if (static_cast<int64_t>(B) * T < 4 * kRows) return MG_STREAM_NOT_APPLICABLE;
 
-  const int sms = mg_cached_sm_count();
-  const int ctas_per_sm = tune.ctas_per_sm;
-  const int n_cw = (D + 31) / 32;
-  int n_warps = n_cw + 1;                      // consumers + producer ...
-  if (n_warps < a.n_slots) n_warps = a.n_slots < kMaxWarps ? a.n_slots : kMaxWarps;   // ... + idle warps so that the last CTA has a warp per slot
-  const int threads = n_warps * 32;
-  const size_t stage_pair = static_cast<size_t>(2) * kRows * D * sizeof(float);
-  const size_t zero_bytes = a.grad != nullptr ? static_cast<size_t>(kRows) * D * sizeof(float) : 0;
-  // shared memory per CTA: 227 KB per SM minus ~13 KB of static arrays and 1 KB of reserve per CTA
-  const size_t budget = (static_cast<size_t>(227) * 1024) / ctas_per_sm - 15 * 1024;
-  int ring = tune.ring;
-  // measured at config 2 (D = 187, two CTAs per SM): ring 2 / 3 / 4 / 5 / 6 / 8 -> 0.140 / 0.124 / 0.123 / 0.132 / 0.136 / 0.138 ms:
-  // four 12 KB stages per CTA cover the latency; a deeper ring only takes shared memory away from L1
-  if (ring <= 0) {
-    ring = budget > zero_bytes ? static_cast<int>((budget - zero_bytes) / stage_pair) : 0;
-    if (ring > 4) ring = 4;
-  }
-  if (ring > kMaxRing) ring = kMaxRing;
-  if (ring < 2) return MG_STREAM_NOT_APPLICABLE;
-  size_t smem = static_cast<size_t>(ring) * stage_pair + zero_bytes;
-
-  const int64_t n_stages = (static_cast<int64_t>(B) * T + kRows - 1) / kRows;
-  int64_t grid = static_cast<int64_t>(sms) * ctas_per_sm;
-  if (grid > n_stages / 4) grid = n_stages / 4 > 0 ? n_stages / 4 : 1;     // tiny batches: at least four stages per CTA
-  if (grid > kMaxCtas) grid = kMaxCtas;
+  const StreamGeometry geo = stream_geometry(B, T, D, a.grad != nullptr, a.n_slots, mg_cached_sm_count(), tune.ctas_per_sm, tune.ring);
+  if (geo.ring < 2) return MG_STREAM_NOT_APPLICABLE;
+  const int n_cw = geo.n_cw, threads = geo.threads, ring = geo.ring;
+  const size_t smem = geo.smem;
+  const int64_t grid = geo.grid;
   const int64_t need = kMgTicketBytes + grid * a.n_slots * static_cast<int64_t>(2 * sizeof(double2));
   if (a.workspace_bytes < need) return MG_STREAM_NOT_APPLICABLE;
 
@@ -895,5 +906,49 @@ int mg_objective_stream_launch(const MgObjectiveArgs& a, cudaStream_t stream) {
   if (a.grad != nullptr) MG_CUDA_OK(mg_launch_pdl(objective_stream_kernel<true>, dim3(static_cast<unsigned>(grid)), dim3(threads), smem, stream, prm));
   else MG_CUDA_OK(mg_launch_pdl(objective_stream_kernel<false>, dim3(static_cast<unsigned>(grid)), dim3(threads), smem, stream, prm));
   MG_LAUNCH_OK();
+  return MG_OK;
+}
+
+// Host-only: the stage -> CTA partition of the stream kernel for given utterance lengths, computed with the SAME functions the
+// device runs (CostModel, cost_to_stage, the double division of the range ends).  out[0] = grid, out[1] = first stage behind the head
+// starts, out[2] = number of stages, out[3 .. 3 + grid] = the range boundaries (CTA c owns [out[3 + c], out[4 + c])).  Returns
+// MG_STREAM_NOT_APPLICABLE for shapes the stream kernel does not take.  Used by the CPU tests to check the partition's invariants.
+extern "C" int mg_objective_stream_plan(const int64_t* seq_len_host, int B, int64_t T, int D, int has_grad, int n_slots, int sms,
+                                        int64_t* out, int64_t out_len) {
+  MG_REQUIRE(B >= 1 && T >= 1 && D >= 1 && n_slots >= 1 && n_slots <= MG_MAX_TERMS && sms >= 1 && out != nullptr, "mg_objective_stream_plan: bad argument");
+  const int cost_valid = has_grad ? 6 : 2, cost_pad = has_grad ? 1 : 0;
+  if (D > (kMaxWarps - 1) * 32 || B > kMaxB) return MG_STREAM_NOT_APPLICABLE;
+  if (static_cast<int64_t>(B) * T * cost_valid >= (int64_t(1) << 31) - (int64_t(1) << 24)) return MG_STREAM_NOT_APPLICABLE;
+  if (static_cast<int64_t>(B) * T < 4 * kRows) return MG_STREAM_NOT_APPLICABLE;
+  const StreamGeometry geo = stream_geometry(B, T, D, has_grad != 0, n_slots, sms, 2, 0);
+  if (geo.ring < 2) return MG_STREAM_NOT_APPLICABLE;
+  MG_REQUIRE(out_len >= 4 + geo.grid, "mg_objective_stream_plan: out holds %lld values, %lld needed", static_cast<long long>(out_len), static_cast<long long>(4 + geo.grid));
+  const int n_head = geo.ring < kHead ? geo.ring : kHead;
+  const int64_t first_stage = geo.grid * n_head < geo.n_stages ? geo.grid * n_head : geo.n_stages;
+  CostModel cm;
+  cm.T = T; cm.first_row = first_stage * kRows; cm.cost_valid = static_cast<unsigned>(cost_valid); cm.cost_pad = static_cast<unsigned>(cost_pad);
+  int* nb = static_cast<int*>(malloc(sizeof(int) * (2 * static_cast<size_t>(B) + 1)));
+  MG_REQUIRE(nb != nullptr, "mg_objective_stream_plan: out of memory");
+  int* pref = nb + B;
+  unsigned carry = 0;
+  for (int b = 0; b < B; ++b) {
+    int64_t n = seq_len_host != nullptr ? seq_len_host[b] : T;
+    n = n < 0 ? 0 : (n > T ? T : n);
+    nb[b] = static_cast<int>(n);
+    pref[b] = static_cast<int>(carry);
+    carry += cm.cost(b, static_cast<unsigned>(n));
+  }
+  pref[B] = static_cast<int>(carry);
+  out[0] = geo.grid; out[1] = first_stage; out[2] = geo.n_stages;
+  for (int64_t c = 0; c <= geo.grid; ++c) {
+    int64_t stage;
+    if (c >= geo.grid) stage = geo.n_stages;
+    else {
+      const unsigned x = static_cast<unsigned>(static_cast<double>(carry) * static_cast<double>(c) / static_cast<double>(geo.grid));
+      stage = cost_to_stage(x, cm, pref, nb, B, first_stage, geo.n_stages);
+    }
+    out[3 + c] = stage;
+  }
+  free(nb);
   return MG_OK;
 }

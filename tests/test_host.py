@@ -277,6 +277,54 @@ def test_wgrad_plan_invariants(mg):
         assert _lib.lib.mg_linear_wgrad_workspace_bytes(M, N, K) == 4 * splits * n_tiles * tile_rows * k_tiles * tile_k
 
 
+def test_objective_stream_partition_invariants(mg):
+    """The stage -> CTA partition of the persistent objective kernel (host-only mg_objective_stream_plan: the same CostModel /
+    cost_to_stage functions the device runs): the ranges tile [first stage behind the head starts, number of stages) exactly and in
+    order, the head starts fit the tensor, and no CTA's range costs more than an even share plus one utterance boundary's worth
+    of rounding -- for ragged, empty, full-length and tiny batches, forward-only and with the gradient."""
+    import ctypes
+    from morgana_b200 import _lib
+    rng = np.random.default_rng(7)
+    cases = [(256, 1387, 187, None), (1, 61, 187, [61]), (7, 5, 187, [5, 3, 5, 1, 4, 5, 2]), (6, 64, 187, [40, 0, 17, 64, 64, 1]),
+             (300, 13, 187, [9] * 300), (3, 701, 187, [700, 3, 350]), (12, 40, 187, list(range(1, 13))), (1024, 1200, 187, None),
+             (8, 16, 4, [16] * 8), (64, 50, 1, None), (33, 333, 224, None), (2, 16, 187, [0, 0])]
+    for _ in range(60):
+        B, T = int(rng.integers(1, 1025)), int(rng.integers(1, 1500))
+        cases.append((B, T, int(rng.integers(1, 225)), None))
+    checked = 0
+    for B, T, D, lengths in cases:
+        if lengths is None:
+            lengths = rng.integers(0, T + 1, B) if rng.random() < 0.8 else np.full(B, T)
+        n = np.clip(np.asarray(lengths, dtype=np.int64), 0, T)
+        for has_grad in (1, 0):
+            out = (ctypes.c_int64 * (4 + 1024))()
+            seq = (ctypes.c_int64 * B)(*[int(v) for v in n])
+            rc = _lib.lib.mg_objective_stream_plan(seq, B, T, D, has_grad, 8, 148, out, len(out))
+            if rc == 1:                      # not a shape of the stream form (fewer than 32 rows, costs beyond 31 bits ...)
+                assert B * T < 32 or B * T * 6 >= 2 ** 31 - 2 ** 24, (B, T, D)
+                continue
+            assert rc == 0, (B, T, D, _lib.last_error() if hasattr(_lib, 'last_error') else rc)
+            grid, first_stage, n_stages = out[0], out[1], out[2]
+            bounds = np.array(out[3:3 + grid + 1])
+            assert n_stages == (B * T + 7) // 8 and 1 <= grid <= 296 and grid <= max(n_stages // 4, 1)
+            assert first_stage == min(4 * grid, n_stages)                       # four fixed stages per CTA
+            assert bounds[0] == first_stage and bounds[-1] == n_stages, (B, T, D, bounds[:3], bounds[-3:])
+            assert (np.diff(bounds) >= 0).all()                                  # contiguous ranges, in order: they tile the stages
+            # cost of every range under the kernel's model (valid row 6 / 2, padding row 1 / 0), rows behind the head starts only
+            cost_valid, cost_pad = (6, 1) if has_grad else (2, 0)
+            row_cost = np.where(np.arange(T)[None, :] < n[:, None], cost_valid, cost_pad).reshape(-1).astype(np.int64)
+            row_cost[:first_stage * 8] = 0
+            prefix = np.concatenate([[0], np.cumsum(row_cost)])
+            ends = np.minimum(bounds * 8, B * T)
+            per_cta = prefix[ends[1:]] - prefix[ends[:-1]]
+            assert per_cta.sum() == prefix[-1]
+            share = prefix[-1] / grid
+            # a boundary is rounded up to a stage (8 rows) and the cost position to one row: nobody is more than ~two stages over
+            assert per_cta.max() <= share + 2 * 8 * cost_valid + cost_valid, (B, T, D, has_grad, per_cta.max(), share)
+            checked += 1
+    assert checked > 100
+
+
 def test_custom_ops_have_fake_kernels_and_autograd_formulas(mg):
     """torch.ops.morgana_b200.*: shape / dtype propagation on meta tensors (no memory, no GPU) for every operator, and
     a backward pass traced through fake tensors (register_fake + register_autograd)."""
