@@ -8,8 +8,9 @@
 //
 //   * The (B*T, D) row space is cut into STAGES of 8 rows (8*D floats = 32*D bytes: 16-byte aligned for every D, and a
 //     whole number of rows, so thread t always sees column t).  One persistent CTA per half SM owns a contiguous range of
-//     stages chosen on the device so that every CTA moves the same number of bytes (cost 3 per valid row: two reads + one
-//     gradient write; 1 per padding row: the zero gradient).
+//     stages chosen on the device so that every CTA carries the same cost (6 per valid row -- two reads, one gradient write and
+//     the arithmetic --, 1 per padding row -- the zero gradient; 3 : 1, the ratio of the bytes, left the padding-heavy ranges
+//     early: measured).
 //   * Warp roles.  A producer lane keeps a ring of stages in flight with cp.async.bulk global->shared (TMA engine, SASS
 //     UBLKCP) on "full" mbarriers and refills a slot as soon as the consumer warps have arrived on its "empty" mbarrier -- no
 //     CTA-wide barrier inside the stream, the bytes in flight live in shared memory (ring x 12 KB per CTA).  Padding-only
