@@ -77,7 +77,14 @@ struct GemmParams {
 
 // bias + activation on 32 accumulator columns; `bias32` points at this chunk's 32 biases in shared memory (zero-padded).
 // Sigmoid as ex2 + rcp (two MUFU ops): the layer's operands are bf16, so approximate-division accuracy (~1e-7) is ample.
-__device__ __forceinline__ void finish_columns(const uint32_t (&acc)[32], float (&v)[32], const float* bias32, int act) {
+// `coarse`: the result is about to be rounded to bf16 (8 bits of mantissa), so the sigmoid may be 0.5 * tanh(0.5 t) + 0.5 with the
+// hardware tanh (ONE MUFU op, relative error 2^-11) instead of ex2 + rcp (two).
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void finish_columns(const uint32_t (&acc)[32], float (&v)[32], const float* bias32, int act, bool coarse = false) {
 #pragma unroll
   for (int j = 0; j < 32; j += 4) {
     const float4 b4 = *reinterpret_cast<const float4*>(bias32 + j);
@@ -85,7 +92,7 @@ __device__ __forceinline__ void finish_columns(const uint32_t (&acc)[32], float 
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       float t = __uint_as_float(acc[j + q]) + b[q];
-      if (act == MG_ACT_SIGMOID) t = __fdividef(1.f, 1.f + __expf(-t));
+      if (act == MG_ACT_SIGMOID) t = coarse ? fmaf(0.5f, tanh_approx(0.5f * t), 0.5f) : __fdividef(1.f, 1.f + __expf(-t));
       v[j + q] = t;
     }
   }
@@ -269,7 +276,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           tmem_ld_32x32(taddr + static_cast<uint32_t>(c0), a0);
           if (second_half) tmem_ld_32x32(taddr + static_cast<uint32_t>(c0 + 32), a1);   // both loads in flight, one wait
           tmem_ld_wait();
-          finish_columns(a0, v, s_bias + n0 + c0, prm.act);
+          finish_columns(a0, v, s_bias + n0 + c0, prm.act, prm.y_is_bf16 != 0);
           if (!prm.y_is_bf16) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
@@ -278,7 +285,7 @@ linear_tcgen05_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
           } else {
             float v1[32];
             if (second_half) {
-              finish_columns(a1, v1, s_bias + n0 + c0 + 32, prm.act);
+              finish_columns(a1, v1, s_bias + n0 + c0 + 32, prm.act, true);
             } else {
 #pragma unroll
               for (int j = 0; j < 32; ++j) v1[j] = 0.f;
