@@ -181,7 +181,6 @@ __host__ __device__ __forceinline__ int64_t cost_to_stage(unsigned x, const Cost
   if (x == 0) return first_stage;
   if (x >= static_cast<unsigned>(s_pref[B])) return n_stages;
   int lo = 0, hi = B;                      // last b with pref[b] <= x
-#pragma unroll 1
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (static_cast<unsigned>(s_pref[mid]) <= x) lo = mid; else hi = mid; }
   const unsigned y = x - static_cast<unsigned>(s_pref[lo]), n = static_cast<unsigned>(s_nb[lo]), c = cm.cut(lo);
   const unsigned valid = n > c ? n - c : 0u, from = n > c ? n : c;
@@ -643,8 +642,10 @@ objective_stream_kernel(const __grid_constant__ StreamParams prm) {
         const float* stage_p = s_ring + static_cast<size_t>(slot) * 2 * stage_elems;
         if (kind == STAGE_PAD) {
           // a padding-only stage of the head start: it was loaded before anything was known; its gradient rows are zero
+          if (GRAD && active) {
 #pragma unroll 1
-          if (GRAD && active) for (int u = 0; u < kRows; ++u) __stcs(g + u * D, 0.f);
+            for (int u = 0; u < kRows; ++u) __stcs(g + u * D, 0.f);
+          }
         } else if (active && !(prm.debug & 1)) {
           if ((hot || served) && T >= kRows) {
             // a boundary stage is at most: valid rows of utterance b | padding | valid rows of utterance b + 1 | padding
