@@ -445,3 +445,42 @@ def test_path_replays_from_a_cuda_graph_on_a_side_stream(mg):
         torch.cuda.synchronize()
         assert torch.equal(g_frames, frames) and g_total.item() == total.item() and torch.equal(g_grad, grad)
     assert torch.equal(shadow, eager_shadow) and float(rmse.sum) == eager_sum
+
+
+def test_back_to_back_launches_overlap_without_racing(mg):
+    """The kernels of the path are launched with programmatic dependent launch: the CTAs of a launch may be resident while the launch
+    before it still runs.  300 launches of the step's kernels back to back, alternating between two batches of different size (so
+    grids, partitions and the shared reduction workspace change from launch to launch), no synchronisation in between: every result
+    must equal, bit for bit, what the same call returns when it runs alone."""
+    from morgana_b200 import workloads
+    from morgana_b200.fused import AcousticObjective
+    batches = []
+    for B, seed in ((48, 5), (17, 6)):
+        ling = workloads.linguistic_batch(batch_size=B, min_phones=20, max_phones=40, max_dur=20, seed=seed)
+        ac = workloads.acoustic_batch(ling['n_frames'], seed=seed)
+        batches.append({'lab': ling['lab'].cuda(), 'dur': ling['dur'].cuda(), 'mm': (ling['mmin'].cuda(), ling['mmax'].cuda()),
+                        'T': int(ling['n_frames'].max()), 'pred': ac['pred'].cuda(), 'target': ac['target'].cuda()})
+
+    def step(b, objective):
+        out, n = mg.utils.upsample_to_repetitions(b['lab'], b['dur'], normaliser=('minmax',) + b['mm'], max_len=b['T'], return_lengths=True)
+        loss, grad = objective(b['pred'], b['target'], n)
+        return out, loss, grad
+
+    alone = []
+    for b in batches:
+        torch.cuda.synchronize()
+        out, loss, grad = step(b, AcousticObjective())
+        torch.cuda.synchronize()
+        alone.append((out.clone(), loss.clone(), grad.clone()))
+    objectives = [AcousticObjective(), AcousticObjective()]
+    kept = []
+    for i in range(300):
+        k = i % 2 if i % 7 else 1 - i % 2            # mostly alternating, sometimes the same batch twice in a row
+        out, loss, grad = step(batches[k], objectives[k])
+        if i % 25 == 0 or i >= 296:
+            kept.append((k, out, loss, grad))
+    torch.cuda.synchronize()
+    for k, out, loss, grad in kept:
+        assert torch.equal(out, alone[k][0])
+        assert torch.equal(loss, alone[k][1]), (float(loss), float(alone[k][1]))
+        assert torch.equal(grad, alone[k][2])
